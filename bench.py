@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- particles/s per PIC step (scatter + push + gather) of the alpine LandauDamping hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a, through the C-ABI)
+  python bench.py --impl reference [...]                         the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1]): LandauDamping, 128^3 cells and 2^27 fp64 particles PER GPU
+(weak scaling: the mesh doubles along x, y, z as N = 2, 4, 8; FieldLayout decomposition), CIC,
+LeapFrog.  A "step" is one pass of the owned path: [fillHalo(E)] -> gather E + kick + kick + drift +
+periodic BC (one fused kernel) -> [particle update] -> cell sort -> rho = 0 -> scatter -> accumulateHalo.
+The FFT field solve is a non-owned stage: it is run once before the timed region to produce a
+self-consistent E and is timed separately (`solve_ms`).  Inputs (6.4 GB of particles) are far larger
+than the 126 MB L2, so no explicit flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particles/s per PIC step (scatter+push+gather), LandauDamping"
+UNIT = "particles/s"
+BYTES_PER_PARTICLE_STEP = 120  # gather+push 96 B + scatter 24 B (uniform scalar charge; 32 with a q array)
+BYTES_PER_CELL_STEP = 40      # rho zero + rho write + E read
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload(n_gpus):
+    """Global mesh for N GPUs (128^3 cells per GPU) and particles per GPU."""
+    dims = [128, 128, 128]
+    v, d = n_gpus, 0
+    while v > 1:
+        dims[d] *= 2
+        v //= 2
+        d = (d + 1) % 3
+    return tuple(dims), 1 << 27
+
+
+def cpu_baseline_run(n_sample, steps, warmup):
+    """The reference algorithm (oracle port, OpenMP, atomic scatter like Kokkos-OpenMP) on the host
+    cores: scatter + push + gather per step on a bounded sample of the workload (same 128^3 mesh)."""
+    import oracle
+    nr = (128, 128, 128)
+    L = 4 * np.pi
+    h = [L / k for k in nr]
+    m = oracle.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(42)
+    R = [rng.uniform(0, L, n_sample) for _ in range(3)]
+    P = [rng.normal(size=n_sample) for _ in range(3)]
+    E = [np.zeros(n_sample) for _ in range(3)]
+    ef = 0.05 * rng.normal(size=m.ext[0] * m.ext[1] * m.ext[2] * 3)
+    rho = oracle.field_zeros(m)
+    dt, q = 0.5 * h[0], -(L ** 3) / n_sample
+    for _ in range(warmup):
+        oracle.pic_step_nosolve(m, R, P, E, q, dt, ef, rho)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.pic_step_nosolve(m, R, P, E, q, dt, ef, rho)
+    dt_s = (time.perf_counter() - t0) / steps
+    return n_sample / dt_s, dt_s, oracle.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 1 << 24
+    value, sec, cores = cpu_baseline_run(n_sample, args.steps, max(1, args.warmup))
+    sample = (f"2^24 of the 2^27 particles on the same 128^3 mesh, {args.steps} steps; oracle port of the "
+              f"reference algorithm (OpenMP, atomic scatter), solve excluded")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "alpine LandauDamping 128^3 mesh, CIC, LeapFrog (bounded sample, CPU)",
+                   "sample_particles": n_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-particles", type=int, default=27, help="particles per GPU = 2^k (default: the metric's 2^27)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import ippl_b200 as ib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    ctx = ib.Context(local)
+    dev = ctx.device
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        uid = [ib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+
+    ng, n_local = workload(world)
+    n_local = 1 << args.log2_particles
+    L = 4 * np.pi  # Landau: rmax = 2*pi/kw, kw = 0.5 -- per 128 cells, so h stays 4*pi/128
+    h = [L / 128.0] * 3
+    origin = (0.0, 0.0, 0.0)
+    layout = ib.Layout(ng, world)
+    mesh = layout.mesh(rank, origin, h)
+    if world > 1:
+        ctx.set_layout(layout, origin, h)
+    dt = min(0.05, 0.5 * min(h))
+    n_total = n_local * world
+    Lg = [ng[d] * h[d] for d in range(3)]
+    q = -(Lg[0] * Lg[1] * Lg[2]) / n_total
+
+    # ---- synthetic particles, created on the device (uniform + Landau perturbation is irrelevant for
+    # throughput; positions uniform inside the rank's region, velocities N(0,1)) -------------------
+    cap = int(n_local * (1.25 if world > 1 else 1.0))
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + 100 * rank)
+    parts = ib.Particles(cap, dev, q=q)
+    scratch = ib.Particles(cap, dev)
+    reg = layout.regions(origin, h)[rank]
+    for d, k in enumerate("xyz"):
+        parts.arr[k][:n_local].uniform_(0.0, 1.0, generator=g).mul_(reg[3 + d] - reg[d]).add_(reg[d])
+        parts.arr[k][:n_local].clamp_(min=float(np.nextafter(reg[d], np.inf)), max=float(reg[3 + d]))
+    for k in ("px", "py", "pz"):
+        parts.arr[k][:n_local].normal_(0.0, 1.0, generator=g)
+    parts.n = n_local
+    off = ctx.offsets_buffer(mesh)
+    rho, ef = ctx.field(mesh), ctx.field(mesh, 3)
+
+    # ---- self-consistent E from one solve (single GPU); synthetic smooth E on N > 1 (solver is non-owned)
+    solve_ms = None
+    if world == 1:
+        ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho)
+        ctx.halo_accumulate_periodic(mesh, rho)
+        cell = h[0] * h[1] * h[2]
+        ctx.field_density(mesh, rho, cell, q * n_total / (Lg[0] * Lg[1] * Lg[2]))
+        sol = ib.Poisson(ctx, mesh)
+        sol.solve(rho, ef)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sol.solve(rho, ef)
+        e1.record()
+        torch.cuda.synchronize()
+        solve_ms = e0.elapsed_time(e1)
+        sol.close()
+    else:
+        ef.normal_(0.0, 0.02, generator=g)
+
+    def fill_e_halo():
+        if world > 1:
+            ctx.halo_exchange(ef, 3, "fill")
+        else:
+            ctx.halo_fill_periodic(mesh, ef, 3)
+
+    def step(first=False):
+        fill_e_halo()
+        push = ib.leapfrog_push(dt, kick2=0 if first else 1)
+        if world == 1:
+            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=True)
+        else:
+            ctx.gather_push(mesh, push, parts, ef)
+            ctx.update(parts)
+            ctx.sort_by_cell(mesh, parts, scratch, off)
+            parts.arr, scratch.arr = scratch.arr, parts.arr
+            ctx.field_fill(rho, 0.0)
+            ctx.scatter_sorted(mesh, parts.n, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, off, rho)
+            ctx.halo_exchange(rho, 1, "accumulate")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step(first=True)
+    for _ in range(args.warmup - 1):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    barrier()
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t0.elapsed_time(t1)
+    n_now = parts.n
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        c = torch.tensor([n_now], device=dev, dtype=torch.int64)
+        dist.all_reduce(c)
+        assert int(c[0]) == n_total, "particles lost in migration"
+    ms_per_step = ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing of the same step (CUDA events on the launching stream) -----------------
+    def timed(fn, reps=3):
+        best = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best.append(a.elapsed_time(b))
+        return float(np.mean(best))
+
+    kern = {}
+    push = ib.leapfrog_push(dt)
+    kern["gather_push"] = timed(lambda: ctx.gather_push(mesh, push, parts, ef))
+    if world > 1:
+        ctx.update(parts)
+
+    def do_sort():
+        ctx.sort_by_cell(mesh, parts, scratch, off)
+        parts.arr, scratch.arr = scratch.arr, parts.arr
+    kern["sort_by_cell"] = timed(do_sort)
+    kern["scatter_sorted"] = timed(lambda: ctx.scatter_sorted(mesh, parts.n, parts.arr["x"], parts.arr["y"],
+                                                              parts.arr["z"], q, off, rho))
+    kern["scatter_atomic"] = timed(lambda: ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho))
+    peak, peak_src = peaks()
+    dom = max(("gather_push", "sort_by_cell", "scatter_sorted"), key=lambda k: kern[k])
+    alg_bytes = {"gather_push": 96.0 * parts.n + 24.0 * mesh.cells,
+                 "scatter_sorted": 24.0 * parts.n + 8.0 * mesh.cells,
+                 "sort_by_cell": 0.0}
+    # the roofline object describes the gather+push kernel (the dominant ALGORITHMIC traffic, 96 of the
+    # 120 B/particle); the sort is pure overhead above the algorithmic bytes and is listed beside it
+    rk = "gather_push"
+    achieved = alg_bytes[rk] / (kern[rk] * 1e-3) / 1e9
+    step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * (mesh.nl[0] * mesh.nl[1] * mesh.nl[2])
+    step_achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"alpine LandauDamping {ng[0]}x{ng[1]}x{ng[2]} mesh, 2^{args.log2_particles} particles/GPU fp64, CIC, LeapFrog",
+                   "particles_total": n_total, "ppc": n_total / (ng[0] * ng[1] * ng[2]),
+                   "decomposition": f"FieldLayout {world} rank(s), 128^3 cells per GPU",
+                   "l2": "inputs (6.4 GB/GPU) exceed L2; no flush needed",
+                   "sort": "counting sort by cell every step", "solve": "excluded (non-owned cuFFT stage)",
+                   "charge": "uniform scalar q (24 B/particle scatter)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes[rk], "ms_per_launch": kern[rk]},
+        "step_roofline": {"bytes_per_particle": BYTES_PER_PARTICLE_STEP, "achieved": step_achieved, "peak": peak,
+                          "unit": "GB/s", "frac": step_achieved / peak},
+        "kernels_ms": kern, "dominant_kernel_by_time": dom, "solve_ms": solve_ms,
+    }
+
+    if rank == 0 and not args.no_cpu and world == 1:
+        v, sec, cores = cpu_baseline_run(1 << 23, 2, 1)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": "2^23 of the 2^27 particles on the same 128^3 mesh, 2 steps after 1 warm-up; "
+                                         "OpenMP restatement of the reference algorithm, solve excluded"}
+
+    # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), copies inside the timed region
+    if not args.no_e2e:
+        import ctypes as C
+        e2e_steps = max(1, min(args.steps, 2))
+        hostbuf = [torch.empty(n_local, dtype=torch.float64).pin_memory() for _ in range(6)]
+        for hb, k in zip(hostbuf, ib.Particles.NAMES):
+            hb.copy_(parts.arr[k][:n_local] if parts.n >= n_local else torch.zeros(n_local, dtype=torch.float64))
+        rho_host = torch.empty(mesh.cells, dtype=torch.float64).pin_memory()
+        arr = (C.c_void_p * 6)(*[hb.data_ptr() for hb in hostbuf])
+        if world == 1:
+            lib = ib.lib()
+            ps, ss = parts.struct(), scratch.struct()
+            pushs = ib.leapfrog_push(dt)
+
+            def e2e_step():
+                rc = lib.ipplb_pic_step_host(ctx._h, C.byref(mesh), C.byref(pushs), C.c_long(n_local), arr,
+                                             C.c_double(q), C.c_void_p(ef.data_ptr()), C.c_void_p(rho_host.data_ptr()),
+                                             C.byref(ps), C.byref(ss), C.c_void_p(off.data_ptr()),
+                                             C.c_void_p(rho.data_ptr()))
+                if rc:
+                    raise RuntimeError(lib.ipplb_last_error().decode())
+            e2e_step()
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            barrier()
+            e2e_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
+            out["e2e"] = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT,
+                          "h2d_bytes_per_step": 48 * n_local, "d2h_bytes_per_step": 48 * n_local + 8 * mesh.cells,
+                          "ms_per_step": e2e_ms, "steps": e2e_steps,
+                          "what": "ipplb_pic_step_host: pinned host R,P -> device, step, R,P + rho -> host"}
+        else:
+            out["e2e"] = None
+
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,229 @@
+/* ============================================================================
+ * ippl_b200.h -- C ABI of the B200-native particle-mesh hot path.
+ *
+ * Drop-in boundary for IPPL's PIC hot path.  The reference has no FFI: its
+ * boundary is the C++ template API (ippl::scatter / ippl::gather / ParticleBase::update /
+ * BareField::accumulateHalo / fillHalo).  The host-side C++ facade in include/ippl/ keeps that
+ * API and forwards to the entry points below; each entry point cites the reference interface it
+ * replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; ipplb_last_error() gives the text.
+ *    Nothing throws across this boundary.  There is NO CPU fallback: without a CUDA device every
+ *    compute entry point fails with IPPLB_ERR_NO_DEVICE.
+ *  - all array pointers are DEVICE pointers owned by the caller unless the name ends in _host.
+ *  - one ipplb_ctx per GPU / rank.  All work is enqueued on the context's stream; calls on one
+ *    context must not be concurrent.  ipplb_sync() waits for the stream (IpplTimings fences).
+ *  - particles are SoA fp64: x,y,z / px,py,pz / q (the reference stores AoS Vector<double,3>,
+ *    src/Particle/ParticleAttrib.h:33-277; the facade presents view(i)[d] over SoA).
+ *  - fields are ghosted, x fastest: idx = i + ex*(j + ey*k), ex = nl[0] + 2*nghost, ncomp doubles
+ *    per cell interleaved (rho: 1, E: 3 == Vector<double,3> per cell as in src/Field/BareField.h).
+ * ========================================================================== */
+#ifndef IPPL_B200_H
+#define IPPL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipplb_ctx ipplb_ctx;
+typedef struct ipplb_layout ipplb_layout;   /* host-only: rank boxes + neighbour tables */
+typedef struct ipplb_poisson ipplb_poisson; /* cuFFT periodic Poisson solver (non-owned stage) */
+
+enum {
+    IPPLB_OK = 0,
+    IPPLB_ERR_ARG = 1,
+    IPPLB_ERR_CUDA = 2,
+    IPPLB_ERR_NO_DEVICE = 3,
+    IPPLB_ERR_NCCL = 4,
+    IPPLB_ERR_CAPACITY = 5,
+    IPPLB_ERR_CUFFT = 6
+};
+
+/* Local view of the mesh: UniformCartesian (src/Meshes/UniformCartesian.h) + the rank's box of the
+ * FieldLayout (src/FieldLayout/FieldLayout.h, getLocalNDIndex) + BareField's ghost width. */
+typedef struct ipplb_mesh {
+    int ng[3];        /* global cells per dim */
+    int first[3];     /* first global cell of the local box */
+    int nl[3];        /* local cells per dim */
+    int nghost;       /* 1 in the reference (src/Field/BareField.hpp:100) */
+    double origin[3];
+    double h[3];
+} ipplb_mesh;
+
+/* SoA particle bundle handed to the fused / sorting entry points. q may be NULL when the charge is
+ * uniform (alpine: q = Q/totalP, demos/alpine/LandauDampingManager.h:246): q_scalar is used. */
+typedef struct ipplb_particles {
+    double* x; double* y; double* z;
+    double* px; double* py; double* pz;
+    double* q;
+    double q_scalar;
+    long n;         /* local particle count */
+    long capacity;  /* allocated elements per array */
+} ipplb_particles;
+
+/* Push variants fused into the gather. */
+enum { IPPLB_PUSH_LEAPFROG = 0, IPPLB_PUSH_PENNING = 1 };
+typedef struct ipplb_push {
+    int kind;
+    double dt;
+    /* which sub-steps run, in reference order (demos/alpine/LandauDampingManager.h:265-320):
+     *   gather E at R -> kick2 (end of step n) -> kick1 (start of step n+1) -> drift -> periodic BC */
+    int do_kick2, do_kick1, do_drift, do_bc;
+    /* Penning trap only (demos/alpine/PenningTrapManager.h:56-74, 242-333) */
+    double origin[3], length[3], V0, alpha, Bext, DrInv;
+} ipplb_push;
+
+const char* ipplb_last_error(void);
+const char* ipplb_version(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to enqueue on, or NULL to let the context create its own. */
+int ipplb_ctx_create(ipplb_ctx** out, int device, void* stream);
+int ipplb_ctx_destroy(ipplb_ctx* ctx);
+int ipplb_sync(ipplb_ctx* ctx);
+void* ipplb_ctx_stream(ipplb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long ipplb_launch_count(ipplb_ctx* ctx);
+
+/* ---- scatter / gather (replaces ParticleAttrib::scatter / gather) --------------------------- */
+/* ippl::scatter(attrib, f, pp[, policy, hash]) kernel part, src/Particle/ParticleAttrib.hpp:132-184 +
+ * src/Interpolation/CIC.hpp:26-45.  Deposits particles [begin,end) (hash == NULL) or hash[begin..end)
+ * into the ghosted field rho (+=).  Order-independent correctness; NO halo accumulate (chain
+ * ipplb_halo_accumulate_periodic / ipplb_halo_exchange like BareField::accumulateHalo does). */
+int ipplb_scatter_cic(ipplb_ctx* ctx, const ipplb_mesh* mesh, long begin, long end, const double* x,
+                      const double* y, const double* z, const double* q, double q_scalar,
+                      const int* hash, double* rho);
+/* Same deposit for particles that are sorted by cell with cell_offsets[ncells+1] (from
+ * ipplb_sort_by_cell): one thread per (cell, stencil node), register accumulation, one
+ * reduction per node -- the fast path. */
+int ipplb_scatter_cic_sorted(ipplb_ctx* ctx, const ipplb_mesh* mesh, long n, const double* x,
+                             const double* y, const double* z, const double* q, double q_scalar,
+                             const int* cell_offsets, double* rho);
+/* ippl::gather(attrib, f, pp, addToAttribute) kernel part, ParticleAttrib.hpp:193-246 + CIC.hpp:47-66.
+ * field: ghosted, ncomp (1 or 3) interleaved comps; out[c] arrays of n. NO halo fill. */
+int ipplb_gather_cic(ipplb_ctx* ctx, const ipplb_mesh* mesh, long n, const double* x, const double* y,
+                     const double* z, const double* field, int ncomp, double* const* out_host_ptrs,
+                     int add_to_attribute);
+/* Fused gather + push: E never round-trips through HBM (north_star).  efield: ghosted AoS-3 with
+ * valid halo.  Reads and rewrites x,y,z,px,py,pz in place. */
+int ipplb_gather_push(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push,
+                      ipplb_particles* p, const double* efield);
+
+/* ---- unfused particle ops (arbitrary driver expressions) ---------------------------------- */
+/* y[i] = y[i] + a * x[i]  (ParticleAttrib::operator=(Expression), ParticleAttrib.hpp:118-130, for
+ * P = P - 0.5*dt*E (a = -0.5*dt; identical rounding to P - c*E) and R = R + dt*P) */
+int ipplb_axpy(ipplb_ctx* ctx, long n, double a, const double* x, double* y);
+/* PeriodicBC per dimension, src/Particle/ParticleBC.h:73-76 via ParticleLayout::applyBC
+ * (src/Particle/ParticleLayout.hpp:34-74); lo/hi = global region bounds; mask bit d = dim d periodic */
+int ipplb_apply_periodic_bc(ipplb_ctx* ctx, long n, double* x, double* y, double* z,
+                            const double lo[3], const double hi[3], int mask);
+/* PenningTrap Kick1 / Kick2 as separate passes (PenningTrapManager.h:256-272, 313-333) */
+int ipplb_penning_kick(ipplb_ctx* ctx, int which, const ipplb_push* push, long n, const double* x,
+                       const double* y, const double* z, double* px, double* py, double* pz,
+                       const double* ex, const double* ey, const double* ez);
+
+/* ---- cell sort (B200-native; replaces the role of Interpolation/Binning.h bin_sort) -------- */
+/* Counting sort by cell key (integer, bit-exact: key from index = (int)((x-origin)*invdx + 0.5),
+ * the same truncation scatter/gather use).  Out of place: in -> out (arrays must not alias).
+ * cell_offsets (device, ncells+1 ints, cells of the local box grown by one layer on the upper side,
+ * see ipplb_sort_ncells) receives the start of every cell in the sorted order. */
+long ipplb_sort_ncells(const ipplb_mesh* mesh);
+int ipplb_sort_by_cell(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_particles* in,
+                       ipplb_particles* out, int* cell_offsets);
+
+/* ---- field ops ------------------------------------------------------------------------------ */
+int ipplb_field_fill(ipplb_ctx* ctx, double* field, long count, double value);
+/* BareField::sum over interior cells (src/Field/BareField.hpp:224-240); result written to *out_host
+ * after a stream sync (the reference's sum is host-synchronous too). */
+int ipplb_field_sum(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* field, double* out_host);
+/* AlpineManager::getDensity, demos/alpine/AlpineManager.h:225-245: v = v / cell_volume - shift on the
+ * interior (two IEEE ops in that order, like the reference's two expression kernels). */
+int ipplb_field_density(ipplb_ctx* ctx, const ipplb_mesh* mesh, double* field, double cell_volume,
+                        double shift);
+/* HaloCells::applyPeriodicSerialDim (src/Field/HaloCells.hpp:297-336): in-rank periodic wrap for the
+ * dims in serial_mask (bit d), cascading d = 0,1,2 like the reference.  accumulate: ghost += into the
+ * opposite interior layer; fill: ghost = opposite interior layer. */
+int ipplb_halo_accumulate_periodic(ipplb_ctx* ctx, const ipplb_mesh* mesh, double* field, int ncomp,
+                                   int serial_mask);
+int ipplb_halo_fill_periodic(ipplb_ctx* ctx, const ipplb_mesh* mesh, double* field, int ncomp,
+                             int serial_mask);
+/* Ex field energy + max norm of demos/alpine/LandauDampingManager.h:339-366 (interior cells, comp 0):
+ * out_host[0] = sum(Ex^2), out_host[1] = max|Ex| */
+int ipplb_field_ex_stats(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* efield,
+                         double* out_host);
+
+/* ---- periodic FFT Poisson solve (NON-OWNED stage, cuFFT; timed separately) ----------------- */
+/* FFTPeriodicPoissonSolver::solve with output_type GRAD, src/PoissonSolvers/
+ * FFTPeriodicPoissonSolver.hpp:53-169 (forward scaled 1/N, Nyquist and DC zeroed, unscaled inverse).
+ * Single-GPU: mesh must be the whole domain.  rho: ghosted scalar field (interior read; like the
+ * reference, rho's interior is clobbered).  efield: ghosted AoS-3, interior written (halo NOT filled). */
+int ipplb_poisson_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, ipplb_poisson** out);
+int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* efield);
+int ipplb_poisson_destroy(ipplb_poisson* s);
+
+/* ---- layout (host only; FieldLayout / Partitioner / RegionLayout) ---------------------------- */
+/* FieldLayout(comm, domain, decomp, isAllPeriodic, nghost) for `nranks` ranks,
+ * src/FieldLayout/FieldLayout.hpp:76-134 + src/Partition/Partitioner.hpp:15-123. */
+int ipplb_layout_create(ipplb_layout** out, const int ng[3], const int is_parallel[3], int nranks,
+                        int periodic, int nghost);
+/* FieldLayout::updateLayout(domains) (ORB repartition): boxes[nranks][6] = lo[3], hi[3] inclusive */
+int ipplb_layout_set_boxes(ipplb_layout* l, const int* boxes);
+int ipplb_layout_destroy(ipplb_layout* l);
+int ipplb_layout_nranks(const ipplb_layout* l);
+/* boxes_out[nranks][6] = lo[3], hi[3] inclusive global cell indices (getLocalNDIndex(rank)) */
+int ipplb_layout_boxes(const ipplb_layout* l, int* boxes_out);
+/* getNeighbors / getNeighborsSendRange / getNeighborsRecvRange of rank `rank`, flattened in component
+ * order: out[i][14] = comp, peer, send lo[3], send hi[3], recv lo[3], recv hi[3] (hi exclusive, local
+ * ghosted indices).  Returns the entry count (writes at most max_entries). */
+int ipplb_layout_neighbors(const ipplb_layout* l, int rank, int* out, int max_entries);
+/* RegionLayout regions: regions_out[nranks][6] = min[3], max[3] (src/Region/RegionLayout.hpp:68-98) */
+int ipplb_layout_regions(const ipplb_layout* l, const double origin[3], const double h[3],
+                         double* regions_out);
+/* fills *mesh for rank `rank` */
+int ipplb_layout_mesh(const ipplb_layout* l, int rank, const double origin[3], const double h[3],
+                      ipplb_mesh* mesh);
+
+/* ---- multi-GPU (NCCL over NVLink; one process per GPU) ---------------------------------------- */
+#define IPPLB_NCCL_ID_BYTES 128
+int ipplb_nccl_unique_id(char id_out[IPPLB_NCCL_ID_BYTES]);
+int ipplb_comm_init(ipplb_ctx* ctx, int rank, int nranks, const char id[IPPLB_NCCL_ID_BYTES]);
+/* binds the decomposition: builds the device-side halo plan (all 26 components batched) and the
+ * ownership tables used by ipplb_update. */
+int ipplb_ctx_set_layout(ipplb_ctx* ctx, const ipplb_layout* l, const double origin[3],
+                         const double h[3]);
+/* BareField::accumulateHalo / fillHalo (src/Field/BareField.hpp:152-172): inter-rank exchange of all
+ * neighbour components (HaloCells::exchangeBoundaries, src/Field/HaloCells.hpp:109-242) as ONE batched
+ * pack kernel, ONE grouped ncclSend/ncclRecv, ONE batched unpack kernel, then the in-rank periodic wrap
+ * for un-split dims.  mode: 0 fill, 1 accumulate. */
+int ipplb_halo_exchange(ipplb_ctx* ctx, double* field, int ncomp, int mode);
+/* ParticleSpatialLayout::update (src/Particle/ParticleSpatialLayout.hpp:115-314): periodic BC,
+ * ownership (bit-exact region test, :316-330, 372-395), count exchange, SoA migration, compaction.
+ * p->n is updated; arrays must have capacity for the arrivals (IPPLB_ERR_CAPACITY otherwise).
+ * sent_host / recv_host (may be NULL): per-rank counts [nranks] for parity checks. */
+int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv_host);
+/* sum over ranks of one double / one long (rho.sum(), particle count: AlpineManager.h:169, 212) */
+int ipplb_allreduce_sum_f64(ipplb_ctx* ctx, double* value_host);
+int ipplb_allreduce_sum_i64(ipplb_ctx* ctx, long* value_host);
+
+/* ---- whole-step conveniences used by bench.py / the facade ---------------------------------- */
+/* One PIC step of the metric (scatter + push + gather) on resident particles, single rank:
+ *   gather_push(E) -> sort (every sort_every steps) -> rho = 0 -> scatter -> periodic accumulate.
+ * The field solve is NOT included (non-owned, timed separately). */
+int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
+                   ipplb_particles* scratch, int* cell_offsets, const double* efield, double* rho,
+                   int do_sort);
+/* Same step through HOST buffers (bench.py's e2e): copies x..pz host->device, runs the step, copies
+ * x..pz and rho back.  Host pointers should be pinned. */
+int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, long n,
+                        double* const host_arrays[6], double q_scalar, const double* efield_dev,
+                        double* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
+                        int* cell_offsets, double* rho_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPPL_B200_H */

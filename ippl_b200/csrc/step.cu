@@ -1,0 +1,68 @@
+// step.cu -- whole-step conveniences on top of the kernels (bench.py, facade).
+#include "common.cuh"
+
+using namespace ipplb;
+
+extern "C" {
+
+int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
+                   ipplb_particles* scratch, int* cell_offsets, const double* efield, double* rho,
+                   int do_sort) {
+    IPPLB_REQUIRE(ctx && mesh && push && p && efield && rho, "pic_step: bad arguments");
+    int rc;
+    if ((rc = ipplb_gather_push(ctx, mesh, push, p, efield))) return rc;
+    const long cells = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
+                       (mesh->nl[2] + 2 * mesh->nghost);
+    if ((rc = ipplb_field_fill(ctx, rho, cells, 0.0))) return rc;
+    if (do_sort) {
+        IPPLB_REQUIRE(scratch && cell_offsets, "pic_step: sort needs scratch arrays and cell_offsets");
+        if ((rc = ipplb_sort_by_cell(ctx, mesh, p, scratch, cell_offsets))) return rc;
+        ipplb_particles t = *p;
+        *p                = *scratch;
+        *scratch          = t;
+        scratch->n        = 0;
+        if ((rc = ipplb_scatter_cic_sorted(ctx, mesh, p->n, p->x, p->y, p->z, p->q, p->q_scalar,
+                                           cell_offsets, rho)))
+            return rc;
+    } else {
+        if ((rc = ipplb_scatter_cic(ctx, mesh, 0, p->n, p->x, p->y, p->z, p->q, p->q_scalar, nullptr,
+                                    rho)))
+            return rc;
+    }
+    int mask = 0;
+    for (int d = 0; d < 3; ++d)
+        if (mesh->nl[d] == mesh->ng[d]) mask |= 1 << d;
+    return ipplb_halo_accumulate_periodic(ctx, mesh, rho, 1, mask);
+}
+
+int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, long n,
+                        double* const host_arrays[6], double q_scalar, const double* efield_dev,
+                        double* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
+                        int* cell_offsets, double* rho_dev) {
+    IPPLB_REQUIRE(ctx && mesh && push && host_arrays && dev && rho_dev, "pic_step_host: bad arguments");
+    IPPLB_REQUIRE(dev->capacity >= n, "pic_step_host: device capacity too small");
+    double* d[6] = {dev->x, dev->y, dev->z, dev->px, dev->py, dev->pz};
+    for (int a = 0; a < 6; ++a)
+        IPPLB_CUDA(cudaMemcpyAsync(d[a], host_arrays[a], sizeof(double) * (size_t)n,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    dev->n        = n;
+    dev->q        = nullptr;
+    dev->q_scalar = q_scalar;
+    int rc = ipplb_pic_step(ctx, mesh, push, dev, scratch, cell_offsets, efield_dev, rho_dev,
+                            scratch != nullptr);
+    if (rc) return rc;
+    double* d2[6] = {dev->x, dev->y, dev->z, dev->px, dev->py, dev->pz};
+    for (int a = 0; a < 6; ++a)
+        IPPLB_CUDA(cudaMemcpyAsync(host_arrays[a], d2[a], sizeof(double) * (size_t)n,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    if (rho_host) {
+        const long cells = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
+                           (mesh->nl[2] + 2 * mesh->nghost);
+        IPPLB_CUDA(cudaMemcpyAsync(rho_host, rho_dev, sizeof(double) * (size_t)cells,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IPPLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+"""ctypes bindings of include/ippl_b200.h + small torch-backed helpers."""
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class IpplbError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libippl_b200.so")
+
+
+def lib():
+    """Loads the product library.  Raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise IpplbError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(the CUDA extension is required; there is no CPU fallback)")
+        # torch bundles its own libnccl.so.2 (2.28); load it first so the library binds to that copy
+        # instead of pulling the older system NCCL in ahead of torch (same SONAME, one copy per process)
+        import torch  # noqa: F401
+        _LIB = C.CDLL(path)
+        _LIB.ipplb_last_error.restype = C.c_char_p
+        _LIB.ipplb_version.restype = C.c_char_p
+        _LIB.ipplb_ctx_stream.restype = C.c_void_p
+        _LIB.ipplb_launch_count.restype = C.c_long
+        _LIB.ipplb_sort_ncells.restype = C.c_long
+    return _LIB
+
+
+def exported_symbols():
+    """Every function name declared in include/ippl_b200.h."""
+    hdr = open(os.path.join(_HERE, "..", "include", "ippl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ipplb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def _check(rc):
+    if rc != 0:
+        raise IpplbError(f"ippl_b200 error {rc}: {lib().ipplb_last_error().decode()}")
+
+
+class Mesh(C.Structure):
+    _fields_ = [("ng", C.c_int * 3), ("first", C.c_int * 3), ("nl", C.c_int * 3), ("nghost", C.c_int),
+                ("origin", C.c_double * 3), ("h", C.c_double * 3)]
+
+    @staticmethod
+    def make(ng, origin, h, first=(0, 0, 0), nl=None, nghost=1):
+        m = Mesh()
+        nl = ng if nl is None else nl
+        for d in range(3):
+            m.ng[d], m.first[d], m.nl[d] = int(ng[d]), int(first[d]), int(nl[d])
+            m.origin[d], m.h[d] = float(origin[d]), float(h[d])
+        m.nghost = nghost
+        return m
+
+    @property
+    def ext(self):
+        return tuple(self.nl[d] + 2 * self.nghost for d in range(3))
+
+    @property
+    def cells(self):
+        e = self.ext
+        return e[0] * e[1] * e[2]
+
+    @property
+    def sort_ncells(self):
+        return (self.nl[0] + 1) * (self.nl[1] + 1) * (self.nl[2] + 1)
+
+    @property
+    def serial_mask(self):
+        return sum(1 << d for d in range(3) if self.nl[d] == self.ng[d])
+
+
+class _Particles(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p), ("px", C.c_void_p),
+                ("py", C.c_void_p), ("pz", C.c_void_p), ("q", C.c_void_p), ("q_scalar", C.c_double),
+                ("n", C.c_long), ("capacity", C.c_long)]
+
+
+class Push(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dt", C.c_double), ("do_kick2", C.c_int), ("do_kick1", C.c_int),
+                ("do_drift", C.c_int), ("do_bc", C.c_int), ("origin", C.c_double * 3),
+                ("length", C.c_double * 3), ("V0", C.c_double), ("alpha", C.c_double),
+                ("Bext", C.c_double), ("DrInv", C.c_double)]
+
+
+def leapfrog_push(dt, kick2=1, kick1=1, drift=1, bc=1):
+    p = Push()
+    p.kind, p.dt, p.do_kick2, p.do_kick1, p.do_drift, p.do_bc = 0, dt, kick2, kick1, drift, bc
+    return p
+
+
+def penning_push(dt, origin, length, Bext=5.0, kick2=1, kick1=1, drift=1, bc=1):
+    p = Push()
+    p.kind, p.dt, p.do_kick2, p.do_kick1, p.do_drift, p.do_bc = 1, dt, kick2, kick1, drift, bc
+    for d in range(3):
+        p.origin[d], p.length[d] = origin[d], length[d]
+    p.V0 = 30 * length[2]
+    p.alpha = -0.5 * dt
+    p.Bext = Bext
+    p.DrInv = 1.0 / (1 + (p.alpha * Bext) ** 2)
+    return p
+
+
+class Particles:
+    """SoA fp64 particle bundle in device memory (torch tensors own the storage)."""
+
+    NAMES = ("x", "y", "z", "px", "py", "pz")
+
+    def __init__(self, capacity, device, q=None, with_q_array=False):
+        import torch
+        self.capacity = int(capacity)
+        self.device = device
+        self.arr = {k: torch.empty(self.capacity, dtype=torch.float64, device=device) for k in self.NAMES}
+        self.qarr = torch.empty(self.capacity, dtype=torch.float64, device=device) if with_q_array else None
+        self.q_scalar = 0.0 if q is None else float(q)
+        self.n = 0
+
+    @staticmethod
+    def from_host(R, P, device, q=0.0, capacity=None):
+        import numpy as np
+        import torch
+        n = len(R[0])
+        qa = isinstance(q, np.ndarray)
+        p = Particles(capacity or n, device, None if qa else q, with_q_array=qa)
+        for k, a in zip(Particles.NAMES, list(R) + list(P)):
+            p.arr[k][:n].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        if qa:
+            p.qarr[:n].copy_(torch.from_numpy(np.ascontiguousarray(q)))
+        p.n = n
+        return p
+
+    def struct(self):
+        s = _Particles()
+        for k in self.NAMES:
+            setattr(s, k, self.arr[k].data_ptr())
+        s.q = self.qarr.data_ptr() if self.qarr is not None else None
+        s.q_scalar = self.q_scalar
+        s.n, s.capacity = self.n, self.capacity
+        return s
+
+    def adopt(self, s):
+        """Take over the pointers/count of a struct the library has updated (sort swaps buffers)."""
+        self.n = int(s.n)
+
+    def host(self, names=None):
+        names = names or self.NAMES
+        return [self.arr[k][: self.n].cpu().numpy() for k in names]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Context:
+    """One ipplb_ctx on one GPU, enqueuing on torch's current stream of that device."""
+
+    def __init__(self, device=0, use_torch_stream=True):
+        import torch
+        if not torch.cuda.is_available():
+            raise IpplbError("no CUDA device: ippl_b200 has no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self._h = C.c_void_p()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if use_torch_stream else None
+        _check(lib().ipplb_ctx_create(C.byref(self._h), device, stream))
+        self.rank, self.nranks = 0, 1
+
+    def close(self):
+        if self._h:
+            lib().ipplb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -----------------------------------------------------------------------------
+    def zeros(self, n):
+        return self.torch.zeros(int(n), dtype=self.torch.float64, device=self.device)
+
+    def field(self, mesh, ncomp=1):
+        return self.zeros(mesh.cells * ncomp)
+
+    def sync(self):
+        _check(lib().ipplb_sync(self._h))
+
+    @property
+    def launches(self):
+        return lib().ipplb_launch_count(self._h)
+
+    # -- kernels -----------------------------------------------------------------------------
+    def scatter(self, mesh, x, y, z, q, rho, begin=0, end=None, hash=None):
+        end = len(x) if end is None else end
+        qa = q if hasattr(q, "data_ptr") else None
+        qs = 0.0 if qa is not None else float(q)
+        _check(lib().ipplb_scatter_cic(self._h, C.byref(mesh), C.c_long(begin), C.c_long(end), _ptr(x),
+                                       _ptr(y), _ptr(z), _ptr(qa), C.c_double(qs), _ptr(hash), _ptr(rho)))
+
+    def scatter_sorted(self, mesh, n, x, y, z, q, offsets, rho):
+        qa = q if hasattr(q, "data_ptr") else None
+        qs = 0.0 if qa is not None else float(q)
+        _check(lib().ipplb_scatter_cic_sorted(self._h, C.byref(mesh), C.c_long(n), _ptr(x), _ptr(y), _ptr(z),
+                                              _ptr(qa), C.c_double(qs), _ptr(offsets), _ptr(rho)))
+
+    def gather(self, mesh, x, y, z, field, out, add=False):
+        ncomp = len(out)
+        arr = (C.c_void_p * 3)(*([o.data_ptr() for o in out] + [None] * (3 - ncomp)))
+        _check(lib().ipplb_gather_cic(self._h, C.byref(mesh), C.c_long(len(x)), _ptr(x), _ptr(y), _ptr(z),
+                                      _ptr(field), ncomp, arr, int(add)))
+
+    def gather_push(self, mesh, push, parts, efield):
+        s = parts.struct()
+        _check(lib().ipplb_gather_push(self._h, C.byref(mesh), C.byref(push), C.byref(s), _ptr(efield)))
+
+    def axpy(self, a, x, y, n=None):
+        n = len(x) if n is None else n
+        _check(lib().ipplb_axpy(self._h, C.c_long(n), C.c_double(a), _ptr(x), _ptr(y)))
+
+    def apply_periodic_bc(self, x, y, z, lo, hi, mask=7, n=None):
+        n = len(x) if n is None else n
+        _check(lib().ipplb_apply_periodic_bc(self._h, C.c_long(n), _ptr(x), _ptr(y), _ptr(z),
+                                             (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), mask))
+
+    def penning_kick(self, which, push, R, P, E, n=None):
+        n = len(R[0]) if n is None else n
+        _check(lib().ipplb_penning_kick(self._h, which, C.byref(push), C.c_long(n), _ptr(R[0]), _ptr(R[1]),
+                                        _ptr(R[2]), _ptr(P[0]), _ptr(P[1]), _ptr(P[2]), _ptr(E[0]),
+                                        _ptr(E[1]), _ptr(E[2])))
+
+    def sort_by_cell(self, mesh, src, dst, offsets):
+        s, d = src.struct(), dst.struct()
+        _check(lib().ipplb_sort_by_cell(self._h, C.byref(mesh), C.byref(s), C.byref(d), _ptr(offsets)))
+        dst.n, dst.q_scalar = src.n, src.q_scalar
+
+    def offsets_buffer(self, mesh):
+        return self.torch.zeros(mesh.sort_ncells + 1, dtype=self.torch.int32, device=self.device)
+
+    def field_fill(self, f, value=0.0):
+        _check(lib().ipplb_field_fill(self._h, _ptr(f), C.c_long(f.numel()), C.c_double(value)))
+
+    def field_sum(self, mesh, f):
+        out = C.c_double()
+        _check(lib().ipplb_field_sum(self._h, C.byref(mesh), _ptr(f), C.byref(out)))
+        return out.value
+
+    def field_ex_stats(self, mesh, ef):
+        out = (C.c_double * 2)()
+        _check(lib().ipplb_field_ex_stats(self._h, C.byref(mesh), _ptr(ef), out))
+        return out[0], out[1]
+
+    def field_density(self, mesh, f, cell_volume, shift):
+        _check(lib().ipplb_field_density(self._h, C.byref(mesh), _ptr(f), C.c_double(cell_volume),
+                                         C.c_double(shift)))
+
+    def halo_accumulate_periodic(self, mesh, f, ncomp=1, mask=None):
+        mask = mesh.serial_mask if mask is None else mask
+        _check(lib().ipplb_halo_accumulate_periodic(self._h, C.byref(mesh), _ptr(f), ncomp, mask))
+
+    def halo_fill_periodic(self, mesh, f, ncomp=1, mask=None):
+        mask = mesh.serial_mask if mask is None else mask
+        _check(lib().ipplb_halo_fill_periodic(self._h, C.byref(mesh), _ptr(f), ncomp, mask))
+
+    def pic_step(self, mesh, push, parts, scratch, offsets, efield, rho, do_sort=True):
+        """One metric step; when sorting, `parts` and `scratch` swap storage."""
+        s = parts.struct()
+        sc = scratch.struct() if scratch is not None else None
+        _check(lib().ipplb_pic_step(self._h, C.byref(mesh), C.byref(push), C.byref(s),
+                                    C.byref(sc) if sc is not None else None, _ptr(offsets), _ptr(efield),
+                                    _ptr(rho), int(do_sort)))
+        if do_sort:
+            parts.arr, scratch.arr = scratch.arr, parts.arr
+            parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
+        parts.n = int(s.n)
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_init(self, rank, nranks, id_bytes=None):
+        self.rank, self.nranks = rank, nranks
+        buf = C.create_string_buffer(bytes(id_bytes), 128) if id_bytes is not None else None
+        _check(lib().ipplb_comm_init(self._h, rank, nranks, buf))
+
+    def set_layout(self, layout, origin, h):
+        _check(lib().ipplb_ctx_set_layout(self._h, layout._h, (C.c_double * 3)(*origin), (C.c_double * 3)(*h)))
+
+    def halo_exchange(self, f, ncomp, mode):
+        _check(lib().ipplb_halo_exchange(self._h, _ptr(f), ncomp, 0 if mode == "fill" else 1))
+
+    def update(self, parts):
+        s = parts.struct()
+        sent = (C.c_long * self.nranks)()
+        recv = (C.c_long * self.nranks)()
+        _check(lib().ipplb_update(self._h, C.byref(s), sent, recv))
+        parts.n = int(s.n)
+        return list(sent), list(recv)
+
+    def allreduce_sum(self, v):
+        if isinstance(v, int):
+            c = C.c_long(v)
+            _check(lib().ipplb_allreduce_sum_i64(self._h, C.byref(c)))
+        else:
+            c = C.c_double(v)
+            _check(lib().ipplb_allreduce_sum_f64(self._h, C.byref(c)))
+        return c.value
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().ipplb_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Poisson:
+    def __init__(self, ctx, mesh):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        _check(lib().ipplb_poisson_create(ctx._h, C.byref(mesh), C.byref(self._h)))
+
+    def solve(self, rho, efield):
+        _check(lib().ipplb_poisson_solve(self._h, _ptr(rho), _ptr(efield)))
+
+    def close(self):
+        if self._h:
+            lib().ipplb_poisson_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Layout:
+    """Host-only FieldLayout mirror (works without a GPU)."""
+
+    def __init__(self, ng, nranks, parallel=(1, 1, 1), periodic=True, nghost=1):
+        self._h = C.c_void_p()
+        self.ng, self.nranks, self.nghost, self.periodic = tuple(ng), nranks, nghost, periodic
+        _check(lib().ipplb_layout_create(C.byref(self._h), (C.c_int * 3)(*ng), (C.c_int * 3)(*parallel), nranks,
+                                         int(periodic), nghost))
+
+    def close(self):
+        if self._h:
+            lib().ipplb_layout_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def boxes(self):
+        import numpy as np
+        out = np.zeros((self.nranks, 6), dtype=np.int32)
+        _check(lib().ipplb_layout_boxes(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_boxes(self, boxes):
+        import numpy as np
+        b = np.ascontiguousarray(boxes, dtype=np.int32)
+        _check(lib().ipplb_layout_set_boxes(self._h, b.ctypes.data_as(C.c_void_p)))
+
+    def neighbors(self, rank):
+        import numpy as np
+        out = np.zeros((512, 14), dtype=np.int32)
+        n = lib().ipplb_layout_neighbors(self._h, rank, out.ctypes.data_as(C.c_void_p), 512)
+        if n < 0 or n > 512:
+            raise IpplbError("layout_neighbors failed")
+        return out[:n].copy()
+
+    def regions(self, origin, h):
+        import numpy as np
+        out = np.zeros((self.nranks, 6), dtype=np.float64)
+        _check(lib().ipplb_layout_regions(self._h, (C.c_double * 3)(*origin), (C.c_double * 3)(*h),
+                                          out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def mesh(self, rank, origin, h):
+        m = Mesh()
+        _check(lib().ipplb_layout_mesh(self._h, rank, (C.c_double * 3)(*origin), (C.c_double * 3)(*h), C.byref(m)))
+        return m

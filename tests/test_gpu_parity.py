@@ -1,0 +1,437 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+Bit-exact for everything deterministic (gather, push, BC, keys, fill, periodic halo); relative L2
+<= 1e-12 for scatter sums (atomic-order tolerance, north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+from util import landau_positions, normal_velocities, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_SUM = 1e-12  # north_star: rho / E relative L2 <= 1e-12 in fp64
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import ippl_b200 as ib
+    c = ib.Context(0)
+    yield c
+    c.close()
+
+
+def _dev(ctx, a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    return t
+
+
+def _case(seed, ng=(12, 10, 8), n=20000, sub=False):
+    import ippl_b200 as ib
+    rng = np.random.default_rng(seed)
+    origin, h = (0.25, -1.0, 3.0), (0.5, 0.125, 1.5)
+    first, nl = ((6, 0, 4), (6, 10, 4)) if sub else ((0, 0, 0), ng)
+    lo = [origin[d] + first[d] * h[d] for d in range(3)]
+    x, y, z = [lo[d] + rng.uniform(0, nl[d] * h[d], n) for d in range(3)]
+    # edge cases the reference's tests hold: on the lower / upper corner, on faces, on centres
+    x[0], y[0], z[0] = lo
+    x[1], y[1], z[1] = [lo[d] + nl[d] * h[d] for d in range(3)]
+    x[2], y[2], z[2] = [lo[d] + 2.5 * h[d] for d in range(3)]
+    x[3], y[3], z[3] = [lo[d] + 3.0 * h[d] for d in range(3)]
+    q = rng.normal(size=n)
+    mo = oracle.Mesh.make(ng, origin, h, first=first, nl=nl)
+    mg = ib.Mesh.make(ng, origin, h, first=first, nl=nl)
+    return rng, mo, mg, x, y, z, q
+
+
+@pytest.mark.parametrize("sub", [False, True])
+def test_scatter_atomic_vs_oracle(ctx, sub):
+    rng, mo, mg, x, y, z, q = _case(1, sub=sub)
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, x, y, z, q, want)
+    rho = ctx.field(mg)
+    ctx.scatter(mg, _dev(ctx, x), _dev(ctx, y), _dev(ctx, z), _dev(ctx, q), rho)
+    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    # uniform scalar charge
+    want[:] = 0
+    oracle.scatter_cic(mo, x, y, z, -0.75, want)
+    rho.zero_()
+    ctx.scatter(mg, _dev(ctx, x), _dev(ctx, y), _dev(ctx, z), -0.75, rho)
+    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+
+
+def test_scatter_golden_vectors(ctx, golden):
+    """CUDA scatter/gather against the vectors produced by the REAL reference headers."""
+    import ippl_b200 as ib
+    for tag in ("full", "sub"):
+        g = golden
+        mg = ib.Mesh.make(g[f"cic_{tag}_ng"], g[f"cic_{tag}_origin"], g[f"cic_{tag}_h"],
+                          first=g[f"cic_{tag}_first"], nl=g[f"cic_{tag}_nl"])
+        x, y, z, q = (_dev(ctx, g[f"cic_{tag}_{k}"]) for k in "xyzq")
+        rho = ctx.field(mg)
+        ctx.scatter(mg, x, y, z, q, rho)
+        assert rel_l2(rho.cpu().numpy(), g[f"cic_{tag}_rho"]) <= TOL_SUM
+        out = [ctx.zeros(len(x)) for _ in range(3)]
+        ctx.gather(mg, x, y, z, _dev(ctx, g[f"cic_{tag}_ef"]), out)
+        for d, k in enumerate("xyz"):
+            assert np.array_equal(out[d].cpu().numpy(), g[f"cic_{tag}_g{k}"])  # bit-exact
+
+
+def test_scatter_range_and_hash(ctx):
+    # ParticleAttrib::scatter(policy, hash_array): subset + index remap (GatherScatterTest.cpp:158-340)
+    import torch
+    rng, mo, mg, x, y, z, q = _case(2)
+    n = len(x)
+    hash_ = rng.permutation(n).astype(np.int32)
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, x, y, z, q, want, begin=100, end=n // 2, hash=hash_)
+    rho = ctx.field(mg)
+    ctx.scatter(mg, _dev(ctx, x), _dev(ctx, y), _dev(ctx, z), _dev(ctx, q), rho, begin=100, end=n // 2,
+                hash=torch.from_numpy(hash_).to(ctx.device))
+    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    # empty range is a no-op
+    rho.zero_()
+    ctx.scatter(mg, _dev(ctx, x), _dev(ctx, y), _dev(ctx, z), _dev(ctx, q), rho, begin=5, end=5)
+    assert float(rho.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("ppc", [1, 8, 64])
+def test_sort_and_sorted_scatter(ctx, ppc):
+    import ippl_b200 as ib
+    ng = (16, 12, 10)
+    n = ng[0] * ng[1] * ng[2] * ppc
+    rng, mo, mg, x, y, z, q = _case(3 + ppc, ng=ng, n=n)
+    P = normal_velocities(n, seed=5)
+    src = ib.Particles.from_host((x, y, z), P, ctx.device, q=q)
+    dst = ib.Particles(n, ctx.device, with_q_array=True)
+    off = ctx.offsets_buffer(mg)
+    ctx.sort_by_cell(mg, src, dst, off)
+    offs = off.cpu().numpy()
+    sx, sy, sz, spx, spy, spz = dst.host()
+    sq = dst.qarr[:n].cpu().numpy()
+    # keys (integer, bit-exact) are non-decreasing and the offsets delimit them
+    def keys(xx, yy, zz):
+        k = []
+        for d, a in enumerate((xx, yy, zz)):
+            l = (a - mo.origin[d]) * (1.0 / mo.h[d]) + 0.5
+            k.append(l.astype(np.int32) - mo.first[d])
+        return k[0] + (mo.nl[0] + 1) * (k[1] + (mo.nl[1] + 1) * k[2])
+    ks = keys(sx, sy, sz)
+    assert np.all(np.diff(ks) >= 0)
+    assert offs[0] == 0 and offs[-1] == n and np.all(np.diff(offs) >= 0)
+    assert np.array_equal(np.bincount(ks, minlength=len(offs) - 1), np.diff(offs))
+    # the sort is a permutation of whole particles (all attributes travel together)
+    def canon(*cols):
+        a = np.stack(cols, axis=1)
+        return a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(canon(sx, sy, sz, spx, spy, spz, sq), canon(x, y, z, P[0], P[1], P[2], q))
+    # sorted scatter == oracle scatter of the same (sorted) particles; also == unsorted oracle to 1e-12
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, sx, sy, sz, sq, want)
+    rho = ctx.field(mg)
+    ctx.scatter_sorted(mg, n, dst.arr["x"], dst.arr["y"], dst.arr["z"], dst.qarr, off, rho)
+    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    want2 = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, x, y, z, q, want2)
+    assert np.max(np.abs(rho.cpu().numpy() - want2)) < 1e-12 * max(1.0, np.max(np.abs(want2)))
+
+
+def test_gather_bit_exact(ctx):
+    rng, mo, mg, x, y, z, q = _case(7, sub=True)
+    n = len(x)
+    ef = rng.normal(size=mg.cells * 3)
+    want = [np.zeros(n) for _ in range(3)]
+    oracle.gather_cic(mo, x, y, z, ef, want)
+    out = [ctx.zeros(n) for _ in range(3)]
+    dx, dy, dz, def_ = _dev(ctx, x), _dev(ctx, y), _dev(ctx, z), _dev(ctx, ef)
+    ctx.gather(mg, dx, dy, dz, def_, out)
+    for d in range(3):
+        assert np.array_equal(out[d].cpu().numpy(), want[d])
+    # addToAttribute
+    oracle.gather_cic(mo, x, y, z, ef, want, add=True)
+    ctx.gather(mg, dx, dy, dz, def_, out, add=True)
+    for d in range(3):
+        assert np.array_equal(out[d].cpu().numpy(), want[d])
+    # scalar field
+    f1 = rng.normal(size=mg.cells)
+    w1 = [np.zeros(n)]
+    oracle.gather_cic(mo, x, y, z, f1, w1)
+    o1 = [ctx.zeros(n)]
+    ctx.gather(mg, dx, dy, dz, _dev(ctx, f1), o1)
+    assert np.array_equal(o1[0].cpu().numpy(), w1[0])
+
+
+def _landau_setup(nr, n, seed=42):
+    import ippl_b200 as ib
+    L = 4 * np.pi
+    h = [L / k for k in nr]
+    mo = oracle.Mesh.make(nr, (0, 0, 0), h)
+    mg = ib.Mesh.make(nr, (0, 0, 0), h)
+    R = landau_positions(n, L, seed=seed)
+    P = normal_velocities(n, seed=seed + 1)
+    dt = min(0.05, 0.5 * min(h))
+    return mo, mg, R, P, dt, L
+
+
+def test_fused_gather_push_leapfrog_bit_exact(ctx):
+    import ippl_b200 as ib
+    n = 50000
+    mo, mg, R, P, dt, L = _landau_setup((16, 16, 16), n)
+    rng = np.random.default_rng(9)
+    ef = 0.3 * rng.normal(size=mg.cells * 3)
+    # oracle: gather, kick, kick, drift, BC as separate passes (reference order)
+    Ro, Po = [r.copy() for r in R], [p.copy() for p in P]
+    E = [np.zeros(n) for _ in range(3)]
+    oracle.gather_cic(mo, *Ro, ef, E)
+    for d in range(3):
+        oracle.kick(Po[d], E[d], 0.5 * dt)
+    for d in range(3):
+        oracle.kick(Po[d], E[d], 0.5 * dt)
+    for d in range(3):
+        oracle.drift(Ro[d], Po[d], dt)
+    for d in range(3):
+        oracle.periodic_bc(Ro[d], 0 * mo.h[d] + 0.0, mo.ng[d] * mo.h[d] + 0.0)
+    parts = ib.Particles.from_host(R, P, ctx.device, q=-1.0)
+    ctx.gather_push(mg, ib.leapfrog_push(dt), parts, _dev(ctx, ef))
+    got = parts.host()
+    for a, b in zip(got, Ro + Po):
+        assert np.array_equal(a, b)  # bit-exact
+    # unfused API path gives the same bits: gather -> axpy -> axpy -> axpy(R) -> BC
+    p2 = ib.Particles.from_host(R, P, ctx.device, q=-1.0)
+    Ed = [ctx.zeros(n) for _ in range(3)]
+    ctx.gather(mg, p2.arr["x"], p2.arr["y"], p2.arr["z"], _dev(ctx, ef), Ed)
+    for d, k in enumerate(("px", "py", "pz")):
+        ctx.axpy(-0.5 * dt, Ed[d], p2.arr[k])
+        ctx.axpy(-0.5 * dt, Ed[d], p2.arr[k])
+    for k, pk in zip("xyz", ("px", "py", "pz")):
+        ctx.axpy(dt, p2.arr[pk], p2.arr[k])
+    ctx.apply_periodic_bc(p2.arr["x"], p2.arr["y"], p2.arr["z"], [0.0] * 3,
+                          [mo.ng[d] * mo.h[d] + 0.0 for d in range(3)])
+    for a, b in zip(p2.host(), Ro + Po):
+        assert np.array_equal(a, b)
+
+
+def test_fused_gather_push_penning_bit_exact(ctx):
+    import ippl_b200 as ib
+    n = 40000
+    nr = (16, 16, 16)
+    Ld = 20.0
+    h = [Ld / k for k in nr]
+    mo = oracle.Mesh.make(nr, (0, 0, 0), h)
+    mg = ib.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(21)
+    R = [np.clip(rng.normal(Ld / 2, s * Ld, n), 0.0, np.nextafter(Ld, 0)) for s in (0.15, 0.05, 0.20)]
+    P = normal_velocities(n, seed=22)
+    dt = 0.5 * Ld / 2048
+    ef = rng.normal(size=mg.cells * 3)
+    pp = oracle.penning_params((0, 0, 0), (Ld, Ld, Ld), dt)
+    Ro, Po = [r.copy() for r in R], [p.copy() for p in P]
+    E = [np.zeros(n) for _ in range(3)]
+    oracle.gather_cic(mo, *Ro, ef, E)
+    oracle.penning_kick(2, pp, Ro, Po, E)
+    oracle.penning_kick(1, pp, Ro, Po, E)
+    for d in range(3):
+        oracle.drift(Ro[d], Po[d], dt)
+    for d in range(3):
+        oracle.periodic_bc(Ro[d], 0.0, nr[d] * h[d] + 0.0)
+    parts = ib.Particles.from_host(R, P, ctx.device, q=-1.0)
+    push = ib.penning_push(dt, (0, 0, 0), (Ld, Ld, Ld))
+    ctx.gather_push(mg, push, parts, _dev(ctx, ef))
+    for a, b in zip(parts.host(), Ro + Po):
+        assert np.array_equal(a, b)
+    # separate kick kernels
+    p2 = ib.Particles.from_host(R, P, ctx.device, q=-1.0)
+    Ed = [_dev(ctx, e) for e in E]
+    Rd = [p2.arr[k] for k in "xyz"]
+    Pd = [p2.arr[k] for k in ("px", "py", "pz")]
+    ctx.penning_kick(2, push, Rd, Pd, Ed)
+    ctx.penning_kick(1, push, Rd, Pd, Ed)
+    for a, b in zip(p2.host(("px", "py", "pz")), Po):
+        assert np.array_equal(a, b)
+
+
+def test_periodic_bc_golden(ctx, golden):
+    X = [_dev(ctx, a) for a in golden["bc_in"]]
+    ctx.apply_periodic_bc(X[0], X[1], X[2], list(golden["bc_lo"]), list(golden["bc_hi"]))
+    for d in range(3):
+        assert np.array_equal(X[d].cpu().numpy(), golden["bc_out"][d])
+
+
+@pytest.mark.parametrize("ncomp", [1, 3])
+def test_periodic_halo_bit_exact(ctx, ncomp):
+    import ippl_b200 as ib
+    ng = (6, 5, 7)
+    mo = oracle.Mesh.make(ng, (0, 0, 0), (1, 1, 1))
+    mg = ib.Mesh.make(ng, (0, 0, 0), (1, 1, 1))
+    rng = np.random.default_rng(4)
+    for mode in ("accumulate", "fill"):
+        for mask in (7, 5, 2):
+            f = rng.normal(size=mg.cells * ncomp)
+            want = f.copy()
+            oracle.halo_periodic(want, mo.ext, ncomp, 1, [(mask >> d) & 1 for d in range(3)], mode)
+            d = _dev(ctx, f)
+            if mode == "fill":
+                ctx.halo_fill_periodic(mg, d, ncomp, mask)
+            else:
+                ctx.halo_accumulate_periodic(mg, d, ncomp, mask)
+            assert np.array_equal(d.cpu().numpy(), want)
+
+
+def test_field_sum_and_density(ctx):
+    import ippl_b200 as ib
+    ng = (20, 12, 9)
+    mo = oracle.Mesh.make(ng, (0, 0, 0), (0.1, 0.2, 0.3))
+    mg = ib.Mesh.make(ng, (0, 0, 0), (0.1, 0.2, 0.3))
+    rng = np.random.default_rng(8)
+    f = rng.normal(size=mg.cells)
+    want = oracle.field_sum(f, mo.ext)
+    got = ctx.field_sum(mg, _dev(ctx, f))
+    assert abs(got - want) <= 1e-12 * np.sum(np.abs(f))
+    d = _dev(ctx, f)
+    ctx.field_density(mg, d, 0.006, -3.25)
+    oracle.density(f, mo.ext, 1, 0.006, -3.25)
+    assert np.array_equal(d.cpu().numpy(), f)
+
+
+def test_poisson_vs_numpy_oracle(ctx):
+    import ippl_b200 as ib
+    nr = (32, 16, 24)
+    L = 4 * np.pi
+    h = [L / k for k in nr]
+    mo = oracle.Mesh.make(nr, (0, 0, 0), h)
+    mg = ib.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(12)
+    rho = oracle.field_zeros(mo)
+    ri = rng.normal(size=(nr[2], nr[1], nr[0]))
+    ri -= ri.mean()
+    oracle.interior(rho, mo)[...] = ri
+    want = oracle.poisson_grad(ri, (0, 0, 0), h)
+    drho = _dev(ctx, rho)
+    ef = ctx.field(mg, 3)
+    sol = ib.Poisson(ctx, mg)
+    sol.solve(drho, ef)
+    got = oracle.interior(ef.cpu().numpy(), mo, 3)
+    assert rel_l2(got, want) <= 1e-12
+    sol.close()
+
+
+def test_landau_energy_history_vs_oracle(ctx):
+    """Config C1 of BASELINE.json scaled to the oracle's CPU budget: LandauDamping 32^3, 2^20 particles,
+    10 steps.  north_star tolerance: energy history <= 1e-10 relative, rho / E <= 1e-12 relative L2."""
+    import ippl_b200 as ib
+    nr, n, nsteps = (32, 32, 32), 1 << 20, 10
+    mo, mg, R, P, dt, L = _landau_setup(nr, n)
+    sim = oracle.LandauOracle(nr, R, P, parallel=False)
+    Q = sim.Q
+    q = Q / n
+    parts = ib.Particles.from_host(R, P, ctx.device, q=q)
+    scratch = ib.Particles(n, ctx.device)
+    off = ctx.offsets_buffer(mg)
+    rho, ef = ctx.field(mg), ctx.field(mg, 3)
+    sol = ib.Poisson(ctx, mg)
+    cell, size = sim.hr[0] * sim.hr[1] * sim.hr[2], sim.rmax ** 3
+    hist = []
+
+    def finish_scatter():
+        rel = abs((Q - ctx.field_sum(mg, rho)) / Q)
+        assert rel < 1e-10  # AlpineManager::checkChargeConservation
+        ctx.field_density(mg, rho, cell, Q / size)
+
+    def solve_and_dump(t):
+        sol.solve(rho, ef)
+        ctx.halo_fill_periodic(mg, ef, 3)
+        e2, emax = ctx.field_ex_stats(mg, ef)
+        hist.append((t, e2 * cell, emax))
+
+    # pre_run: scatter, solve, (gather is fused into the first push)
+    ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho)
+    ctx.halo_accumulate_periodic(mg, rho)
+    sim.pre_run()
+    finish_scatter()
+    solve_and_dump(0.0)
+    t = 0.0
+    for it in range(nsteps):
+        # step it: kick1 (E of previous solve), drift, BC, scatter, solve, then kick2 -- the fused kernel
+        # does [kick2 of step it-1] + kick1 + drift + BC; the very first call has no pending kick2.
+        push = ib.leapfrog_push(dt, kick2=1 if it > 0 else 0)
+        ctx.pic_step(mg, push, parts, scratch, off, ef, rho, do_sort=True)
+        sim.step()
+        finish_scatter()
+        t += dt
+        solve_and_dump(t)
+        assert rel_l2(oracle.interior(ef.cpu().numpy(), mo, 3), oracle.interior(sim.Ef, mo, 3)) <= 1e-9
+    hist, want = np.array(hist), np.array(sim.history)
+    assert np.max(np.abs(hist[:, 1] - want[:, 1]) / want[:, 1]) <= 1e-10
+    assert np.max(np.abs(hist[:, 2] - want[:, 2]) / want[:, 2]) <= 1e-10
+    sol.close()
+
+
+def test_step_rho_and_e_vs_oracle_tight(ctx):
+    """One full step on identical inputs: rho (after accumulate) and E (after solve) relative L2 <= 1e-12."""
+    import ippl_b200 as ib
+    nr, n = (16, 16, 16), 200000
+    mo, mg, R, P, dt, L = _landau_setup(nr, n, seed=77)
+    q = -(L ** 3) / n
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, *R, q, want)
+    oracle.halo_periodic(want, mo.ext, 1, 1, (1, 1, 1), "accumulate")
+    parts = ib.Particles.from_host(R, P, ctx.device, q=q)
+    rho = ctx.field(mg)
+    ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho)
+    ctx.halo_accumulate_periodic(mg, rho)
+    assert rel_l2(oracle.interior(rho.cpu().numpy(), mo), oracle.interior(want, mo)) <= TOL_SUM
+    cell = np.prod(mo.h[:])
+    oracle.density(want, mo.ext, 1, cell, q * n / L ** 3)
+    ctx.field_density(mg, rho, cell, q * n / L ** 3)
+    E = oracle.poisson_grad(oracle.interior(want, mo), (0, 0, 0), list(mo.h))
+    ef = ctx.field(mg, 3)
+    sol = ib.Poisson(ctx, mg)
+    sol.solve(rho, ef)
+    assert rel_l2(oracle.interior(ef.cpu().numpy(), mo, 3), E) <= 1e-12
+    sol.close()
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config C2 size (128^3, 2^27 particles): size-independent properties.
+    charge conservation to 1e-10 (reference abort threshold), sortedness, count conservation,
+    sorted-vs-atomic scatter agreement < 1e-12 (KernelGatherScatterTest.cpp:1083-1145)."""
+    import torch
+    import ippl_b200 as ib
+    nr, n = (128, 128, 128), 1 << 27
+    L = 4 * np.pi
+    h = [L / k for k in nr]
+    mg = ib.Mesh.make(nr, (0, 0, 0), h)
+    g = torch.Generator(device=ctx.device)
+    g.manual_seed(1234)
+    parts = ib.Particles(n, ctx.device, q=-(L ** 3) / n)
+    for k in "xyz":
+        parts.arr[k].uniform_(0.0, L, generator=g).clamp_(max=float(np.nextafter(L, 0)))
+    for k in ("px", "py", "pz"):
+        parts.arr[k].normal_(0.0, 1.0, generator=g)
+    parts.n = n
+    Q = parts.q_scalar * n
+    rho_a = ctx.field(mg)
+    ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], parts.q_scalar, rho_a)
+    ctx.halo_accumulate_periodic(mg, rho_a)
+    assert abs((Q - ctx.field_sum(mg, rho_a)) / Q) < 1e-10
+    scratch = ib.Particles(n, ctx.device)
+    off = ctx.offsets_buffer(mg)
+    ef = ctx.field(mg, 3)
+    ef.normal_(0.0, 0.05, generator=g)
+    ctx.halo_fill_periodic(mg, ef, 3)
+    rho = ctx.field(mg)
+    ksum0 = float(parts.arr["px"][:n].sum())
+    ctx.pic_step(mg, ib.leapfrog_push(0.5 * h[0], kick2=0, kick1=0), parts, scratch, off, ef, rho)
+    assert parts.n == n
+    offs = off.cpu()
+    assert int(offs[0]) == 0 and int(offs[-1]) == n and bool((offs[1:] >= offs[:-1]).all())
+    assert abs(float(parts.arr["px"][:n].sum()) - ksum0) < 1e-6 * n ** 0.5 + 1e-9 * abs(ksum0)  # momenta permuted only
+    assert abs((Q - ctx.field_sum(mg, rho)) / Q) < 1e-10
+    xs = parts.arr["x"][:n]
+    assert float(xs.min()) >= 0.0 and float(xs.max()) <= L
+    # atomic scatter of the same (sorted) particles agrees with the sorted kernel
+    rho_b = ctx.field(mg)
+    ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], parts.q_scalar, rho_b)
+    ctx.halo_accumulate_periodic(mg, rho_b)
+    num = float((rho - rho_b).norm())
+    assert num / float(rho_b.norm()) < 1e-12
