@@ -81,8 +81,10 @@ const char* ipplb_last_error(void);
 const char* ipplb_version(void);
 
 /* ---- context ---------------------------------------------------------------------------- */
-/* stream: a cudaStream_t to enqueue on, or NULL to let the context create its own. */
-int ipplb_ctx_create(ipplb_ctx** out, int device, void* stream);
+/* stream: the cudaStream_t to enqueue on (NULL = the CUDA default stream, which is what a host
+ * framework such as torch uses unless told otherwise).  create_stream != 0: ignore `stream` and let the
+ * context create and own a non-blocking stream. */
+int ipplb_ctx_create(ipplb_ctx** out, int device, void* stream, int create_stream);
 int ipplb_ctx_destroy(ipplb_ctx* ctx);
 int ipplb_sync(ipplb_ctx* ctx);
 void* ipplb_ctx_stream(ipplb_ctx* ctx);

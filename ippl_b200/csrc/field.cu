@@ -208,7 +208,7 @@ extern "C" {
 const char* ipplb_last_error(void) { return g_error.c_str(); }
 const char* ipplb_version(void) { return "ippl_b200 0.1 (sm_100a)"; }
 
-int ipplb_ctx_create(ipplb_ctx** out, int device, void* stream) {
+int ipplb_ctx_create(ipplb_ctx** out, int device, void* stream, int create_stream) {
     IPPLB_REQUIRE(out, "ctx_create: out is NULL");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -221,11 +221,11 @@ int ipplb_ctx_create(ipplb_ctx** out, int device, void* stream) {
     IPPLB_CUDA(cudaSetDevice(device));
     ipplb_ctx* ctx = new ipplb_ctx();
     ctx->device    = device;
-    if (stream) {
-        ctx->stream = (cudaStream_t)stream;
-    } else {
+    if (create_stream) {
         IPPLB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)stream;  // NULL = default stream
     }
     cudaDeviceProp prop;
     IPPLB_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -172,7 +172,7 @@ class Context:
         torch.cuda.set_device(self.device)
         self._h = C.c_void_p()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if use_torch_stream else None
-        _check(lib().ipplb_ctx_create(C.byref(self._h), device, stream))
+        _check(lib().ipplb_ctx_create(C.byref(self._h), device, stream, 0 if use_torch_stream else 1))
         self.rank, self.nranks = 0, 1
 
     def close(self):

@@ -22,7 +22,7 @@ def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     h = C.c_void_p()
-    rc = ib.lib().ipplb_ctx_create(C.byref(h), 0, None)
+    rc = ib.lib().ipplb_ctx_create(C.byref(h), 0, None, 0)
     assert rc == 3  # IPPLB_ERR_NO_DEVICE
     assert b"no CPU fallback" in ib.lib().ipplb_last_error()
     with pytest.raises(ib.IpplbError):
