@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-particles", type=int, default=27, help="particles per GPU = 2^k (default: the metric's 2^27)")
+    ap.add_argument("--mode", type=int, default=2, help="1: push + counting sort + sorted scatter; 2: fused two-pass step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -225,7 +226,7 @@ def main():
         fill_e_halo()
         push = ib.leapfrog_push(dt, kick2=0 if first else 1)
         if world == 1:
-            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=True)
+            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=args.mode)
         else:
             ctx.gather_push(mesh, push, parts, ef)
             ctx.update(parts)
@@ -241,6 +242,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ctx.sort_by_cell(mesh, parts, scratch, off)   # initial cell sort (the fused step keeps the order)
+    parts.arr, scratch.arr = scratch.arr, parts.arr
     step(first=True)
     for _ in range(args.warmup - 1):
         step()

@@ -211,10 +211,27 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
 int ipplb_allreduce_sum_f64(ipplb_ctx* ctx, double* value_host);
 int ipplb_allreduce_sum_i64(ipplb_ctx* ctx, long* value_host);
 
+/* ---- fused PIC step (the B200-first path) ------------------------------------------------------- */
+/* Two passes over the particles instead of push + sort + scatter (see ippl_b200/csrc/fused.cu):
+ *   pass A: push (gather E, kick, kick, drift, BC) in registers, histogram of the NEW cell keys;
+ *   pass B: same push again, shared-memory binning by new cell, coalesced move into cell-sorted order,
+ *           charge deposit from the sorted shared-memory copy (rho += ; caller zeroes rho first).
+ * In: p cell-sorted for its first n_sorted particles with cell_offsets valid (from ipplb_sort_by_cell or a
+ * previous fused step); particles beyond n_sorted (migration arrivals) may be in any order.  Out: p and
+ * scratch swap storage, p is cell-sorted, cell_offsets updated, p->n = particles still inside the local
+ * box.  Particles that left the box (multi-GPU) are written to exit_buf[6][exit_cap] (x,y,z,px,py,pz) and
+ * counted in *n_exit_host; they are NOT deposited.  Uniform charge only (p->q == NULL).
+ * Replaces, for one step: ParticleAttrib::operator= x3 (ParticleAttrib.hpp:118-130), applyBC
+ * (ParticleLayout.hpp:34-74), gather (:193-246) and scatter (:132-184). */
+int ipplb_step_fused(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
+                     ipplb_particles* scratch, int* cell_offsets, long n_sorted, const double* efield,
+                     double* rho, double* exit_buf, int exit_cap, int* n_exit_host);
+
 /* ---- whole-step conveniences used by bench.py / the facade ---------------------------------- */
 /* One PIC step of the metric (scatter + push + gather) on resident particles, single rank:
  *   gather_push(E) -> sort (every sort_every steps) -> rho = 0 -> scatter -> periodic accumulate.
- * The field solve is NOT included (non-owned, timed separately). */
+ * do_sort: 0 = no sort, atomic scatter; 1 = counting sort + sorted scatter; 2 = ipplb_step_fused (p must
+ * already be cell-sorted with cell_offsets valid).  The field solve is NOT included (non-owned). */
 int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
                    ipplb_particles* scratch, int* cell_offsets, const double* efield, double* rho,
                    int do_sort);

@@ -52,16 +52,43 @@ __device__ __forceinline__ long cic_node(const MeshDev& m, const int a[3], int p
     return i + (long)m.ex * (j + (long)m.ey * k);
 }
 
-// cell key used by the sort: (index - first) per dim in [0, nl[d]] (a particle sitting exactly on
-// the upper region boundary has index == first + nl), x fastest.
+// Cell key used by the sort: c[d] = index[d] - first[d] in [0, nl[d]] (a particle sitting exactly on
+// the upper region boundary has index == first + nl).  Keys are TILE-MAJOR: the key space is cut into
+// 4x4x4-cell tiles, key = tile_id * 64 + cell_in_tile (x fastest inside the tile and across tiles), so
+// any run of consecutive sorted particles is spatially compact in 3-D (what the fused push/move/deposit
+// kernel needs for its shared-memory window).
+constexpr int TILE = 4;
+constexpr int TILE_CELLS = TILE * TILE * TILE;
+
+__host__ __device__ __forceinline__ int tiles_along(int nl) { return (nl + 1 + TILE - 1) / TILE; }
+
+__device__ __forceinline__ int cell_key_c(const MeshDev& m, int cx, int cy, int cz) {
+    const int ntx = tiles_along(m.nl[0]), nty = tiles_along(m.nl[1]);
+    const int tile = (cx >> 2) + ntx * ((cy >> 2) + nty * (cz >> 2));
+    return tile * TILE_CELLS + ((cz & 3) << 4) + ((cy & 3) << 2) + (cx & 3);
+}
+
 __device__ __forceinline__ int cell_key(const MeshDev& m, const int a[3]) {
-    int cx = a[0] - m.nghost, cy = a[1] - m.nghost, cz = a[2] - m.nghost;
-    return cx + (m.nl[0] + 1) * (cy + (m.nl[1] + 1) * cz);
+    return cell_key_c(m, a[0] - m.nghost, a[1] - m.nghost, a[2] - m.nghost);
+}
+
+// inverse: key -> args (ghosted local index of the cell's upper node)
+__device__ __forceinline__ void key_to_args(const MeshDev& m, int key, int a[3]) {
+    const int ntx = tiles_along(m.nl[0]), nty = tiles_along(m.nl[1]);
+    const int tile = key >> 6, in = key & 63;
+    const int tx = tile % ntx, ty = (tile / ntx) % nty, tz = tile / (ntx * nty);
+    a[0] = tx * TILE + (in & 3) + m.nghost;
+    a[1] = ty * TILE + ((in >> 2) & 3) + m.nghost;
+    a[2] = tz * TILE + (in >> 4) + m.nghost;
 }
 
 // PeriodicBC::operator(), src/Particle/ParticleBC.h:73-76
 __device__ __forceinline__ double periodic_wrap(double v, double extent, double middle) {
-    double t = __ddiv_rn(dmul(dsub(v, middle), 2.0), extent);
+    const double num = dmul(dsub(v, middle), 2.0);
+    // |num| < extent  =>  |num/extent| < 1 after correct rounding  =>  (int) = 0  =>  v - extent*0 == v:
+    // skip the fp64 division for particles that stay inside (bit-identical result)
+    if (fabs(num) < extent) return v;
+    const double t = __ddiv_rn(num, extent);
     return dsub(v, dmul(extent, (double)__double2int_rz(t)));
 }
 

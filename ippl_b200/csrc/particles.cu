@@ -4,7 +4,7 @@
 // All kernels are HBM-bound streaming kernels; no tensor cores (nothing here is a contraction).
 #include <cub/device/device_scan.cuh>
 
-#include "cic.cuh"
+#include "push.cuh"
 
 namespace ipplb {
 
@@ -121,36 +121,10 @@ scatter_sorted_kernel(MeshDev m, int ncells, const double* __restrict__ x,
             __syncthreads();
         }
         if (me > mb) {
-            // key -> (cx,cy,cz) in [0,nl]; args = c + nghost
-            const int k0 = m.nl[0] + 1, k1 = m.nl[1] + 1;
             int a[3];
-            a[0] = cell % k0 + m.nghost;
-            a[1] = (cell / k0) % k1 + m.nghost;
-            a[2] = cell / (k0 * k1) + m.nghost;
+            key_to_args(m, cell, a);
             atomicAdd(&rho[cic_node(m, a, node)], acc);
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Gather (API-faithful): E_p = sum_p w_p * F(node_p), right fold like CIC.hpp:63-65.
-// ------------------------------------------------------------------------------------------------
-template <int NCOMP>
-__device__ __forceinline__ void gather_point(const MeshDev& m, const Cic& c,
-                                             const double* __restrict__ f, double out[NCOMP]) {
-    double w[8];
-    long id[8];
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        w[p]  = cic_weight(c.whi, p);
-        id[p] = cic_node(m, c.a, p) * NCOMP;
-    }
-#pragma unroll
-    for (int d = 0; d < NCOMP; ++d) {
-        double acc = dmul(w[7], __ldg(&f[id[7] + d]));
-#pragma unroll
-        for (int p = 6; p >= 0; --p) acc = dadd(dmul(w[p], __ldg(&f[id[p] + d])), acc);
-        out[d] = acc;
     }
 }
 
@@ -176,60 +150,6 @@ gather_kernel(MeshDev m, long n, const double* __restrict__ x, const double* __r
 //   leapfrog: P = P - c*E (kick2), P = P - c*E (kick1), R = R + dt*P, wrap     (c = 0.5*dt)
 //   penning : Kick2, Kick1 of PenningTrapManager.h:313-333 / 256-272, drift, wrap
 // ------------------------------------------------------------------------------------------------
-struct PushDev {
-    int kind, do_kick2, do_kick1, do_drift, do_bc;
-    double dt, c;          // c = 0.5*dt
-    double lo[3], ext[3], mid[3];  // periodic BC constants (ParticleBC.h:43-52)
-    double p_origin[3], p_half_len[3], cxy, cz, alpha, Bext, DrInv, aB;  // penning
-};
-
-__device__ __forceinline__ void penning_field(const PushDev& P, double x, double y, double z,
-                                              const double E[3], double Ee[3]) {
-    // Eext_x = -(x - origin - 0.5*length) * (V0 / (2 * length_z^2)), etc.; then += E
-    Ee[0] = dadd(dmul(-dsub(dsub(x, P.p_origin[0]), P.p_half_len[0]), P.cxy), E[0]);
-    Ee[1] = dadd(dmul(-dsub(dsub(y, P.p_origin[1]), P.p_half_len[1]), P.cxy), E[1]);
-    Ee[2] = dadd(dmul(dsub(dsub(z, P.p_origin[2]), P.p_half_len[2]), P.cz), E[2]);
-}
-
-__device__ __forceinline__ void push_particle(const PushDev& P, double r[3], double p[3],
-                                              const double E[3]) {
-    if (P.kind == IPPLB_PUSH_LEAPFROG) {
-        if (P.do_kick2) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) p[d] = dsub(p[d], dmul(P.c, E[d]));
-        }
-        if (P.do_kick1) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) p[d] = dsub(p[d], dmul(P.c, E[d]));
-        }
-    } else {
-        double Ee[3];
-        penning_field(P, r[0], r[1], r[2], E, Ee);
-        const double a = P.alpha, B = P.Bext;
-        if (P.do_kick2) {
-            // P0 = DrInv * (P0 + a * (Ex + P1*B + a*B*Ey));  a*B*Ey parses as (a*B)*Ey
-            p[0] = dmul(P.DrInv,
-                        dadd(p[0], dmul(a, dadd(dadd(Ee[0], dmul(p[1], B)), dmul(P.aB, Ee[1])))));
-            p[1] = dmul(P.DrInv,
-                        dadd(p[1], dmul(a, dsub(dsub(Ee[1], dmul(p[0], B)), dmul(P.aB, Ee[0])))));
-            p[2] = dadd(p[2], dmul(a, Ee[2]));
-        }
-        if (P.do_kick1) {
-            p[0] = dadd(p[0], dmul(a, dadd(Ee[0], dmul(p[1], B))));
-            p[1] = dadd(p[1], dmul(a, dsub(Ee[1], dmul(p[0], B))));
-            p[2] = dadd(p[2], dmul(a, Ee[2]));
-        }
-    }
-    if (P.do_drift) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) r[d] = dadd(r[d], dmul(P.dt, p[d]));
-    }
-    if (P.do_bc) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) r[d] = periodic_wrap(r[d], P.ext[d], P.mid[d]);
-    }
-}
-
 __global__ void __launch_bounds__(256)
 gather_push_kernel(MeshDev m, PushDev P, long n, double* __restrict__ x, double* __restrict__ y,
                    double* __restrict__ z, double* __restrict__ px, double* __restrict__ py,
@@ -354,40 +274,6 @@ static int grid_for(const ipplb_ctx* ctx, long n, int block, int per_sm) {
     return (int)(want < cap ? want : cap);
 }
 
-PushDev make_push_dev(const ipplb_mesh* mesh, const ipplb_push* push) {
-    PushDev P;
-    std::memset(&P, 0, sizeof(P));
-    P.kind     = push->kind;
-    P.do_kick2 = push->do_kick2;
-    P.do_kick1 = push->do_kick1;
-    P.do_drift = push->do_drift;
-    P.do_bc    = push->do_bc;
-    P.dt       = push->dt;
-    P.c        = 0.5 * push->dt;
-    for (int d = 0; d < 3; ++d) {
-        // region of the global domain: RegionLayout::convertNDIndex (min = 0*h + origin, max = N*h + origin)
-        const double lo = 0 * mesh->h[d] + mesh->origin[d];
-        const double hi = mesh->ng[d] * mesh->h[d] + mesh->origin[d];
-        P.lo[d]  = lo;
-        P.ext[d] = hi - lo;
-        P.mid[d] = (lo + hi) / 2;
-    }
-    if (push->kind == IPPLB_PUSH_PENNING) {
-        const double l2 = std::pow(push->length[2], 2);
-        for (int d = 0; d < 3; ++d) {
-            P.p_origin[d]   = push->origin[d];
-            P.p_half_len[d] = 0.5 * push->length[d];
-        }
-        P.cxy   = push->V0 / (2 * l2);
-        P.cz    = push->V0 / (l2);
-        P.alpha = push->alpha;
-        P.Bext  = push->Bext;
-        P.DrInv = push->DrInv;
-        P.aB    = push->alpha * push->Bext;
-    }
-    return P;
-}
-
 }  // namespace ipplb
 
 using namespace ipplb;
@@ -407,7 +293,7 @@ int ipplb_scatter_cic(ipplb_ctx* ctx, const ipplb_mesh* mesh, long begin, long e
 }
 
 long ipplb_sort_ncells(const ipplb_mesh* mesh) {
-    return (long)(mesh->nl[0] + 1) * (mesh->nl[1] + 1) * (mesh->nl[2] + 1);
+    return (long)tiles_along(mesh->nl[0]) * tiles_along(mesh->nl[1]) * tiles_along(mesh->nl[2]) * TILE_CELLS;
 }
 
 int ipplb_scatter_cic_sorted(ipplb_ctx* ctx, const ipplb_mesh* mesh, long n, const double* x,

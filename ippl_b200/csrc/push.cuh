@@ -1,0 +1,119 @@
+// push.cuh -- gather stencil + particle push device functions shared by the kernels.
+#pragma once
+#include <cmath>
+
+#include "cic.cuh"
+
+namespace ipplb {
+
+// ------------------------------------------------------------------------------------------------
+// Gather (API-faithful): E_p = sum_p w_p * F(node_p), right fold like CIC.hpp:63-65.
+// ------------------------------------------------------------------------------------------------
+template <int NCOMP>
+__device__ __forceinline__ void gather_point(const MeshDev& m, const Cic& c,
+                                             const double* __restrict__ f, double out[NCOMP]) {
+    double w[8];
+    long id[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        w[p]  = cic_weight(c.whi, p);
+        id[p] = cic_node(m, c.a, p) * NCOMP;
+    }
+#pragma unroll
+    for (int d = 0; d < NCOMP; ++d) {
+        double acc = dmul(w[7], __ldg(&f[id[7] + d]));
+#pragma unroll
+        for (int p = 6; p >= 0; --p) acc = dadd(dmul(w[p], __ldg(&f[id[p] + d])), acc);
+        out[d] = acc;
+    }
+}
+
+struct PushDev {
+    int kind, do_kick2, do_kick1, do_drift, do_bc;
+    double dt, c;          // c = 0.5*dt
+    double lo[3], ext[3], mid[3];  // periodic BC constants (ParticleBC.h:43-52)
+    double p_origin[3], p_half_len[3], cxy, cz, alpha, Bext, DrInv, aB;  // penning
+};
+
+__device__ __forceinline__ void penning_field(const PushDev& P, double x, double y, double z,
+                                              const double E[3], double Ee[3]) {
+    // Eext_x = -(x - origin - 0.5*length) * (V0 / (2 * length_z^2)), etc.; then += E
+    Ee[0] = dadd(dmul(-dsub(dsub(x, P.p_origin[0]), P.p_half_len[0]), P.cxy), E[0]);
+    Ee[1] = dadd(dmul(-dsub(dsub(y, P.p_origin[1]), P.p_half_len[1]), P.cxy), E[1]);
+    Ee[2] = dadd(dmul(dsub(dsub(z, P.p_origin[2]), P.p_half_len[2]), P.cz), E[2]);
+}
+
+__device__ __forceinline__ void push_particle(const PushDev& P, double r[3], double p[3],
+                                              const double E[3]) {
+    if (P.kind == IPPLB_PUSH_LEAPFROG) {
+        if (P.do_kick2) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) p[d] = dsub(p[d], dmul(P.c, E[d]));
+        }
+        if (P.do_kick1) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) p[d] = dsub(p[d], dmul(P.c, E[d]));
+        }
+    } else {
+        double Ee[3];
+        penning_field(P, r[0], r[1], r[2], E, Ee);
+        const double a = P.alpha, B = P.Bext;
+        if (P.do_kick2) {
+            // P0 = DrInv * (P0 + a * (Ex + P1*B + a*B*Ey));  a*B*Ey parses as (a*B)*Ey
+            p[0] = dmul(P.DrInv,
+                        dadd(p[0], dmul(a, dadd(dadd(Ee[0], dmul(p[1], B)), dmul(P.aB, Ee[1])))));
+            p[1] = dmul(P.DrInv,
+                        dadd(p[1], dmul(a, dsub(dsub(Ee[1], dmul(p[0], B)), dmul(P.aB, Ee[0])))));
+            p[2] = dadd(p[2], dmul(a, Ee[2]));
+        }
+        if (P.do_kick1) {
+            p[0] = dadd(p[0], dmul(a, dadd(Ee[0], dmul(p[1], B))));
+            p[1] = dadd(p[1], dmul(a, dsub(Ee[1], dmul(p[0], B))));
+            p[2] = dadd(p[2], dmul(a, Ee[2]));
+        }
+    }
+    if (P.do_drift) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) r[d] = dadd(r[d], dmul(P.dt, p[d]));
+    }
+    if (P.do_bc) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) r[d] = periodic_wrap(r[d], P.ext[d], P.mid[d]);
+    }
+}
+
+inline PushDev make_push_dev(const ipplb_mesh* mesh, const ipplb_push* push) {
+    PushDev P;
+    std::memset(&P, 0, sizeof(P));
+    P.kind     = push->kind;
+    P.do_kick2 = push->do_kick2;
+    P.do_kick1 = push->do_kick1;
+    P.do_drift = push->do_drift;
+    P.do_bc    = push->do_bc;
+    P.dt       = push->dt;
+    P.c        = 0.5 * push->dt;
+    for (int d = 0; d < 3; ++d) {
+        // region of the global domain: RegionLayout::convertNDIndex (min = 0*h + origin, max = N*h + origin)
+        const double lo = 0 * mesh->h[d] + mesh->origin[d];
+        const double hi = mesh->ng[d] * mesh->h[d] + mesh->origin[d];
+        P.lo[d]  = lo;
+        P.ext[d] = hi - lo;
+        P.mid[d] = (lo + hi) / 2;
+    }
+    if (push->kind == IPPLB_PUSH_PENNING) {
+        const double l2 = std::pow(push->length[2], 2);
+        for (int d = 0; d < 3; ++d) {
+            P.p_origin[d]   = push->origin[d];
+            P.p_half_len[d] = 0.5 * push->length[d];
+        }
+        P.cxy   = push->V0 / (2 * l2);
+        P.cz    = push->V0 / (l2);
+        P.alpha = push->alpha;
+        P.Bext  = push->Bext;
+        P.DrInv = push->DrInv;
+        P.aB    = push->alpha * push->Bext;
+    }
+    return P;
+}
+
+}  // namespace ipplb

@@ -10,6 +10,18 @@ int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* pus
                    int do_sort) {
     IPPLB_REQUIRE(ctx && mesh && push && p && efield && rho, "pic_step: bad arguments");
     int rc;
+    int mask = 0;
+    for (int d = 0; d < 3; ++d)
+        if (mesh->nl[d] == mesh->ng[d]) mask |= 1 << d;
+    if (do_sort == 2) {
+        const long cells2 = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
+                            (mesh->nl[2] + 2 * mesh->nghost);
+        if ((rc = ipplb_field_fill(ctx, rho, cells2, 0.0))) return rc;
+        if ((rc = ipplb_step_fused(ctx, mesh, push, p, scratch, cell_offsets, p->n, efield, rho, nullptr, 0,
+                                   nullptr)))
+            return rc;
+        return ipplb_halo_accumulate_periodic(ctx, mesh, rho, 1, mask);
+    }
     if ((rc = ipplb_gather_push(ctx, mesh, push, p, efield))) return rc;
     const long cells = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
                        (mesh->nl[2] + 2 * mesh->nghost);
@@ -29,9 +41,6 @@ int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* pus
                                     rho)))
             return rc;
     }
-    int mask = 0;
-    for (int d = 0; d < 3; ++d)
-        if (mesh->nl[d] == mesh->ng[d]) mask |= 1 << d;
     return ipplb_halo_accumulate_periodic(ctx, mesh, rho, 1, mask);
 }
 

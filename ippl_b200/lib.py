@@ -72,7 +72,8 @@ class Mesh(C.Structure):
 
     @property
     def sort_ncells(self):
-        return (self.nl[0] + 1) * (self.nl[1] + 1) * (self.nl[2] + 1)
+        """size of the (tile-major, padded) cell-key space: cell_offsets needs sort_ncells + 1 ints"""
+        return int(lib().ipplb_sort_ncells(C.byref(self)))
 
     @property
     def serial_mask(self):
@@ -272,8 +273,21 @@ class Context:
         mask = mesh.serial_mask if mask is None else mask
         _check(lib().ipplb_halo_fill_periodic(self._h, C.byref(mesh), _ptr(f), ncomp, mask))
 
+    def step_fused(self, mesh, push, parts, scratch, offsets, efield, rho, n_sorted=None, exit_buf=None):
+        """ipplb_step_fused; `parts` and `scratch` swap storage.  Returns the number of leavers."""
+        s, sc = parts.struct(), scratch.struct()
+        n_exit = C.c_int(0)
+        cap = 0 if exit_buf is None else exit_buf.numel() // 6
+        _check(lib().ipplb_step_fused(self._h, C.byref(mesh), C.byref(push), C.byref(s), C.byref(sc),
+                                      _ptr(offsets), C.c_long(parts.n if n_sorted is None else n_sorted),
+                                      _ptr(efield), _ptr(rho), _ptr(exit_buf), cap, C.byref(n_exit)))
+        parts.arr, scratch.arr = scratch.arr, parts.arr
+        parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
+        parts.n = int(s.n)
+        return n_exit.value
+
     def pic_step(self, mesh, push, parts, scratch, offsets, efield, rho, do_sort=True):
-        """One metric step; when sorting, `parts` and `scratch` swap storage."""
+        """One metric step; when sorting (1) or fused (2), `parts` and `scratch` swap storage."""
         s = parts.struct()
         sc = scratch.struct() if scratch is not None else None
         _check(lib().ipplb_pic_step(self._h, C.byref(mesh), C.byref(push), C.byref(s),

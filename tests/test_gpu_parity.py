@@ -115,7 +115,9 @@ def test_sort_and_sorted_scatter(ctx, ppc):
         for d, a in enumerate((xx, yy, zz)):
             l = (a - mo.origin[d]) * (1.0 / mo.h[d]) + 0.5
             k.append(l.astype(np.int32) - mo.first[d])
-        return k[0] + (mo.nl[0] + 1) * (k[1] + (mo.nl[1] + 1) * k[2])
+        ntx, nty = (mo.nl[0] + 4) // 4, (mo.nl[1] + 4) // 4   # tile-major keys (4x4x4 tiles)
+        tile = (k[0] >> 2) + ntx * ((k[1] >> 2) + nty * (k[2] >> 2))
+        return tile * 64 + ((k[2] & 3) << 4) + ((k[1] & 3) << 2) + (k[0] & 3)
     ks = keys(sx, sy, sz)
     assert np.all(np.diff(ks) >= 0)
     assert offs[0] == 0 and offs[-1] == n and np.all(np.diff(offs) >= 0)
@@ -315,7 +317,8 @@ def test_poisson_vs_numpy_oracle(ctx):
     sol.close()
 
 
-def test_landau_energy_history_vs_oracle(ctx):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_landau_energy_history_vs_oracle(ctx, mode):
     """Config C1 of BASELINE.json scaled to the oracle's CPU budget: LandauDamping 32^3, 2^20 particles,
     10 steps.  north_star tolerance: energy history <= 1e-10 relative, rho / E <= 1e-12 relative L2."""
     import ippl_b200 as ib
@@ -350,11 +353,14 @@ def test_landau_energy_history_vs_oracle(ctx):
     finish_scatter()
     solve_and_dump(0.0)
     t = 0.0
+    if mode == 2:  # the fused step wants cell-sorted input with valid offsets
+        ctx.sort_by_cell(mg, parts, scratch, off)
+        parts.arr, scratch.arr = scratch.arr, parts.arr
     for it in range(nsteps):
         # step it: kick1 (E of previous solve), drift, BC, scatter, solve, then kick2 -- the fused kernel
         # does [kick2 of step it-1] + kick1 + drift + BC; the very first call has no pending kick2.
         push = ib.leapfrog_push(dt, kick2=1 if it > 0 else 0)
-        ctx.pic_step(mg, push, parts, scratch, off, ef, rho, do_sort=True)
+        ctx.pic_step(mg, push, parts, scratch, off, ef, rho, do_sort=mode)
         sim.step()
         finish_scatter()
         t += dt
@@ -435,3 +441,105 @@ def test_full_size_properties(ctx):
     ctx.halo_accumulate_periodic(mg, rho_b)
     num = float((rho - rho_b).norm())
     assert num / float(rho_b.norm()) < 1e-12
+
+
+@pytest.mark.parametrize("ppc,kind", [(2, "leapfrog"), (40, "leapfrog"), (40, "penning")])
+def test_fused_step_vs_unfused_and_oracle(ctx, ppc, kind):
+    """ipplb_step_fused == (gather_push; sort; scatter) of the unfused kernels: same multiset of particles
+    bit for bit, cell-sorted output with valid offsets, rho equal to the oracle's to 1e-12."""
+    import ippl_b200 as ib
+    nr = (20, 16, 12)
+    n = nr[0] * nr[1] * nr[2] * ppc
+    Ld = 4 * np.pi
+    h = [Ld / 16] * 3
+    L = [nr[d] * h[d] for d in range(3)]
+    mo = oracle.Mesh.make(nr, (0, 0, 0), h)
+    mg = ib.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(100 + ppc)
+    R = [rng.uniform(0, L[d], n) for d in range(3)]
+    P = [3.0 * p for p in normal_velocities(n, seed=7)]   # fast particles: up to ~4 cells per step
+    dt = 0.5 * h[0]
+    ef = rng.normal(size=mg.cells * 3)
+    q = -0.37
+    push = ib.leapfrog_push(dt) if kind == "leapfrog" else ib.penning_push(dt, (0, 0, 0), L)
+    # reference: unfused kernels (bit-exact vs the oracle, tested above)
+    pa = ib.Particles.from_host(R, P, ctx.device, q=q)
+    ctx.gather_push(mg, push, pa, _dev(ctx, ef))
+    Ro = pa.host()
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], q, want)
+    # fused
+    pb = ib.Particles.from_host(R, P, ctx.device, q=q)
+    sc = ib.Particles(n, ctx.device)
+    off = ctx.offsets_buffer(mg)
+    ctx.sort_by_cell(mg, pb, sc, off)
+    pb.arr, sc.arr = sc.arr, pb.arr
+    rho = ctx.field(mg)
+    nexit = ctx.step_fused(mg, push, pb, sc, off, _dev(ctx, ef), rho)
+    assert nexit == 0 and pb.n == n
+    got = pb.host()
+
+    def canon(cols):
+        a = np.stack(cols, axis=1)
+        return a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(canon(got), canon(Ro))
+    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    # output is cell-sorted and the offsets delimit the cells
+    offs = off.cpu().numpy()
+    k = []
+    for d in range(3):
+        l = (got[d] - 0.0) * (1.0 / h[d]) + 0.5
+        k.append(l.astype(np.int32))
+    ntx, nty = (nr[0] + 4) // 4, (nr[1] + 4) // 4
+    keys = ((k[0] >> 2) + ntx * ((k[1] >> 2) + nty * (k[2] >> 2))) * 64 + ((k[2] & 3) << 4) + ((k[1] & 3) << 2) + (k[0] & 3)
+    assert np.all(np.diff(keys) >= 0)
+    assert offs[-1] == n and np.array_equal(np.bincount(keys, minlength=len(offs) - 1), np.diff(offs))
+    # a second fused step from the fused output (steady state) still matches
+    ctx.gather_push(mg, push, pa, _dev(ctx, ef))
+    Ro2 = pa.host()
+    want2 = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, Ro2[0], Ro2[1], Ro2[2], q, want2)
+    rho.zero_()
+    ctx.step_fused(mg, push, pb, sc, off, _dev(ctx, ef), rho)
+    assert np.array_equal(canon(pb.host()), canon(Ro2))
+    assert rel_l2(rho.cpu().numpy(), want2) <= TOL_SUM
+
+
+def test_fused_step_unsorted_input_and_tail(ctx):
+    """Correct for ANY input order: fully unsorted input (n_sorted = 0) and sorted + unsorted tail."""
+    import ippl_b200 as ib
+    nr = (16, 16, 16)
+    n = 60000
+    L = 4 * np.pi
+    h = [L / 16] * 3
+    mo, mg = oracle.Mesh.make(nr, (0, 0, 0), h), ib.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(5)
+    R = [rng.uniform(0, L, n) for _ in range(3)]
+    P = normal_velocities(n, seed=8)
+    ef = rng.normal(size=mg.cells * 3)
+    push = ib.leapfrog_push(0.05)
+    pa = ib.Particles.from_host(R, P, ctx.device, q=1.0)
+    ctx.gather_push(mg, push, pa, _dev(ctx, ef))
+    Ro = pa.host()
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], 1.0, want)
+
+    def canon(cols):
+        a = np.stack(cols, axis=1)
+        return a[np.lexsort(a.T[::-1])]
+    for n_sorted in (0, 40000):
+        pb = ib.Particles.from_host(R, P, ctx.device, q=1.0)
+        sc = ib.Particles(n, ctx.device)
+        off = ctx.offsets_buffer(mg)
+        if n_sorted:
+            # sort the first n_sorted particles only, leave the rest as an unsorted tail
+            head = ib.Particles.from_host([r[:n_sorted] for r in R], [p[:n_sorted] for p in P], ctx.device, q=1.0)
+            hs = ib.Particles(n_sorted, ctx.device)
+            ctx.sort_by_cell(mg, head, hs, off)
+            for k in ib.Particles.NAMES:
+                pb.arr[k][:n_sorted].copy_(hs.arr[k][:n_sorted])
+        rho = ctx.field(mg)
+        ctx.step_fused(mg, push, pb, sc, off, _dev(ctx, ef), rho, n_sorted=n_sorted)
+        assert pb.n == n
+        assert np.array_equal(canon(pb.host()), canon(Ro))
+        assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
