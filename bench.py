@@ -181,7 +181,7 @@ def main():
 
     # ---- synthetic particles, created on the device (uniform + Landau perturbation is irrelevant for
     # throughput; positions uniform inside the rank's region, velocities N(0,1)) -------------------
-    cap = int(n_local * (1.25 if world > 1 else 1.0))
+    cap = int(n_local * 1.25)  # bucket slack + tail of the fused store; migration head-room on N > 1
     g = torch.Generator(device=dev)
     g.manual_seed(42 + 100 * rank)
     parts = ib.Particles(cap, dev, q=q)
@@ -194,6 +194,7 @@ def main():
         parts.arr[k][:n_local].normal_(0.0, 1.0, generator=g)
     parts.n = n_local
     off = ctx.offsets_buffer(mesh)
+    bins = ib.Bins(ctx, mesh, cap) if (world == 1 and args.mode == 2) else None
     rho, ef = ctx.field(mesh), ctx.field(mesh, 3)
 
     # ---- self-consistent E from one solve (single GPU); synthetic smooth E on N > 1 (solver is non-owned)
@@ -226,7 +227,7 @@ def main():
         fill_e_halo()
         push = ib.leapfrog_push(dt, kick2=0 if first else 1)
         if world == 1:
-            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=args.mode)
+            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=args.mode, bins=bins)
         else:
             ctx.gather_push(mesh, push, parts, ef)
             ctx.update(parts)
@@ -242,7 +243,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx.sort_by_cell(mesh, parts, scratch, off)   # initial cell sort (the fused step keeps the order)
+    if bins is not None:
+        bins.build(parts, scratch)                # initial bucketing (the fused step keeps the particles bucketed)
+    else:
+        ctx.sort_by_cell(mesh, parts, scratch, off)
     parts.arr, scratch.arr = scratch.arr, parts.arr
     step(first=True)
     for _ in range(args.warmup - 1):
@@ -287,27 +291,43 @@ def main():
 
     kern = {}
     push = ib.leapfrog_push(dt)
-    kern["gather_push"] = timed(lambda: ctx.gather_push(mesh, push, parts, ef))
-    if world > 1:
-        ctx.update(parts)
-
-    def do_sort():
-        ctx.sort_by_cell(mesh, parts, scratch, off)
-        parts.arr, scratch.arr = scratch.arr, parts.arr
-    kern["sort_by_cell"] = timed(do_sort)
-    kern["scatter_sorted"] = timed(lambda: ctx.scatter_sorted(mesh, parts.n, parts.arr["x"], parts.arr["y"],
-                                                              parts.arr["z"], q, off, rho))
-    kern["scatter_atomic"] = timed(lambda: ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho))
     peak, peak_src = peaks()
-    dom = max(("gather_push", "sort_by_cell", "scatter_sorted"), key=lambda k: kern[k])
-    alg_bytes = {"gather_push": 96.0 * parts.n + 24.0 * mesh.cells,
-                 "scatter_sorted": 24.0 * parts.n + 8.0 * mesh.cells,
-                 "sort_by_cell": 0.0}
-    # the roofline object describes the gather+push kernel (the dominant ALGORITHMIC traffic, 96 of the
-    # 120 B/particle); the sort is pure overhead above the algorithmic bytes and is listed beside it
-    rk = "gather_push"
+    ncell_int = mesh.nl[0] * mesh.nl[1] * mesh.nl[2]
+    if bins is not None:
+        nloc, ntail, nexit, flags = bins.status()
+        assert nloc == n_local and nexit == 0 and (flags & 7) == 0, f"fused store lost particles: {bins.status()}"
+        kern["fused_step"] = timed(lambda: bins.step(push, parts, scratch, ef, rho), reps=5)
+        kern["rho_zero"] = timed(lambda: ctx.field_fill(rho, 0.0))
+        kern["halo_accumulate"] = timed(lambda: ctx.halo_accumulate_periodic(mesh, rho))
+        kern["halo_fill_E"] = timed(fill_e_halo)
+        rk = "fused_step"
+        # the fused kernel does all per-particle work of the step: SURVEY 8d algorithmic bytes, 120 B/particle
+        # (96 gather+push, 24 scatter with a uniform scalar charge) + E read and rho written once per cell
+        alg_bytes = {rk: float(BYTES_PER_PARTICLE_STEP) * n_local + 32.0 * ncell_int}
+        dom = rk
+        tail_frac = ntail / max(nloc, 1)
+    else:
+        kern["gather_push"] = timed(lambda: ctx.gather_push(mesh, push, parts, ef))
+        if world > 1:
+            ctx.update(parts)
+
+        def do_sort():
+            ctx.sort_by_cell(mesh, parts, scratch, off)
+            parts.arr, scratch.arr = scratch.arr, parts.arr
+        kern["sort_by_cell"] = timed(do_sort)
+        kern["scatter_sorted"] = timed(lambda: ctx.scatter_sorted(mesh, parts.n, parts.arr["x"], parts.arr["y"],
+                                                                  parts.arr["z"], q, off, rho))
+        kern["scatter_atomic"] = timed(lambda: ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho))
+        dom = max(("gather_push", "sort_by_cell", "scatter_sorted"), key=lambda k: kern[k])
+        alg_bytes = {"gather_push": 96.0 * parts.n + 24.0 * mesh.cells,
+                     "scatter_sorted": 24.0 * parts.n + 8.0 * mesh.cells,
+                     "sort_by_cell": 0.0}
+        # unfused path: the roofline object describes the gather+push kernel (96 of the 120 B/particle); the
+        # sort is pure overhead above the algorithmic bytes and is listed beside it
+        rk = "gather_push"
+        tail_frac = None
     achieved = alg_bytes[rk] / (kern[rk] * 1e-3) / 1e9
-    step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * (mesh.nl[0] * mesh.nl[1] * mesh.nl[2])
+    step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * ncell_int
     step_achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
 
     out = {
@@ -318,7 +338,9 @@ def main():
                    "particles_total": n_total, "ppc": n_total / (ng[0] * ng[1] * ng[2]),
                    "decomposition": f"FieldLayout {world} rank(s), 128^3 cells per GPU",
                    "l2": "inputs (6.4 GB/GPU) exceed L2; no flush needed",
-                   "sort": "counting sort by cell every step", "solve": "excluded (non-owned cuFFT stage)",
+                   "sort": ("none: single-pass fused step on per-tile buckets" if bins is not None
+                            else "counting sort by cell every step"),
+                   "tail_fraction": tail_frac, "solve": "excluded (non-owned cuFFT stage)",
                    "charge": "uniform scalar q (24 B/particle scatter)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -341,20 +363,23 @@ def main():
         import ctypes as C
         e2e_steps = max(1, min(args.steps, 2))
         hostbuf = [torch.empty(n_local, dtype=torch.float64).pin_memory() for _ in range(6)]
+        if bins is not None:   # contiguous copy of the bucketed particles
+            bins.compact(parts, scratch)
+            parts.arr, scratch.arr = scratch.arr, parts.arr
         for hb, k in zip(hostbuf, ib.Particles.NAMES):
-            hb.copy_(parts.arr[k][:n_local] if parts.n >= n_local else torch.zeros(n_local, dtype=torch.float64))
+            hb.copy_(parts.arr[k][:n_local])
         rho_host = torch.empty(mesh.cells, dtype=torch.float64).pin_memory()
         arr = (C.c_void_p * 6)(*[hb.data_ptr() for hb in hostbuf])
         if world == 1:
             lib = ib.lib()
+            ebins = bins if bins is not None else ib.Bins(ctx, mesh, cap)
             ps, ss = parts.struct(), scratch.struct()
             pushs = ib.leapfrog_push(dt)
 
             def e2e_step():
                 rc = lib.ipplb_pic_step_host(ctx._h, C.byref(mesh), C.byref(pushs), C.c_long(n_local), arr,
                                              C.c_double(q), C.c_void_p(ef.data_ptr()), C.c_void_p(rho_host.data_ptr()),
-                                             C.byref(ps), C.byref(ss), C.c_void_p(off.data_ptr()),
-                                             C.c_void_p(rho.data_ptr()))
+                                             C.byref(ps), C.byref(ss), ebins._h, C.c_void_p(rho.data_ptr()))
                 if rc:
                     raise RuntimeError(lib.ipplb_last_error().decode())
             e2e_step()
@@ -367,7 +392,7 @@ def main():
             out["e2e"] = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT,
                           "h2d_bytes_per_step": 48 * n_local, "d2h_bytes_per_step": 48 * n_local + 8 * mesh.cells,
                           "ms_per_step": e2e_ms, "steps": e2e_steps,
-                          "what": "ipplb_pic_step_host: pinned host R,P -> device, step, R,P + rho -> host"}
+                          "what": "ipplb_pic_step_host: pinned host R,P -> device, bucket, fused step, compact, R,P + rho -> host"}
         else:
             out["e2e"] = None
 

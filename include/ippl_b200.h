@@ -211,36 +211,72 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
 int ipplb_allreduce_sum_f64(ipplb_ctx* ctx, double* value_host);
 int ipplb_allreduce_sum_i64(ipplb_ctx* ctx, long* value_host);
 
-/* ---- fused PIC step (the B200-first path) ------------------------------------------------------- */
-/* Two passes over the particles instead of push + sort + scatter (see ippl_b200/csrc/fused.cu):
- *   pass A: push (gather E, kick, kick, drift, BC) in registers, histogram of the NEW cell keys;
- *   pass B: same push again, shared-memory binning by new cell, coalesced move into cell-sorted order,
- *           charge deposit from the sorted shared-memory copy (rho += ; caller zeroes rho first).
- * In: p cell-sorted for its first n_sorted particles with cell_offsets valid (from ipplb_sort_by_cell or a
- * previous fused step); particles beyond n_sorted (migration arrivals) may be in any order.  Out: p and
- * scratch swap storage, p is cell-sorted, cell_offsets updated, p->n = particles still inside the local
- * box.  Particles that left the box (multi-GPU) are written to exit_buf[6][exit_cap] (x,y,z,px,py,pz) and
- * counted in *n_exit_host; they are NOT deposited.  Uniform charge only (p->q == NULL).
+/* ---- cell-ordered particle store + fused single-pass PIC step (the B200-first path) ------------------ */
+/* ipplb_bins keeps the particles of one rank grouped in per-tile buckets (tile = 4x4x4 key cells, key =
+ * index - first of the CIC index (int)((x-origin)*invdx+0.5), the same truncation scatter/gather use).
+ * Bucket t owns slots [start[t], start[t]+cap[t]) of the six SoA arrays and holds count[t] particles in
+ * runs that are sorted by cell; caps carry a few per cent of slack so ONE pass over the particles can push
+ * them, re-bin them and write them straight into next step's buckets (no counting pass, no separate sort).
+ * Particles that do not fit (or arrive from other ranks) live in an unsorted tail after the last bucket.
+ * The tables live in device memory and are re-planned on the device after every step: no host sync.
+ * This is storage behind ParticleAttrib (src/Particle/ParticleAttrib.h:33-277): ipplb_bins_compact gives
+ * the contiguous [0,n) view the reference API exposes. */
+typedef struct ipplb_bins ipplb_bins;
+enum {
+    IPPLB_FLAG_EXIT_OVERFLOW = 1,  /* more leavers than exit_cap (leavers beyond it were dropped) */
+    IPPLB_FLAG_CAPACITY      = 2,  /* arrays too small for buckets + tail (particles were dropped) */
+    IPPLB_FLAG_INTERNAL      = 4,  /* invariant violated (bug) */
+    IPPLB_FLAG_SLACK_SCALED  = 8   /* informational: bucket slack was reduced to fit the capacity */
+};
+/* capacity: elements per SoA array of BOTH particle bundles handed to build/step (>= ~1.25 n). */
+int ipplb_bins_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, long capacity, ipplb_bins** out);
+int ipplb_bins_destroy(ipplb_bins* bins);
+/* Counting sort of `in` (contiguous, any order, in->n particles; uniform charge) into buckets of `out`
+ * (cell-sorted inside every bucket).  in and out must not alias. */
+int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* in, ipplb_particles* out);
+/* One fused step over the bucketed particles `cur`, written re-bucketed into `nxt` (the caller swaps the
+ * two bundles afterwards): per particle gather E (tile of E staged in shared memory) -> kick, kick, drift,
+ * periodic BC (ipplb_push, bit-identical to ipplb_gather_push) -> shared-memory binning by new cell ->
+ * coalesced store into next step's buckets -> charge deposit from the sorted shared-memory copy
+ * (rho +=; caller zeroes rho and chains the halo accumulate).  Asynchronous on the context's stream.
+ * Input is streamed with bulk async copies (TMA, cp.async.bulk + mbarrier) by a producer warp.
+ * Particles that left the rank's region (multi-GPU: reference ownership test, ParticleSpatialLayout.hpp:
+ * 316-330) go to exit_buf[6][exit_cap] (x,y,z,px,py,pz) and are not deposited.
  * Replaces, for one step: ParticleAttrib::operator= x3 (ParticleAttrib.hpp:118-130), applyBC
  * (ParticleLayout.hpp:34-74), gather (:193-246) and scatter (:132-184). */
-int ipplb_step_fused(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
-                     ipplb_particles* scratch, int* cell_offsets, long n_sorted, const double* efield,
-                     double* rho, double* exit_buf, int exit_cap, int* n_exit_host);
+int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_push* push, const ipplb_particles* cur,
+                    ipplb_particles* nxt, const double* efield, double* rho, double* exit_buf,
+                    int exit_cap, const double region_min[3], const double region_max[3]);
+/* Synchronises the stream and reports the state after the last build/step/append: particles held
+ * (buckets + tail), of which in the tail, leavers written to exit_buf by the last step, IPPLB_FLAG_* bits. */
+int ipplb_bins_status(ipplb_ctx* ctx, ipplb_bins* bins, long* n_local, long* n_tail, long* n_exit,
+                      int* flags);
+/* Appends `count` particles (device SoA pointers src[6]) to the tail of `cur` (migration arrivals). */
+int ipplb_bins_append(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, const double* const src[6],
+                      long count);
+/* Contiguous copy (bucket order, then tail) of the bucketed `cur` into out[0..n). Sets out->n (syncs). */
+int ipplb_bins_compact(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* cur,
+                       ipplb_particles* out);
+/* read-only access for tests: copies start/cap/count of the current buffer to host arrays [ntiles] */
+int ipplb_bins_ntiles(const ipplb_bins* bins);
+int ipplb_bins_tables(ipplb_ctx* ctx, ipplb_bins* bins, int* start_host, int* cap_host, int* count_host);
 
 /* ---- whole-step conveniences used by bench.py / the facade ---------------------------------- */
 /* One PIC step of the metric (scatter + push + gather) on resident particles, single rank:
- *   gather_push(E) -> sort (every sort_every steps) -> rho = 0 -> scatter -> periodic accumulate.
- * do_sort: 0 = no sort, atomic scatter; 1 = counting sort + sorted scatter; 2 = ipplb_step_fused (p must
- * already be cell-sorted with cell_offsets valid).  The field solve is NOT included (non-owned). */
+ *   do_sort 0: gather_push -> rho = 0 -> atomic scatter -> periodic accumulate
+ *   do_sort 1: gather_push -> counting sort -> rho = 0 -> sorted scatter -> periodic accumulate
+ *   do_sort 2: rho = 0 -> ipplb_bins_step (p must be bucketed by `bins`) -> periodic accumulate;
+ *              p and scratch swap.
+ * The field solve is NOT included (non-owned). */
 int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
-                   ipplb_particles* scratch, int* cell_offsets, const double* efield, double* rho,
-                   int do_sort);
-/* Same step through HOST buffers (bench.py's e2e): copies x..pz host->device, runs the step, copies
- * x..pz and rho back.  Host pointers should be pinned. */
+                   ipplb_particles* scratch, int* cell_offsets, ipplb_bins* bins, const double* efield,
+                   double* rho, int do_sort);
+/* Same step through HOST buffers (bench.py's e2e): copies x..pz host->device, bins them, runs the fused
+ * step, compacts and copies x..pz and rho back.  Host pointers should be pinned. */
 int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, long n,
                         double* const host_arrays[6], double q_scalar, const double* efield_dev,
                         double* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
-                        int* cell_offsets, double* rho_dev);
+                        ipplb_bins* bins, double* rho_dev);
 
 #ifdef __cplusplus
 }

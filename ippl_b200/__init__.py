@@ -7,8 +7,8 @@ facade that keeps IPPL's ParticleAttrib / Field / FieldLayout / ParticleSpatialL
 include/ippl/.  There is NO CPU fallback: without the library or without a CUDA device every
 compute call raises.
 """
-from .lib import (Context, IpplbError, Layout, Mesh, Particles, Poisson, Push, lib, lib_path,  # noqa: F401
+from .lib import (Bins, Context, IpplbError, Layout, Mesh, Particles, Poisson, Push, lib, lib_path,  # noqa: F401
                   exported_symbols, leapfrog_push, nccl_unique_id, penning_push)
 
-__all__ = ["Context", "IpplbError", "Layout", "Mesh", "Particles", "Poisson", "Push", "lib", "lib_path",
+__all__ = ["Bins", "Context", "IpplbError", "Layout", "Mesh", "Particles", "Poisson", "Push", "lib", "lib_path",
            "exported_symbols", "leapfrog_push", "nccl_unique_id", "penning_push"]

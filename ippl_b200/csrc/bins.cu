@@ -1,0 +1,401 @@
+// bins.cu -- the cell-ordered particle store behind the fused step: bucket tables, device-side planning,
+// initial build (counting sort into buckets), tail append, compaction to the contiguous API view.
+#include <cub/device/device_scan.cuh>
+
+#include "bins.h"
+#include "keys.cuh"
+
+namespace ipplb {
+
+__device__ __forceinline__ int round16(int v) { return (v + 15) & ~15; }
+
+// ---- planning: one CTA (ntiles is a few 10^4) ------------------------------------------------------------
+// o = buffer that was just written: its cursor counts every particle that WANTED the tile, including those
+// that overflowed into the tail.  i = the other buffer, planned here as the next output: every bucket gets
+// room for the tile's current total plus slack (the flux through a tile's faces is a few per cent per step).
+__global__ void __launch_bounds__(1024)
+bins_plan_kernel(int nt, const int* __restrict__ cap_o, int* __restrict__ count_o, int* __restrict__ state_o,
+                 int* __restrict__ start_i, int* __restrict__ cap_i, int* __restrict__ count_i,
+                 int* __restrict__ state_i, int* __restrict__ misc, int capacity, int slack_div,
+                 int slack_sqrt, int slack_const, int tail_reserve) {
+    __shared__ long long red[3][32];
+    __shared__ long long tot[3];
+    __shared__ long long wsum[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int per = (nt + 1023) / 1024;
+    const int j0 = min(nt, t * per), j1 = min(nt, j0 + per);
+    long long s0 = 0, s1 = 0, nb = 0;
+    for (int j = j0; j < j1; ++j) {
+        const int total = count_o[j];
+        const int c     = min(total, cap_o[j]);
+        count_o[j]      = c;      // particles really stored in the bucket
+        cap_i[j]        = total;  // scratch for the second phase (same thread)
+        s0 += round16(total);
+        s1 += total / slack_div + slack_sqrt * (int)sqrtf((float)total) + slack_const;
+        nb += c;
+    }
+    long long v[3] = {s0, s1, nb};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[k][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            long long x = red[k][lane];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) tot[k] = x;
+        }
+    }
+    __syncthreads();
+    int flags = 0;
+    const long long avail = (long long)capacity - tail_reserve - tot[0];
+    double scale = 1.0;
+    if (tot[1] > avail) {
+        scale = avail > 0 ? (double)avail / (double)tot[1] : 0.0;
+        flags |= IPPLB_FLAG_SLACK_SCALED;
+    }
+    long long mine = 0;
+    for (int j = j0; j < j1; ++j) {
+        const int total = cap_i[j];
+        const int slack = total / slack_div + slack_sqrt * (int)sqrtf((float)total) + slack_const;
+        const int want  = round16(total + (int)(slack * scale));
+        cap_i[j]        = want;
+        mine += want;
+    }
+    // block-wide exclusive scan of the per-thread sums
+    long long inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = wsum[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        wsum[lane] = wi - w;
+        if (lane == 31) tot[0] = wi;  // sum of all wants
+    }
+    __syncthreads();
+    long long run = wsum[warp] + inc - mine;
+    for (int j = j0; j < j1; ++j) {
+        const int want = cap_i[j];
+        // never plan a bucket beyond the arrays: what does not fit overflows into the tail / is flagged
+        const long long s = run < capacity ? run : capacity;
+        start_i[j]        = (int)s;
+        cap_i[j]          = (int)(s + want <= capacity ? want : capacity - s);
+        count_i[j]        = 0;
+        run += want;
+    }
+    if (t == 0) {
+        const long long all = tot[0];
+        if (all > capacity) flags |= IPPLB_FLAG_CAPACITY;
+        state_i[BS_TAIL_START] = (int)(all < capacity ? all : capacity);
+        state_i[BS_TAIL_COUNT] = 0;
+        // tail of the buffer just written: clamp the cursor to what fitted
+        int tc = state_o[BS_TAIL_COUNT];
+        const int room = capacity - state_o[BS_TAIL_START];
+        if (tc > room) tc = room > 0 ? room : 0;
+        state_o[BS_TAIL_COUNT] = tc;
+        misc[BM_ST_TOTAL]      = (int)(tot[2] + tc);
+        misc[BM_ST_BUCKETED]   = (int)tot[2];
+        misc[BM_ST_TAIL]       = tc;
+        misc[BM_ST_EXIT]       = misc[BM_EXIT];
+        misc[BM_ST_FLAGS]      = misc[BM_FLAGS] | flags;
+    }
+}
+
+// ---- build ---------------------------------------------------------------------------------------------------
+// totals per tile from the per-cell offsets; written as the "cursor" of the buffer that bins_plan treats as
+// just-written, with caps equal to the totals (nothing overflowed)
+__global__ void tile_totals_kernel(int nt, const int* __restrict__ cell_off, int* __restrict__ cap_o,
+                                   int* __restrict__ count_o) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+        const int tot = cell_off[(t + 1) * TILE_CELLS] - cell_off[t * TILE_CELLS];
+        cap_o[t]      = tot;
+        count_o[t]    = tot;
+    }
+}
+
+__global__ void set_counts_kernel(int nt, const int* __restrict__ tot, const int* __restrict__ cap,
+                                  int* __restrict__ count, int* __restrict__ misc) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+        count[t] = min(tot[t], cap[t]);
+        if (tot[t] > cap[t]) atomicOr(&misc[BM_FLAGS], IPPLB_FLAG_CAPACITY);
+    }
+}
+
+struct SoA6 {
+    const double* in[6];
+    double* out[6];
+};
+
+__global__ void __launch_bounds__(256)
+bins_move_kernel(long n, const int* __restrict__ keys, const int* __restrict__ cell_off,
+                 int* __restrict__ cell_cursor, const int* __restrict__ start, const int* __restrict__ cap,
+                 SoA6 P) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int key  = keys[i];
+        const int tile = key >> 6;
+        const int in_t = cell_off[key] - cell_off[tile << 6] + atomicAdd(&cell_cursor[key], 1);
+        if (in_t < cap[tile]) {
+            const long g = (long)start[tile] + in_t;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) P.out[a][g] = P.in[a][i];
+        }
+    }
+}
+
+// ---- append / compact -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bins_append_kernel(long count, const int* __restrict__ state, int capacity, SoA6 P, int* __restrict__ misc) {
+    const long base   = (long)state[BS_TAIL_START] + state[BS_TAIL_COUNT];
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long g = base + i;
+        if (g < capacity) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) P.out[a][g] = P.in[a][i];
+        } else if (i == count - 1) {
+            atomicOr(&misc[BM_ST_FLAGS], IPPLB_FLAG_CAPACITY);
+        }
+    }
+}
+
+__global__ void bins_append_commit_kernel(long count, int* __restrict__ state, int capacity,
+                                          int* __restrict__ misc) {
+    const long room = (long)capacity - state[BS_TAIL_START] - state[BS_TAIL_COUNT];
+    const int add   = (int)(count < room ? count : (room > 0 ? room : 0));
+    state[BS_TAIL_COUNT] += add;
+    misc[BM_ST_TOTAL] += add;
+    misc[BM_ST_TAIL] += add;
+}
+
+// one CTA per tile: bucket -> contiguous; the last CTAs copy the tail
+__global__ void __launch_bounds__(256)
+bins_compact_kernel(int nt, const int* __restrict__ start, const int* __restrict__ count,
+                    const int* __restrict__ off, const int* __restrict__ state, SoA6 P) {
+    for (int b = blockIdx.x; b < nt + 64; b += gridDim.x) {
+        long src, dst;
+        int cnt;
+        if (b < nt) {
+            src = start[b];
+            dst = off[b];
+            cnt = count[b];
+            for (int j = threadIdx.x; j < cnt; j += 256) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) P.out[a][dst + j] = P.in[a][src + j];
+            }
+        } else {
+            const int part = b - nt;  // 64 CTAs share the tail
+            src = state[BS_TAIL_START];
+            dst = off[nt];
+            cnt = state[BS_TAIL_COUNT];
+            for (long j = (long)part * 256 + threadIdx.x; j < cnt; j += 64 * 256) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) P.out[a][dst + j] = P.in[a][src + j];
+            }
+        }
+    }
+}
+
+int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o) {
+    const int i = 1 - o;
+    const int reserve = (int)(b->capacity / 50) + 1024;
+    bins_plan_kernel<<<1, 1024, 0, ctx->stream>>>(b->ntiles, b->cap(o), b->count(o), b->state(o), b->start(i),
+                                                  b->cap(i), b->count(i), b->state(i), b->misc(),
+                                                  (int)b->capacity, b->slack_div, b->slack_sqrt,
+                                                  b->slack_const, reserve);
+    IPPLB_CHECK_LAUNCH(ctx);
+    return IPPLB_OK;
+}
+
+static int grid_for(const ipplb_ctx* ctx, long n, int block, int per_sm) {
+    long want = (n + block - 1) / block;
+    long cap  = (long)ctx->num_sms * per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace ipplb
+
+using namespace ipplb;
+
+extern "C" {
+
+int ipplb_bins_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, long capacity, ipplb_bins** out) {
+    IPPLB_REQUIRE(ctx && mesh && out && capacity > 0, "bins_create: bad arguments");
+    IPPLB_REQUIRE(capacity < (1L << 31) - 64, "bins_create: capacity must stay below 2^31 elements per rank");
+    ipplb_bins* b = new ipplb_bins();
+    b->mesh     = *mesh;
+    b->ntx      = tiles_along(mesh->nl[0]);
+    b->nty      = tiles_along(mesh->nl[1]);
+    b->ntz      = tiles_along(mesh->nl[2]);
+    b->ntiles   = b->ntx * b->nty * b->ntz;
+    b->ncells   = (long)b->ntiles * TILE_CELLS;
+    b->capacity = capacity & ~15L;
+    cudaError_t e = cudaMalloc(&b->d_tab, sizeof(int) * b->tab_words());
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cell, sizeof(int) * (size_t)(b->ncells + 1));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_status, sizeof(int) * BM_WORDS);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_tab, 0, sizeof(int) * b->tab_words(), ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("bins_create: %s", cudaGetErrorString(e));
+        ipplb_bins_destroy(b);
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? IPPLB_ERR_NO_DEVICE : IPPLB_ERR_CUDA;
+    }
+    *out = b;
+    return IPPLB_OK;
+}
+
+int ipplb_bins_destroy(ipplb_bins* b) {
+    if (!b) return IPPLB_OK;
+    if (b->d_tab) cudaFree(b->d_tab);
+    if (b->d_cell) cudaFree(b->d_cell);
+    if (b->h_status) cudaFreeHost(b->h_status);
+    delete b;
+    return IPPLB_OK;
+}
+
+int ipplb_bins_ntiles(const ipplb_bins* b) { return b ? b->ntiles : -1; }
+
+int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_particles* in, ipplb_particles* out) {
+    IPPLB_REQUIRE(ctx && b && in && out, "bins_build: bad arguments");
+    IPPLB_REQUIRE(in->q == nullptr, "bins_build: per-particle charge arrays take the unfused path");
+    IPPLB_REQUIRE(out->capacity >= b->capacity, "bins_build: output bundle smaller than the bins capacity");
+    IPPLB_REQUIRE(in->n <= b->capacity, "bins_build: more particles than capacity");
+    const long n = in->n;
+    MeshDev m    = make_mesh_dev(&b->mesh);
+    int rc;
+    if ((rc = ensure(ctx, ctx->keys, sizeof(int) * (size_t)(n > 0 ? n : 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->counts, sizeof(int) * (size_t)(b->ncells + 1)))) return rc;
+    int* keys   = (int*)ctx->keys.ptr;
+    int* counts = (int*)ctx->counts.ptr;
+    IPPLB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (b->ncells + 1), ctx->stream));
+    IPPLB_CUDA(cudaMemsetAsync(b->misc(), 0, sizeof(int) * BM_WORDS, ctx->stream));
+    if (n > 0) {
+        sort_keys_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(m, n, in->x, in->y, in->z, keys,
+                                                                             counts);
+        IPPLB_CHECK_LAUNCH(ctx);
+    }
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, b->d_cell, (int)(b->ncells + 1), ctx->stream);
+    if ((rc = ensure(ctx, ctx->cub_tmp, tmp_bytes))) return rc;
+    IPPLB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.ptr, tmp_bytes, counts, b->d_cell,
+                                             (int)(b->ncells + 1), ctx->stream));
+    ctx->launches += 2;
+    const int c = b->cur, o = 1 - b->cur;
+    const int tg = (b->ntiles + 255) / 256;
+    // totals -> "just written" pseudo buffer o; plan c from them; place the particles; plan o for the first step
+    tile_totals_kernel<<<tg, 256, 0, ctx->stream>>>(b->ntiles, b->d_cell, b->cap(o), b->count(o));
+    IPPLB_CHECK_LAUNCH(ctx);
+    IPPLB_CUDA(cudaMemsetAsync(b->state(o), 0, sizeof(int) * BS_WORDS, ctx->stream));
+    if ((rc = bins_plan(ctx, b, o))) return rc;
+    set_counts_kernel<<<tg, 256, 0, ctx->stream>>>(b->ntiles, b->count(o), b->cap(c), b->count(c), b->misc());
+    IPPLB_CHECK_LAUNCH(ctx);
+    IPPLB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (b->ncells + 1), ctx->stream));
+    if (n > 0) {
+        SoA6 P;
+        const double* pi[6] = {in->x, in->y, in->z, in->px, in->py, in->pz};
+        double* po[6]       = {out->x, out->y, out->z, out->px, out->py, out->pz};
+        for (int a = 0; a < 6; ++a) {
+            IPPLB_REQUIRE(pi[a] && po[a] && pi[a] != po[a], "bins_build: null or aliased particle arrays");
+            P.in[a]  = pi[a];
+            P.out[a] = po[a];
+        }
+        bins_move_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(n, keys, b->d_cell, counts,
+                                                                             b->start(c), b->cap(c), P);
+        IPPLB_CHECK_LAUNCH(ctx);
+    }
+    if ((rc = bins_plan(ctx, b, c))) return rc;
+    b->built      = true;
+    out->n        = n;
+    out->q        = nullptr;
+    out->q_scalar = in->q_scalar;
+    return IPPLB_OK;
+}
+
+int ipplb_bins_status(ipplb_ctx* ctx, ipplb_bins* b, long* n_local, long* n_tail, long* n_exit, int* flags) {
+    IPPLB_REQUIRE(ctx && b, "bins_status: bad arguments");
+    IPPLB_CUDA(cudaMemcpyAsync(b->h_status, b->misc(), sizeof(int) * BM_WORDS, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_local) *n_local = b->h_status[BM_ST_TOTAL];
+    if (n_tail) *n_tail = b->h_status[BM_ST_TAIL];
+    if (n_exit) *n_exit = b->h_status[BM_ST_EXIT];
+    if (flags) *flags = b->h_status[BM_ST_FLAGS];
+    return IPPLB_OK;
+}
+
+int ipplb_bins_append(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, const double* const src[6],
+                      long count) {
+    IPPLB_REQUIRE(ctx && b && cur && src && count >= 0, "bins_append: bad arguments");
+    IPPLB_REQUIRE(b->built, "bins_append: call ipplb_bins_build first");
+    if (count == 0) return IPPLB_OK;
+    SoA6 P;
+    double* po[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
+    for (int a = 0; a < 6; ++a) {
+        P.in[a]  = src[a];
+        P.out[a] = po[a];
+    }
+    bins_append_kernel<<<grid_for(ctx, count, 256, 8), 256, 0, ctx->stream>>>(count, b->state(b->cur),
+                                                                              (int)b->capacity, P, b->misc());
+    IPPLB_CHECK_LAUNCH(ctx);
+    bins_append_commit_kernel<<<1, 1, 0, ctx->stream>>>(count, b->state(b->cur), (int)b->capacity, b->misc());
+    IPPLB_CHECK_LAUNCH(ctx);
+    cur->n += count;
+    return IPPLB_OK;
+}
+
+int ipplb_bins_compact(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_particles* cur, ipplb_particles* out) {
+    IPPLB_REQUIRE(ctx && b && cur && out, "bins_compact: bad arguments");
+    IPPLB_REQUIRE(b->built, "bins_compact: call ipplb_bins_build first");
+    long n = 0;
+    int flags = 0, rc;
+    if ((rc = ipplb_bins_status(ctx, b, &n, nullptr, nullptr, &flags))) return rc;
+    IPPLB_REQUIRE(out->capacity >= n, "bins_compact: output capacity too small");
+    size_t tmp_bytes = 0;
+    int* off = b->d_cell;  // scratch, ntiles + 1 <= ncells + 1
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b->count(b->cur), off, b->ntiles + 1, ctx->stream);
+    if ((rc = ensure(ctx, ctx->cub_tmp, tmp_bytes))) return rc;
+    // ntiles + 1 items so that off[ntiles] = sum of the counts (the extra input word is another table word
+    // inside d_tab and does not influence any output that is read)
+    IPPLB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.ptr, tmp_bytes, b->count(b->cur), off, b->ntiles + 1,
+                                             ctx->stream));
+    ctx->launches += 2;
+    SoA6 P;
+    const double* pi[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
+    double* po[6]       = {out->x, out->y, out->z, out->px, out->py, out->pz};
+    for (int a = 0; a < 6; ++a) {
+        IPPLB_REQUIRE(pi[a] && po[a] && pi[a] != po[a], "bins_compact: null or aliased particle arrays");
+        P.in[a]  = pi[a];
+        P.out[a] = po[a];
+    }
+    const int grid = b->ntiles + 64 < ctx->num_sms * 16 ? b->ntiles + 64 : ctx->num_sms * 16;
+    bins_compact_kernel<<<grid, 256, 0, ctx->stream>>>(b->ntiles, b->start(b->cur), b->count(b->cur), off,
+                                                       b->state(b->cur), P);
+    IPPLB_CHECK_LAUNCH(ctx);
+    out->n        = n;
+    out->q        = nullptr;
+    out->q_scalar = cur->q_scalar;
+    return IPPLB_OK;
+}
+
+int ipplb_bins_tables(ipplb_ctx* ctx, ipplb_bins* b, int* start_host, int* cap_host, int* count_host) {
+    IPPLB_REQUIRE(ctx && b, "bins_tables: bad arguments");
+    const size_t bytes = sizeof(int) * (size_t)b->ntiles;
+    if (start_host) IPPLB_CUDA(cudaMemcpyAsync(start_host, b->start(b->cur), bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cap_host) IPPLB_CUDA(cudaMemcpyAsync(cap_host, b->cap(b->cur), bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (count_host) IPPLB_CUDA(cudaMemcpyAsync(count_host, b->count(b->cur), bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IPPLB_OK;
+}
+
+}  // extern "C"

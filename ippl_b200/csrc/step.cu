@@ -3,36 +3,46 @@
 
 using namespace ipplb;
 
+static long ghosted_cells(const ipplb_mesh* mesh) {
+    return (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
+           (mesh->nl[2] + 2 * mesh->nghost);
+}
+
+static void swap_bundles(ipplb_particles* p, ipplb_particles* scratch) {
+    ipplb_particles t = *p;
+    *p                = *scratch;
+    *scratch          = t;
+}
+
 extern "C" {
 
 int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
-                   ipplb_particles* scratch, int* cell_offsets, const double* efield, double* rho,
-                   int do_sort) {
+                   ipplb_particles* scratch, int* cell_offsets, ipplb_bins* bins, const double* efield,
+                   double* rho, int do_sort) {
     IPPLB_REQUIRE(ctx && mesh && push && p && efield && rho, "pic_step: bad arguments");
     int rc;
     int mask = 0;
     for (int d = 0; d < 3; ++d)
         if (mesh->nl[d] == mesh->ng[d]) mask |= 1 << d;
+    const long cells = ghosted_cells(mesh);
     if (do_sort == 2) {
-        const long cells2 = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
-                            (mesh->nl[2] + 2 * mesh->nghost);
-        if ((rc = ipplb_field_fill(ctx, rho, cells2, 0.0))) return rc;
-        if ((rc = ipplb_step_fused(ctx, mesh, push, p, scratch, cell_offsets, p->n, efield, rho, nullptr, 0,
-                                   nullptr)))
+        IPPLB_REQUIRE(bins && scratch, "pic_step: the fused step needs bins and a second particle bundle");
+        if ((rc = ipplb_field_fill(ctx, rho, cells, 0.0))) return rc;
+        const long n = p->n;
+        if ((rc = ipplb_bins_step(ctx, bins, push, p, scratch, efield, rho, nullptr, 0, nullptr, nullptr)))
             return rc;
+        swap_bundles(p, scratch);
+        p->n       = n;  // single rank, periodic: nobody leaves (ipplb_bins_status reports the device truth)
+        scratch->n = 0;
         return ipplb_halo_accumulate_periodic(ctx, mesh, rho, 1, mask);
     }
     if ((rc = ipplb_gather_push(ctx, mesh, push, p, efield))) return rc;
-    const long cells = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
-                       (mesh->nl[2] + 2 * mesh->nghost);
     if ((rc = ipplb_field_fill(ctx, rho, cells, 0.0))) return rc;
     if (do_sort) {
         IPPLB_REQUIRE(scratch && cell_offsets, "pic_step: sort needs scratch arrays and cell_offsets");
         if ((rc = ipplb_sort_by_cell(ctx, mesh, p, scratch, cell_offsets))) return rc;
-        ipplb_particles t = *p;
-        *p                = *scratch;
-        *scratch          = t;
-        scratch->n        = 0;
+        swap_bundles(p, scratch);
+        scratch->n = 0;
         if ((rc = ipplb_scatter_cic_sorted(ctx, mesh, p->n, p->x, p->y, p->z, p->q, p->q_scalar,
                                            cell_offsets, rho)))
             return rc;
@@ -47,9 +57,12 @@ int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* pus
 int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, long n,
                         double* const host_arrays[6], double q_scalar, const double* efield_dev,
                         double* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
-                        int* cell_offsets, double* rho_dev) {
-    IPPLB_REQUIRE(ctx && mesh && push && host_arrays && dev && rho_dev, "pic_step_host: bad arguments");
-    IPPLB_REQUIRE(dev->capacity >= n, "pic_step_host: device capacity too small");
+                        ipplb_bins* bins, double* rho_dev) {
+    IPPLB_REQUIRE(ctx && mesh && push && host_arrays && dev && scratch && bins && rho_dev,
+                  "pic_step_host: bad arguments");
+    IPPLB_REQUIRE(dev->capacity >= n && scratch->capacity >= n, "pic_step_host: device capacity too small");
+    // host -> dev (contiguous), dev -> scratch (bucketed), scratch -> dev (fused step), dev -> scratch
+    // (contiguous), scratch -> host
     double* d[6] = {dev->x, dev->y, dev->z, dev->px, dev->py, dev->pz};
     for (int a = 0; a < 6; ++a)
         IPPLB_CUDA(cudaMemcpyAsync(d[a], host_arrays[a], sizeof(double) * (size_t)n,
@@ -57,19 +70,19 @@ int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push
     dev->n        = n;
     dev->q        = nullptr;
     dev->q_scalar = q_scalar;
-    int rc = ipplb_pic_step(ctx, mesh, push, dev, scratch, cell_offsets, efield_dev, rho_dev,
-                            scratch != nullptr);
-    if (rc) return rc;
+    int rc;
+    if ((rc = ipplb_bins_build(ctx, bins, dev, scratch))) return rc;
+    if ((rc = ipplb_pic_step(ctx, mesh, push, scratch, dev, nullptr, bins, efield_dev, rho_dev, 2))) return rc;
+    // after the swap inside pic_step `scratch` names the bucketed result and `dev` the spare bundle
+    if ((rc = ipplb_bins_compact(ctx, bins, scratch, dev))) return rc;
+    IPPLB_REQUIRE(dev->n == n, "pic_step_host: particle count changed");
     double* d2[6] = {dev->x, dev->y, dev->z, dev->px, dev->py, dev->pz};
     for (int a = 0; a < 6; ++a)
         IPPLB_CUDA(cudaMemcpyAsync(host_arrays[a], d2[a], sizeof(double) * (size_t)n,
                                    cudaMemcpyDeviceToHost, ctx->stream));
-    if (rho_host) {
-        const long cells = (long)(mesh->nl[0] + 2 * mesh->nghost) * (mesh->nl[1] + 2 * mesh->nghost) *
-                           (mesh->nl[2] + 2 * mesh->nghost);
-        IPPLB_CUDA(cudaMemcpyAsync(rho_host, rho_dev, sizeof(double) * (size_t)cells,
+    if (rho_host)
+        IPPLB_CUDA(cudaMemcpyAsync(rho_host, rho_dev, sizeof(double) * (size_t)ghosted_cells(mesh),
                                    cudaMemcpyDeviceToHost, ctx->stream));
-    }
     IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
     return IPPLB_OK;
 }

@@ -273,26 +273,14 @@ class Context:
         mask = mesh.serial_mask if mask is None else mask
         _check(lib().ipplb_halo_fill_periodic(self._h, C.byref(mesh), _ptr(f), ncomp, mask))
 
-    def step_fused(self, mesh, push, parts, scratch, offsets, efield, rho, n_sorted=None, exit_buf=None):
-        """ipplb_step_fused; `parts` and `scratch` swap storage.  Returns the number of leavers."""
-        s, sc = parts.struct(), scratch.struct()
-        n_exit = C.c_int(0)
-        cap = 0 if exit_buf is None else exit_buf.numel() // 6
-        _check(lib().ipplb_step_fused(self._h, C.byref(mesh), C.byref(push), C.byref(s), C.byref(sc),
-                                      _ptr(offsets), C.c_long(parts.n if n_sorted is None else n_sorted),
-                                      _ptr(efield), _ptr(rho), _ptr(exit_buf), cap, C.byref(n_exit)))
-        parts.arr, scratch.arr = scratch.arr, parts.arr
-        parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
-        parts.n = int(s.n)
-        return n_exit.value
-
-    def pic_step(self, mesh, push, parts, scratch, offsets, efield, rho, do_sort=True):
-        """One metric step; when sorting (1) or fused (2), `parts` and `scratch` swap storage."""
+    def pic_step(self, mesh, push, parts, scratch, offsets, efield, rho, do_sort=True, bins=None):
+        """One metric step.  do_sort 1: counting sort + sorted scatter, 2: fused single-pass step on bucketed
+        particles (`bins`); in both `parts` and `scratch` swap storage."""
         s = parts.struct()
         sc = scratch.struct() if scratch is not None else None
         _check(lib().ipplb_pic_step(self._h, C.byref(mesh), C.byref(push), C.byref(s),
-                                    C.byref(sc) if sc is not None else None, _ptr(offsets), _ptr(efield),
-                                    _ptr(rho), int(do_sort)))
+                                    C.byref(sc) if sc is not None else None, _ptr(offsets),
+                                    bins._h if bins is not None else None, _ptr(efield), _ptr(rho), int(do_sort)))
         if do_sort:
             parts.arr, scratch.arr = scratch.arr, parts.arr
             parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
@@ -332,6 +320,65 @@ def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _check(lib().ipplb_nccl_unique_id(buf))
     return buf.raw
+
+
+class Bins:
+    """ipplb_bins: per-tile bucketed particle store behind the fused step.  `cur` holds the particles,
+    `nxt` is the spare bundle; both must have `capacity` elements per array."""
+
+    def __init__(self, ctx, mesh, capacity):
+        self.ctx, self.mesh, self.capacity = ctx, mesh, int(capacity)
+        self._h = C.c_void_p()
+        _check(lib().ipplb_bins_create(ctx._h, C.byref(mesh), C.c_long(self.capacity), C.byref(self._h)))
+        self.ntiles = lib().ipplb_bins_ntiles(self._h)
+
+    def close(self):
+        if self._h:
+            lib().ipplb_bins_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def build(self, src, dst):
+        """counting sort of the contiguous `src` into the buckets of `dst`"""
+        s, d = src.struct(), dst.struct()
+        _check(lib().ipplb_bins_build(self.ctx._h, self._h, C.byref(s), C.byref(d)))
+        dst.n, dst.q_scalar = src.n, src.q_scalar
+
+    def step(self, push, cur, nxt, efield, rho, exit_buf=None, region=None):
+        """ipplb_bins_step; the caller's `cur` / `nxt` swap storage (like the sort).  Asynchronous."""
+        s, d = cur.struct(), nxt.struct()
+        cap = 0 if exit_buf is None else exit_buf.numel() // 6
+        rmin = (C.c_double * 3)(*region[:3]) if region is not None else None
+        rmax = (C.c_double * 3)(*region[3:]) if region is not None else None
+        _check(lib().ipplb_bins_step(self.ctx._h, self._h, C.byref(push), C.byref(s), C.byref(d), _ptr(efield),
+                                     _ptr(rho), _ptr(exit_buf), cap, rmin, rmax))
+        cur.arr, nxt.arr = nxt.arr, cur.arr
+        cur.qarr, nxt.qarr = nxt.qarr, cur.qarr
+
+    def status(self):
+        """(n_local, n_tail, n_exit, flags) after the last build / step / append (synchronises)"""
+        n, t, e, f = C.c_long(), C.c_long(), C.c_long(), C.c_int()
+        _check(lib().ipplb_bins_status(self.ctx._h, self._h, C.byref(n), C.byref(t), C.byref(e), C.byref(f)))
+        return n.value, t.value, e.value, f.value
+
+    def append(self, cur, src, count):
+        """append `count` particles (six device tensors) to the tail of `cur`"""
+        s = cur.struct()
+        arr = (C.c_void_p * 6)(*[a.data_ptr() for a in src])
+        _check(lib().ipplb_bins_append(self.ctx._h, self._h, C.byref(s), arr, C.c_long(count)))
+        cur.n += count
+
+    def compact(self, cur, out):
+        s, d = cur.struct(), out.struct()
+        _check(lib().ipplb_bins_compact(self.ctx._h, self._h, C.byref(s), C.byref(d)))
+        out.n, out.q_scalar = int(d.n), cur.q_scalar
+        return out.n
+
+    def tables(self):
+        import numpy as np
+        st, cp, ct = (np.zeros(self.ntiles, dtype=np.int32) for _ in range(3))
+        _check(lib().ipplb_bins_tables(self.ctx._h, self._h, st.ctypes.data_as(C.c_void_p),
+                                       cp.ctypes.data_as(C.c_void_p), ct.ctypes.data_as(C.c_void_p)))
+        return st, cp, ct
 
 
 class Poisson:

@@ -327,9 +327,11 @@ def test_landau_energy_history_vs_oracle(ctx, mode):
     sim = oracle.LandauOracle(nr, R, P, parallel=False)
     Q = sim.Q
     q = Q / n
-    parts = ib.Particles.from_host(R, P, ctx.device, q=q)
-    scratch = ib.Particles(n, ctx.device)
+    cap = int(1.5 * n) if mode == 2 else n
+    parts = ib.Particles.from_host(R, P, ctx.device, q=q, capacity=cap)
+    scratch = ib.Particles(cap, ctx.device)
     off = ctx.offsets_buffer(mg)
+    bins = ib.Bins(ctx, mg, cap) if mode == 2 else None
     rho, ef = ctx.field(mg), ctx.field(mg, 3)
     sol = ib.Poisson(ctx, mg)
     cell, size = sim.hr[0] * sim.hr[1] * sim.hr[2], sim.rmax ** 3
@@ -347,20 +349,20 @@ def test_landau_energy_history_vs_oracle(ctx, mode):
         hist.append((t, e2 * cell, emax))
 
     # pre_run: scatter, solve, (gather is fused into the first push)
-    ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho)
+    ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho, end=n)
     ctx.halo_accumulate_periodic(mg, rho)
     sim.pre_run()
     finish_scatter()
     solve_and_dump(0.0)
     t = 0.0
-    if mode == 2:  # the fused step wants cell-sorted input with valid offsets
-        ctx.sort_by_cell(mg, parts, scratch, off)
+    if mode == 2:  # the fused step works on bucketed particles
+        bins.build(parts, scratch)
         parts.arr, scratch.arr = scratch.arr, parts.arr
     for it in range(nsteps):
         # step it: kick1 (E of previous solve), drift, BC, scatter, solve, then kick2 -- the fused kernel
         # does [kick2 of step it-1] + kick1 + drift + BC; the very first call has no pending kick2.
         push = ib.leapfrog_push(dt, kick2=1 if it > 0 else 0)
-        ctx.pic_step(mg, push, parts, scratch, off, ef, rho, do_sort=mode)
+        ctx.pic_step(mg, push, parts, scratch, off, ef, rho, do_sort=mode, bins=bins)
         sim.step()
         finish_scatter()
         t += dt
@@ -369,6 +371,10 @@ def test_landau_energy_history_vs_oracle(ctx, mode):
     hist, want = np.array(hist), np.array(sim.history)
     assert np.max(np.abs(hist[:, 1] - want[:, 1]) / want[:, 1]) <= 1e-10
     assert np.max(np.abs(hist[:, 2] - want[:, 2]) / want[:, 2]) <= 1e-10
+    if bins is not None:
+        nloc, ntail, nexit, flags = bins.status()
+        assert nloc == n and nexit == 0 and (flags & 7) == 0
+        bins.close()
     sol.close()
 
 
@@ -441,12 +447,75 @@ def test_full_size_properties(ctx):
     ctx.halo_accumulate_periodic(mg, rho_b)
     num = float((rho - rho_b).norm())
     assert num / float(rho_b.norm()) < 1e-12
+    # the fused single-pass step on the same particles: same rho as gather_push + scatter (to 1e-12), all
+    # particles kept, charge conserved, every bucket holds only its own tile's particles
+    del scratch
+    cap = int(1.25 * n)
+    pb, sc = ib.Particles(cap, ctx.device, q=parts.q_scalar), ib.Particles(cap, ctx.device, q=parts.q_scalar)
+    bins = ib.Bins(ctx, mg, cap)
+    bins.build(parts, pb)
+    push = ib.leapfrog_push(0.5 * h[0])
+    for it in range(2):
+        ctx.gather_push(mg, push, parts, ef)
+        rho_b.zero_()
+        ctx.scatter(mg, parts.arr["x"], parts.arr["y"], parts.arr["z"], parts.q_scalar, rho_b)
+        rho.zero_()
+        bins.step(push, pb, sc, ef, rho)
+        nloc, ntail, nexit, flags = bins.status()
+        assert nloc == n and nexit == 0 and (flags & 7) == 0 and ntail < n // 100
+        assert float((rho - rho_b).norm()) / float(rho_b.norm()) < 1e-12
+        ctx.halo_accumulate_periodic(mg, rho)
+        assert abs((Q - ctx.field_sum(mg, rho)) / Q) < 1e-10
+    st, cp, ct = bins.tables()
+    assert int(ct.sum()) + ntail == n and np.all(ct <= cp)
+    ntx = (nr[0] + 4) // 4
+    for t in (0, 1, ntx * ntx + 5, len(st) // 2, len(st) - ntx * ntx - 7):
+        if ct[t] == 0:
+            continue
+        sl = slice(int(st[t]), int(st[t]) + int(ct[t]))
+        R3 = [pb.arr[k][sl].cpu().numpy() for k in "xyz"]
+        assert np.all(_tile_of(mg, R3, h) == t)
+    out = ib.Particles(n, ctx.device)
+    assert bins.compact(pb, out) == n
+    assert abs(float(out.arr["px"][:n].sum()) - float(parts.arr["px"][:n].sum())) < 1e-6 * n ** 0.5
+    bins.close()
 
 
-@pytest.mark.parametrize("ppc,kind", [(2, "leapfrog"), (40, "leapfrog"), (40, "penning")])
-def test_fused_step_vs_unfused_and_oracle(ctx, ppc, kind):
-    """ipplb_step_fused == (gather_push; sort; scatter) of the unfused kernels: same multiset of particles
-    bit for bit, cell-sorted output with valid offsets, rho equal to the oracle's to 1e-12."""
+def _canon(cols):
+    a = np.stack(cols, axis=1)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def _tile_of(mg, R, h, origin=(0.0, 0.0, 0.0)):
+    """tile id of every particle (same integer arithmetic as the kernels: index = (int)((x-o)/h + 0.5))"""
+    k = []
+    for d in range(3):
+        l = (R[d] - origin[d]) * (1.0 / h[d]) + 0.5
+        k.append(l.astype(np.int32) - mg.first[d])
+    ntx, nty = (mg.nl[0] + 4) // 4, (mg.nl[1] + 4) // 4
+    return (k[0] >> 2) + ntx * ((k[1] >> 2) + nty * (k[2] >> 2))
+
+
+def _check_buckets(bins, parts, mg, h, n_expected):
+    """every bucket [start, start+count) holds only particles of its tile; buckets do not overlap"""
+    st, cp, ct = bins.tables()
+    nloc, ntail, nexit, flags = bins.status()
+    assert (flags & 7) == 0
+    assert nloc == n_expected and int(ct.sum()) + ntail == nloc
+    order = np.argsort(st, kind="stable")
+    assert np.all(st[order][1:] >= (st[order] + cp[order])[:-1]) and np.all(ct <= cp)
+    x, y, z = (parts.arr[k].cpu().numpy() for k in "xyz")
+    idx = np.concatenate([np.arange(s, s + c) for s, c in zip(st, ct) if c]) if ct.sum() else np.zeros(0, int)
+    tid = np.repeat(np.arange(len(st)), ct)
+    assert np.array_equal(_tile_of(mg, [x[idx], y[idx], z[idx]], h), tid)
+    return ntail
+
+
+@pytest.mark.parametrize("ppc,kind,vscale", [(2, "leapfrog", 3.0), (40, "leapfrog", 1.0), (40, "leapfrog", 3.0),
+                                             (40, "penning", 3.0)])
+def test_fused_step_vs_unfused_and_oracle(ctx, ppc, kind, vscale):
+    """ipplb_bins_step == (gather_push; scatter) of the unfused kernels: same multiset of particles bit for
+    bit, valid buckets, rho equal to the oracle's to 1e-12; also in steady state (second and third step)."""
     import ippl_b200 as ib
     nr = (20, 16, 12)
     n = nr[0] * nr[1] * nr[2] * ppc
@@ -457,89 +526,121 @@ def test_fused_step_vs_unfused_and_oracle(ctx, ppc, kind):
     mg = ib.Mesh.make(nr, (0, 0, 0), h)
     rng = np.random.default_rng(100 + ppc)
     R = [rng.uniform(0, L[d], n) for d in range(3)]
-    P = [3.0 * p for p in normal_velocities(n, seed=7)]   # fast particles: up to ~4 cells per step
+    P = [vscale * p for p in normal_velocities(n, seed=7)]   # vscale 3: up to ~6 cells per step (direct path)
     dt = 0.5 * h[0]
-    ef = rng.normal(size=mg.cells * 3)
+    ef = 0.2 * rng.normal(size=mg.cells * 3)   # (a particle must not cross half the domain per step: PeriodicBC)
     q = -0.37
     push = ib.leapfrog_push(dt) if kind == "leapfrog" else ib.penning_push(dt, (0, 0, 0), L)
-    # reference: unfused kernels (bit-exact vs the oracle, tested above)
-    pa = ib.Particles.from_host(R, P, ctx.device, q=q)
-    ctx.gather_push(mg, push, pa, _dev(ctx, ef))
-    Ro = pa.host()
-    want = oracle.field_zeros(mo)
-    oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], q, want)
-    # fused
-    pb = ib.Particles.from_host(R, P, ctx.device, q=q)
-    sc = ib.Particles(n, ctx.device)
-    off = ctx.offsets_buffer(mg)
-    ctx.sort_by_cell(mg, pb, sc, off)
-    pb.arr, sc.arr = sc.arr, pb.arr
+    pa = ib.Particles.from_host(R, P, ctx.device, q=q)   # reference: unfused kernels (bit-exact vs the oracle)
+    cap = int(1.6 * n) + 4096
+    src = ib.Particles.from_host(R, P, ctx.device, q=q)
+    pb, sc = ib.Particles(cap, ctx.device, q=q), ib.Particles(cap, ctx.device, q=q)
+    bins = ib.Bins(ctx, mg, cap)
+    bins.build(src, pb)
+    assert _check_buckets(bins, pb, mg, h, n) == 0
     rho = ctx.field(mg)
-    nexit = ctx.step_fused(mg, push, pb, sc, off, _dev(ctx, ef), rho)
-    assert nexit == 0 and pb.n == n
-    got = pb.host()
-
-    def canon(cols):
-        a = np.stack(cols, axis=1)
-        return a[np.lexsort(a.T[::-1])]
-    assert np.array_equal(canon(got), canon(Ro))
-    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
-    # output is cell-sorted and the offsets delimit the cells
-    offs = off.cpu().numpy()
-    k = []
-    for d in range(3):
-        l = (got[d] - 0.0) * (1.0 / h[d]) + 0.5
-        k.append(l.astype(np.int32))
-    ntx, nty = (nr[0] + 4) // 4, (nr[1] + 4) // 4
-    keys = ((k[0] >> 2) + ntx * ((k[1] >> 2) + nty * (k[2] >> 2))) * 64 + ((k[2] & 3) << 4) + ((k[1] & 3) << 2) + (k[0] & 3)
-    assert np.all(np.diff(keys) >= 0)
-    assert offs[-1] == n and np.array_equal(np.bincount(keys, minlength=len(offs) - 1), np.diff(offs))
-    # a second fused step from the fused output (steady state) still matches
-    ctx.gather_push(mg, push, pa, _dev(ctx, ef))
-    Ro2 = pa.host()
-    want2 = oracle.field_zeros(mo)
-    oracle.scatter_cic(mo, Ro2[0], Ro2[1], Ro2[2], q, want2)
-    rho.zero_()
-    ctx.step_fused(mg, push, pb, sc, off, _dev(ctx, ef), rho)
-    assert np.array_equal(canon(pb.host()), canon(Ro2))
-    assert rel_l2(rho.cpu().numpy(), want2) <= TOL_SUM
+    efd = _dev(ctx, ef)
+    for it in range(3):
+        ctx.gather_push(mg, push, pa, efd)
+        Ro = pa.host()
+        want = oracle.field_zeros(mo)
+        oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], q, want)
+        rho.zero_()
+        bins.step(push, pb, sc, efd, rho)
+        _check_buckets(bins, pb, mg, h, n)
+        out = ib.Particles(n, ctx.device)
+        assert bins.compact(pb, out) == n
+        assert np.array_equal(_canon(out.host()), _canon(Ro))
+        assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    bins.close()
 
 
-def test_fused_step_unsorted_input_and_tail(ctx):
-    """Correct for ANY input order: fully unsorted input (n_sorted = 0) and sorted + unsorted tail."""
+def test_fused_step_overflow_tail_and_append(ctx):
+    """Buckets that are too small overflow into the tail, appended particles (migration arrivals) are picked
+    up from the tail by the next step; nothing is lost and rho still matches the oracle."""
+    import ctypes as C
     import ippl_b200 as ib
     nr = (16, 16, 16)
-    n = 60000
+    n, n_add = 60000, 5000
     L = 4 * np.pi
     h = [L / 16] * 3
     mo, mg = oracle.Mesh.make(nr, (0, 0, 0), h), ib.Mesh.make(nr, (0, 0, 0), h)
     rng = np.random.default_rng(5)
-    R = [rng.uniform(0, L, n) for _ in range(3)]
-    P = normal_velocities(n, seed=8)
-    ef = rng.normal(size=mg.cells * 3)
-    push = ib.leapfrog_push(0.05)
+    # a drifting blob: all particles move the same way, so tile populations change by more than the slack
+    R = [np.clip(rng.normal(L / 2, L / 10, n + n_add), 0, np.nextafter(L, 0)) for _ in range(3)]
+    P = [p + 6.0 for p in normal_velocities(n + n_add, seed=8)]
+    ef = 0.1 * rng.normal(size=mg.cells * 3)
+    push = ib.leapfrog_push(0.5 * h[0])
     pa = ib.Particles.from_host(R, P, ctx.device, q=1.0)
-    ctx.gather_push(mg, push, pa, _dev(ctx, ef))
-    Ro = pa.host()
-    want = oracle.field_zeros(mo)
-    oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], 1.0, want)
-
-    def canon(cols):
-        a = np.stack(cols, axis=1)
-        return a[np.lexsort(a.T[::-1])]
-    for n_sorted in (0, 40000):
-        pb = ib.Particles.from_host(R, P, ctx.device, q=1.0)
-        sc = ib.Particles(n, ctx.device)
-        off = ctx.offsets_buffer(mg)
-        if n_sorted:
-            # sort the first n_sorted particles only, leave the rest as an unsorted tail
-            head = ib.Particles.from_host([r[:n_sorted] for r in R], [p[:n_sorted] for p in P], ctx.device, q=1.0)
-            hs = ib.Particles(n_sorted, ctx.device)
-            ctx.sort_by_cell(mg, head, hs, off)
-            for k in ib.Particles.NAMES:
-                pb.arr[k][:n_sorted].copy_(hs.arr[k][:n_sorted])
-        rho = ctx.field(mg)
-        ctx.step_fused(mg, push, pb, sc, off, _dev(ctx, ef), rho, n_sorted=n_sorted)
-        assert pb.n == n
-        assert np.array_equal(canon(pb.host()), canon(Ro))
+    cap = 2 * (n + n_add)
+    src = ib.Particles.from_host([r[:n] for r in R], [p[:n] for p in P], ctx.device, q=1.0)
+    pb, sc = ib.Particles(cap, ctx.device, q=1.0), ib.Particles(cap, ctx.device, q=1.0)
+    bins = ib.Bins(ctx, mg, cap)
+    bins.build(src, pb)
+    add = [_dev(ctx, a[n:]) for a in R + P]
+    bins.append(pb, add, n_add)
+    assert bins.status()[:2] == (n + n_add, n_add)
+    efd = _dev(ctx, ef)
+    rho = ctx.field(mg)
+    saw_tail = False
+    for it in range(4):
+        ctx.gather_push(mg, push, pa, efd)
+        Ro = pa.host()
+        want = oracle.field_zeros(mo)
+        oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], 1.0, want)
+        rho.zero_()
+        bins.step(push, pb, sc, efd, rho)
+        saw_tail |= _check_buckets(bins, pb, mg, h, n + n_add) > 0
+        out = ib.Particles(n + n_add, ctx.device)
+        assert bins.compact(pb, out) == n + n_add
+        assert np.array_equal(_canon(out.host()), _canon(Ro))
         assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    assert saw_tail, "the drifting blob was meant to overflow some buckets"
+    bins.close()
+
+
+def test_fused_step_exit_buffer_subdomain(ctx):
+    """Multi-rank ownership inside the fused step: on a sub-box of the global mesh, particles that leave the
+    rank's region (reference test pos > min && pos <= max) land in the exit buffer, the others stay bucketed."""
+    import torch
+    import ippl_b200 as ib
+    ng, first, nl = (16, 16, 16), (8, 0, 0), (8, 16, 16)
+    L = 4 * np.pi
+    h = [L / 16] * 3
+    mo = oracle.Mesh.make(ng, (0, 0, 0), h, first=first, nl=nl)
+    mg = ib.Mesh.make(ng, (0, 0, 0), h, first=first, nl=nl)
+    n = 50000
+    rng = np.random.default_rng(11)
+    lo = [first[d] * h[d] for d in range(3)]
+    hi = [(first[d] + nl[d]) * h[d] for d in range(3)]
+    R = [np.nextafter(lo[d], np.inf) + rng.uniform(0, 1, n) * (hi[d] - np.nextafter(lo[d], np.inf)) for d in range(3)]
+    P = [2.0 * p for p in normal_velocities(n, seed=3)]
+    ef = 0.1 * rng.normal(size=mg.cells * 3)
+    push = ib.leapfrog_push(0.5 * h[0])
+    pa = ib.Particles.from_host(R, P, ctx.device, q=1.0)
+    efd = _dev(ctx, ef)
+    ctx.gather_push(mg, push, pa, efd)
+    Ro = pa.host()
+    stay = np.ones(n, dtype=bool)
+    for d in range(3):
+        stay &= (Ro[d] > lo[d]) & (Ro[d] <= hi[d])
+    want = oracle.field_zeros(mo)
+    oracle.scatter_cic(mo, Ro[0][stay], Ro[1][stay], Ro[2][stay], 1.0, want)
+    cap = 2 * n
+    src = ib.Particles.from_host(R, P, ctx.device, q=1.0)
+    pb, sc = ib.Particles(cap, ctx.device, q=1.0), ib.Particles(cap, ctx.device, q=1.0)
+    bins = ib.Bins(ctx, mg, cap)
+    bins.build(src, pb)
+    exit_cap = n
+    exit_buf = torch.zeros(6 * exit_cap, dtype=torch.float64, device=ctx.device)
+    rho = ctx.field(mg)
+    bins.step(push, pb, sc, efd, rho, exit_buf=exit_buf, region=lo + hi)
+    nloc, ntail, nexit, flags = bins.status()
+    assert (flags & 7) == 0 and nloc == int(stay.sum()) and nexit == n - int(stay.sum()) and nexit > 0
+    out = ib.Particles(n, ctx.device)
+    assert bins.compact(pb, out) == nloc
+    assert np.array_equal(_canon(out.host()), _canon([a[stay] for a in Ro]))
+    ex = exit_buf.view(6, exit_cap)[:, :nexit].cpu().numpy()
+    assert np.array_equal(_canon(list(ex)), _canon([a[~stay] for a in Ro]))
+    assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+    bins.close()
