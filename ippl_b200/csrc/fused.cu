@@ -20,6 +20,7 @@
 // the unfused path (same device functions, same operation order).
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 
 #include "bins.h"
 #include "push.cuh"
@@ -38,7 +39,8 @@ enum { CH_TILE = 0, CH_TAIL = 1, CH_STOP = 2 };
 struct ChunkDesc {
     int kind, cnt;
     int hx, hy, hz;  // home tile coords
-    int pad[3];
+    int epi;         // which E window (tile chunks)
+    int pad[2];
 };
 
 struct StepArgs {
@@ -66,16 +68,17 @@ struct StepSmem {
     static constexpr int CAP = NT * K;
     struct Stage {
         double dat[6][CAP];
-        double2 ep[EP_N];
     } st[2];
+    double2 ep[2][EP_N];  // E window of the current / next tile (x-pairs), indexed by ChunkDesc::epi
     ChunkDesc desc[2];
     unsigned long long full[2], empty[2];
     int hist[WIN_CELLS];
     int prefix[WIN_CELLS + 1];
     unsigned short local[CAP], rank[CAP], perm[CAP];
     unsigned short list[WIN_CELLS];
-    unsigned short cellxyz[WIN_CELLS];
-    unsigned char tsof[WIN_CELLS];
+    unsigned short cellxyz[WIN_CELLS];  // window id -> packed window coords
+    unsigned short winid[WIN_CELLS];    // window coords (wz*64 + wy*8 + wx) -> tile-major window id
+    unsigned char tsof[WIN_CELLS];      // window id -> destination tile slot
     int tsbase[NSLOT + 1];
     int adj[NSLOT], lim[NSLOT], tadj[NSLOT];
     int warp_sums[32];
@@ -223,10 +226,9 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
             run += wx * wy * wz;
         }
         s.tsbase[NSLOT] = run;
-        s.nne           = 0;
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.full[i], 1);
-            mbar_init(&s.empty[i], 1);
+            mbar_init(&s.empty[i], NT / 32);
         }
         fence_mbar_init();
     }
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
         const int ts = sx + 3 * (sy + 3 * sz);
         const int id = s.tsbase[ts] + (lz * dy + ly) * dx + lx;
         s.cellxyz[id] = (unsigned short)(wx | (wy << 4) | (wz << 8));
+        s.winid[c]    = (unsigned short)id;
         s.tsof[id]    = (unsigned char)ts;
         s.hist[c]     = 0;
     }
@@ -249,19 +252,35 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
     if (warp == NT / 32) {
         const int tail_start = A.state_in[BS_TAIL_START];
         const int tail_count = A.state_in[BS_TAIL_COUNT];
-        int rem = 0, kind = CH_STOP, hx = 0, hy = 0, hz = 0;
+        int rem = 0, kind = CH_STOP, hx = 0, hy = 0, hz = 0, epi = 1;
+        bool fresh = false;  // first chunk of a tile: its E window has to be staged
         long pbeg = 0;
+        // work items are fetched two deep so that neither the scheduler atomic nor the table loads sit on the
+        // critical path: C = atomic issued (result pending in lane 0), B = item known, count/start loads in flight
+        int c_it = 0, b_it = 0, b_rem = 0, b_start = 0;
+        auto issue_c = [&]() {
+            if (lane == 0) c_it = atomicAdd(&A.misc[BM_WORK], 1);
+        };
+        auto load_b = [&]() {
+            b_it = __shfl_sync(0xffffffffu, c_it, 0);
+            if (b_it < A.ntiles) {
+                b_rem   = A.count_in[b_it];
+                b_start = A.start_in[b_it];
+            }
+        };
+        issue_c();
+        load_b();
+        issue_c();
         for (unsigned seq = 0;; ++seq) {
             const int st = seq & 1;
             mbar_wait(&s.empty[st], ((seq >> 1) & 1) ^ 1);
             while (rem == 0) {
-                int it = 0;
-                if (lane == 0) it = atomicAdd(&A.misc[BM_WORK], 1);
-                it = __shfl_sync(0xffffffffu, it, 0);
+                const int it = b_it;
                 if (it < A.ntiles) {
-                    rem  = A.count_in[it];
-                    pbeg = A.start_in[it];
-                    kind = CH_TILE;
+                    rem   = b_rem;
+                    pbeg  = b_start;
+                    kind  = CH_TILE;
+                    fresh = rem > 0;
                     hx   = it % A.ntx;
                     hy   = (it / A.ntx) % A.nty;
                     hz   = it / (A.ntx * A.nty);
@@ -275,6 +294,8 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
                     pbeg = (long)tail_start + off;
                     kind = CH_TAIL;
                 }
+                load_b();
+                issue_c();
             }
             if (kind == CH_STOP) {
                 if (lane == 0) {
@@ -287,13 +308,17 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
             if (lane == 0) {
                 ChunkDesc d;
                 d.kind = kind; d.cnt = cnt; d.hx = hx; d.hy = hy; d.hz = hz;
+                d.epi  = epi ^ (fresh ? 1 : 0);
                 s.desc[st] = d;
                 const uint32_t bytes = (uint32_t)(((cnt + 1) & ~1) * 8);
                 mbar_expect_tx(&s.full[st], 6 * bytes);
 #pragma unroll
                 for (int a = 0; a < 6; ++a) bulk_g2s(&s.st[st].dat[a][0], A.in[a] + pbeg, bytes, &s.full[st]);
             }
-            if (kind == CH_TILE) {
+            if (kind == CH_TILE && fresh) {
+                // (safe to overwrite: the window of two tiles ago is dead once the stage of chunk seq - 2 was released)
+                epi ^= 1;
+                fresh = false;
                 // E window of the tile as x-pairs: ep[c][kz][jy][ix] = (E_c(node ix), E_c(node ix+1)); node (0,0,0)
                 // is the lower node of the tile's first cell, ghosted index = 4*h + nghost - 1
                 const int gx0 = 4 * hx + A.m.nghost - 1, gy0 = 4 * hy + A.m.nghost - 1,
@@ -307,7 +332,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
                         if (gx < A.m.ex) v.x = __ldg(&A.ef[base]);
                         if (gx + 1 < A.m.ex) v.y = __ldg(&A.ef[base + 3]);
                     }
-                    s.st[st].ep[e] = v;
+                    s.ep[epi][e] = v;
                 }
             }
             __syncwarp();
@@ -348,121 +373,146 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
                 }
             }
             fence_proxy_async();
-            consumer_sync<NT>();
-            if (t == 0) mbar_arrive(&s.empty[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty[st]);
             continue;
         }
 
         const int wox = D.hx * TILE - WH, woy = D.hy * TILE - WH, woz = D.hz * TILE - WH;
         // ---- P1: gather, push, bin by new cell ------------------------------------------------------------
+        {
+            const double2* ep = s.ep[D.epi];
 #pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            const int slot = k * NT + t;
-            unsigned short loc = NOSLOT, rk = 0;
-            if (slot < cnt) {
-                double r[3] = {G.dat[0][slot], G.dat[1][slot], G.dat[2][slot]};
-                double p[3] = {G.dat[3][slot], G.dat[4][slot], G.dat[5][slot]};
-                Cic c;
-                cic_setup(A.m, r[0], r[1], r[2], c);
-                double E[3];
-                gather_pairs(G.ep, c.a[0] - A.m.nghost - D.hx * TILE, c.a[1] - A.m.nghost - D.hy * TILE,
-                             c.a[2] - A.m.nghost - D.hz * TILE, c.whi, E);
-                push_particle(A.P, r, p, E);
-                Cic cn;
-                cic_setup(A.m, r[0], r[1], r[2], cn);
-                const int cc[3] = {cn.a[0] - A.m.nghost, cn.a[1] - A.m.nghost, cn.a[2] - A.m.nghost};
-                if (!owned_by_me(A, r, cc)) {
-                    place_exit(A, r, p);
-                } else {
-                    const int wx = cc[0] - wox, wy = cc[1] - woy, wz = cc[2] - woz;
-                    if ((unsigned)wx < (unsigned)WIN && (unsigned)wy < (unsigned)WIN && (unsigned)wz < (unsigned)WIN) {
-                        int sx, lx, dx, sy, ly, dy, sz, lz, dz;
-                        win_seg(wx, sx, lx, dx);
-                        win_seg(wy, sy, ly, dy);
-                        win_seg(wz, sz, lz, dz);
-                        const int id = s.tsbase[sx + 3 * (sy + 3 * sz)] + (lz * dy + ly) * dx + lx;
-                        loc          = (unsigned short)id;
-                        rk           = (unsigned short)atomicAdd(&s.hist[id], 1);
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            G.dat[d][slot]     = r[d];
-                            G.dat[3 + d][slot] = p[d];
-                        }
+            for (int k = 0; k < K; ++k) {
+                const int slot = k * NT + t;
+                unsigned short loc = NOSLOT, rk = 0;
+                if (slot < cnt) {
+                    double r[3] = {G.dat[0][slot], G.dat[1][slot], G.dat[2][slot]};
+                    double p[3] = {G.dat[3][slot], G.dat[4][slot], G.dat[5][slot]};
+                    Cic c;
+                    cic_setup(A.m, r[0], r[1], r[2], c);
+                    double E[3];
+                    gather_pairs(ep, c.a[0] - A.m.nghost - D.hx * TILE, c.a[1] - A.m.nghost - D.hy * TILE,
+                                 c.a[2] - A.m.nghost - D.hz * TILE, c.whi, E);
+                    push_particle(A.P, r, p, E);
+                    Cic cn;
+                    cic_setup(A.m, r[0], r[1], r[2], cn);
+                    const int cc[3] = {cn.a[0] - A.m.nghost, cn.a[1] - A.m.nghost, cn.a[2] - A.m.nghost};
+                    if (!owned_by_me(A, r, cc)) {
+                        place_exit(A, r, p);
                     } else {
-                        place_direct(A, r, p, cc, cn.whi);
+                        const int wx = cc[0] - wox, wy = cc[1] - woy, wz = cc[2] - woz;
+                        if ((unsigned)wx < (unsigned)WIN && (unsigned)wy < (unsigned)WIN &&
+                            (unsigned)wz < (unsigned)WIN) {
+                            const int id = s.winid[(wz * WIN + wy) * WIN + wx];
+                            loc          = (unsigned short)id;
+                            rk           = (unsigned short)atomicAdd(&s.hist[id], 1);
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                G.dat[d][slot]     = r[d];
+                                G.dat[3 + d][slot] = p[d];
+                            }
+                        } else {
+                            place_direct(A, r, p, cc, cn.whi);
+                        }
                     }
                 }
+                s.local[slot] = loc;
+                s.rank[slot]  = rk;
             }
-            s.local[slot] = loc;
-            s.rank[slot]  = rk;
         }
         consumer_sync<NT>();
-        // ---- P2: exclusive scan of the window histogram (tile-major ids) -----------------------------------
-        {
-            constexpr int IPT = (WIN_CELLS + NT - 1) / NT;
-            int v[IPT], sum = 0;
-#pragma unroll
-            for (int j = 0; j < IPT; ++j) {
-                const int c = t * IPT + j;
-                v[j]        = c < WIN_CELLS ? s.hist[c] : 0;
-                sum += v[j];
-            }
-            int inc = sum;
+        // ---- P2: exclusive scan of the window histogram (tile-major ids), 2 cells per thread ---------------
+        static_assert(NT >= WIN_CELLS / 2, "the scan uses WIN_CELLS / 2 threads");
+        // value = count | (count > 0) << 16: one scan yields the particle prefix and the ordered list of non-empty cells
+        int v0 = 0, v1 = 0, inc = 0;
+        if (t < WIN_CELLS / 2) {
+            v0 = s.hist[2 * t];
+            v1 = s.hist[2 * t + 1];
+            v0 |= (v0 > 0) << 16;
+            v1 |= (v1 > 0) << 16;
+            inc = v0 + v1;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int y = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += y;
             }
             if (lane == 31) s.warp_sums[warp] = inc;
-            consumer_sync<NT>();
-            if (warp == 0) {
-                int w  = lane < NT / 32 ? s.warp_sums[lane] : 0;
-                int wi = w;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, wi, o);
-                    if (lane >= o) wi += y;
-                }
-                s.warp_sums[lane] = wi - w;  // exclusive
-                if (lane == 31) s.total = wi;
-            }
-            consumer_sync<NT>();
-            int run = s.warp_sums[warp] + inc - sum;
-#pragma unroll
-            for (int j = 0; j < IPT; ++j) {
-                const int c = t * IPT + j;
-                if (c < WIN_CELLS) {
-                    s.prefix[c] = run;
-                    if (v[j] > 0) {
-                        s.list[atomicAdd(&s.nne, 1)] = (unsigned short)c;
-                        s.hist[c]                    = 0;  // ready for the next chunk
-                    }
-                    run += v[j];
-                }
-            }
-            if (t == 0) s.prefix[WIN_CELLS] = s.total;
         }
         consumer_sync<NT>();
-        // ---- reserve one block per destination tile; P3: sorted position -> arrival slot ----------------
+        if (t < WIN_CELLS / 2) {
+            int run = inc - v0 - v1;
+#pragma unroll
+            for (int w = 0; w < WIN_CELLS / 64 - 1; ++w)
+                if (w < warp) run += s.warp_sums[w];
+            s.prefix[2 * t]     = run & 0xFFFF;
+            s.prefix[2 * t + 1] = (run + v0) & 0xFFFF;
+            if (v0 >> 16) {
+                s.list[run >> 16] = (unsigned short)(2 * t);
+                s.hist[2 * t]     = 0;  // ready for the next chunk
+            }
+            if (v1 >> 16) {
+                s.list[(run + v0) >> 16] = (unsigned short)(2 * t + 1);
+                s.hist[2 * t + 1]        = 0;
+            }
+            if (t == WIN_CELLS / 2 - 1) {
+                s.prefix[WIN_CELLS] = (run + v0 + v1) & 0xFFFF;
+                s.nne               = (run + v0 + v1) >> 16;
+            }
+        }
+        consumer_sync<NT>();
+        // ---- reserve one block per destination tile (global atomics, consumed only after the next barrier so
+        //      their latency hides behind P3 and the P4 loads); P3: sorted position -> arrival slot -----------
+        int rs_b0 = 0, rs_n = 0, rs_base = 0, rs_cap = 0, rs_start = 0;
+        bool rs_bad = false;
         if (t < NSLOT) {
-            const int b0 = s.prefix[s.tsbase[t]], b1 = s.prefix[s.tsbase[t + 1]];
-            const int n  = b1 - b0;
-            int adj = 0, lim = 0, tadj = 0;
-            if (n > 0) {
+            rs_b0 = s.prefix[s.tsbase[t]];
+            rs_n  = s.prefix[s.tsbase[t + 1]] - rs_b0;
+            if (rs_n > 0) {
                 const int tx = D.hx + (t % 3) - 1, ty = D.hy + ((t / 3) % 3) - 1, tz = D.hz + (t / 9) - 1;
-                if (tx < 0 || tx >= A.ntx || ty < 0 || ty >= A.nty || tz < 0 || tz >= A.ntz) {
-                    atomicOr(&A.misc[BM_FLAGS], IPPLB_FLAG_INTERNAL);
-                    lim  = 0;  // everything of this block is dropped
-                    tadj = INT_MIN;
-                } else {
+                rs_bad = tx < 0 || tx >= A.ntx || ty < 0 || ty >= A.nty || tz < 0 || tz >= A.ntz;
+                if (!rs_bad) {
                     const int tile = tx + A.ntx * (ty + A.nty * tz);
-                    const int base = atomicAdd(&A.cursor_out[tile], n);
-                    const int cap  = A.cap_out[tile];
-                    const int abs0 = A.start_out[tile] + base;
-                    adj            = abs0 - b0;
-                    lim            = A.start_out[tile] + cap;
+                    rs_base        = atomicAdd(&A.cursor_out[tile], rs_n);
+                    rs_cap         = A.cap_out[tile];
+                    rs_start       = A.start_out[tile];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int slot           = k * NT + t;
+            const unsigned short loc = s.local[slot];
+            if (loc != NOSLOT) s.perm[s.prefix[loc] + s.rank[slot]] = (unsigned short)slot;
+        }
+        consumer_sync<NT>();
+        // ---- P4: sorted order -> registers (random shared-memory reads) ----------------------------------------
+        const int ntot = s.prefix[WIN_CELLS];
+        double pr[K][6];
+        int pts[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = k * NT + t;
+            pts[k]      = -1;
+            if (p < ntot) {
+                const int slot = s.perm[p];
+                pts[k]         = s.tsof[s.local[slot]];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) pr[k][a] = G.dat[a][slot];
+            }
+        }
+        if (t < NSLOT) {
+            int adj = 0, lim = 0, tadj = 0;
+            if (rs_n > 0) {
+                if (rs_bad) {
+                    atomicOr(&A.misc[BM_FLAGS], IPPLB_FLAG_INTERNAL);
+                    tadj = INT_MIN;  // lim = 0: everything of this block is dropped
+                } else {
+                    const int abs0 = rs_start + rs_base;
+                    adj            = abs0 - rs_b0;
+                    lim            = rs_start + rs_cap;
                     const int g0   = max(lim, abs0);  // first absolute slot that does not fit
-                    const int over = abs0 + n - g0;
+                    const int over = abs0 + rs_n - g0;
                     if (over > 0) {
                         const int tb = A.state_out[BS_TAIL_START] + atomicAdd(&A.state_out[BS_TAIL_COUNT], over);
                         tadj         = tb - g0;
@@ -477,117 +527,101 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
             s.lim[t]  = lim;
             s.tadj[t] = tadj;
         }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int slot           = k * NT + t;
-            const unsigned short loc = s.local[slot];
-            if (loc != NOSLOT) s.perm[s.prefix[loc] + s.rank[slot]] = (unsigned short)slot;
-        }
         consumer_sync<NT>();
-        // ---- P4: coalesced write-out in sorted order; weights of the new position ------------------------
-        const int ntot = s.total;
-        int gdst[K], src[K];
+        // ---- coalesced store into next step's buckets; CIC weights of the new positions, sorted order --------
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int p = k * NT + t;
-            gdst[k]     = -1;
-            src[k]      = 0;
-            if (p < ntot) {
-                const int slot = s.perm[p];
-                const int ts   = s.tsof[s.local[slot]];
-                int g          = s.adj[ts] + p;
+            if (pts[k] >= 0) {
+                const int ts = pts[k];
+                int g        = s.adj[ts] + p;
                 if (g >= s.lim[ts]) {
                     const int ta = s.tadj[ts];
                     g            = ta == INT_MIN ? -1 : g + ta;
                 }
-                src[k]  = slot;
-                gdst[k] = g;  // negative: dropped (flag already raised)
-                if (g >= 0) {
-                    A.out[3][g] = G.dat[3][slot];
-                    A.out[4][g] = G.dat[4][slot];
-                    A.out[5][g] = G.dat[5][slot];
-                }
-            }
-        }
-        consumer_sync<NT>();
+                if (g >= 0) {  // negative: dropped (flag already raised)
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int p = k * NT + t;
-            if (p < ntot) {
-                const int slot = src[k];
-                const double r0 = G.dat[0][slot], r1 = G.dat[1][slot], r2 = G.dat[2][slot];
-                const int g = gdst[k];
-                if (g >= 0) {
-                    A.out[0][g] = r0;
-                    A.out[1][g] = r1;
-                    A.out[2][g] = r2;
+                    for (int a = 0; a < 6; ++a) A.out[a][g] = pr[k][a];
                 }
                 int idx;
                 double w0, w1, w2;
-                cic_axis(r0, A.m.origin[0], A.m.invdx[0], idx, w0);
-                cic_axis(r1, A.m.origin[1], A.m.invdx[1], idx, w1);
-                cic_axis(r2, A.m.origin[2], A.m.invdx[2], idx, w2);
+                cic_axis(pr[k][0], A.m.origin[0], A.m.invdx[0], idx, w0);
+                cic_axis(pr[k][1], A.m.origin[1], A.m.invdx[1], idx, w1);
+                cic_axis(pr[k][2], A.m.origin[2], A.m.invdx[2], idx, w2);
                 G.dat[3][p] = w0;
                 G.dat[4][p] = w1;
                 G.dat[5][p] = w2;
             }
         }
         consumer_sync<NT>();
-        // ---- P5: deposit, two lanes per non-empty cell -----------------------------------------------------
+        // ---- P5: deposit, one lane per non-empty cell (list is in tile-major id order: the 64 home cells, which hold
+        //      most particles, are neighbours in the list, so the lanes of a warp run similar trip counts).  The eight
+        //      node sums follow from eight moments of the weights: 4 multiplies + 7 adds per particle.
         {
-            const int nitems = s.nne * 2;
-            const int nround = (nitems + 31) & ~31;
-            for (int j = t; j < nround; j += NT) {
-                const bool valid = j < nitems;
-                const int id     = valid ? s.list[j >> 1] : 0;
-                const int g      = j & 1;
-                const int b = valid ? s.prefix[id] + g : 0, e = valid ? s.prefix[id + 1] : 0;
-                double acc[8];
-#pragma unroll
-                for (int n = 0; n < 8; ++n) acc[n] = 0.0;
-                for (int p = b; p < e; p += 2) {
+            const int nne = s.nne;
+            for (int j = t; j < nne; j += NT) {
+                const int id = s.list[j];
+                const int b = s.prefix[id], e = s.prefix[id + 1];
+                double s1 = 0.0, s2 = 0.0, s3 = 0.0, s12 = 0.0, s13 = 0.0, s23 = 0.0, s123 = 0.0;
+                for (int p = b; p < e; ++p) {
                     const double w0 = G.dat[3][p], w1 = G.dat[4][p], w2 = G.dat[5][p];
-                    const double u0 = 1.0 - w0, u1 = 1.0 - w1, u2 = 1.0 - w2;
-                    const double t00 = w1 * w2, t10 = u1 * w2, t01 = w1 * u2, t11 = u1 * u2;
-                    acc[0] += w0 * t00;
-                    acc[1] += u0 * t00;
-                    acc[2] += w0 * t10;
-                    acc[3] += u0 * t10;
-                    acc[4] += w0 * t01;
-                    acc[5] += u0 * t01;
-                    acc[6] += w0 * t11;
-                    acc[7] += u0 * t11;
+                    const double w01 = w0 * w1;
+                    s1 += w0;
+                    s2 += w1;
+                    s3 += w2;
+                    s12 += w01;
+                    s13 += w0 * w2;
+                    s23 += w1 * w2;
+                    s123 += w01 * w2;
                 }
-                // pair exchange: lane g = 0 finishes nodes 0..3, lane g = 1 nodes 4..7
+                const double cnt = (double)(e - b);
+                double nd[8];  // node n: bit d set -> lower node along d (weight 1 - w_d)
+                nd[0] = s123;
+                nd[1] = s23 - s123;
+                nd[2] = s13 - s123;
+                nd[3] = (s3 - s13) - (s23 - s123);
+                nd[4] = s12 - s123;
+                nd[5] = (s2 - s12) - (s23 - s123);
+                nd[6] = (s1 - s12) - (s13 - s123);
+                nd[7] = ((cnt - s1) - (s2 - s12)) - ((s3 - s13) - (s23 - s123));
+                const unsigned xyz = s.cellxyz[id];
+                const int a[3]     = {(int)(xyz & 15) + wox + A.m.nghost, (int)((xyz >> 4) & 15) + woy + A.m.nghost,
+                                      (int)(xyz >> 8) + woz + A.m.nghost};
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                    const double give = g ? acc[n] : acc[4 + n];
-                    const double got  = __shfl_xor_sync(0xffffffffu, give, 1);
-                    const double mine = (g ? acc[4 + n] : acc[n]) + got;
-                    if (g) acc[4 + n] = mine; else acc[n] = mine;
-                }
-                if (valid) {
-                    const unsigned xyz = s.cellxyz[id];
-                    const int a[3]     = {(int)(xyz & 15) + wox + A.m.nghost, (int)((xyz >> 4) & 15) + woy + A.m.nghost,
-                                          (int)(xyz >> 8) + woz + A.m.nghost};
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-                        const int node = 4 * g + n;
-                        atomicAdd(&A.rho[cic_node(A.m, a, node)], A.q * (g ? acc[4 + n] : acc[n]));
-                    }
-                }
+                for (int n = 0; n < 8; ++n) atomicAdd(&A.rho[cic_node(A.m, a, n)], A.q * nd[n]);
             }
         }
+        // every consumer releases the stage on its own (no CTA barrier between chunks): the next chunk's P1 only
+        // touches the other stage, hist (already reset) and local / rank (dead since P4)
         fence_proxy_async();
-        consumer_sync<NT>();
-        if (t == 0) {
-            s.nne = 0;
-            mbar_arrive(&s.empty[st]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[st]);
     }
 }
 
-constexpr int F_NT = 384, F_K = 2, F_MINB = 2;
+template <int NT, int K, int MINB>
+static int launch_fused(ipplb_ctx* ctx, const StepArgs& A) {
+    using S   = StepSmem<NT, K>;
+    auto kern = fused_step_kernel<NT, K, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IPPLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
+        attr_set = true;
+    }
+    kern<<<ctx->num_sms * MINB, NT + 32, sizeof(S), ctx->stream>>>(A);
+    IPPLB_CHECK_LAUNCH(ctx);
+    return IPPLB_OK;
+}
+
+// tuning knob (experiments only): IPPLB_FUSED_CFG selects the CTA shape; the default is the measured best
+static int fused_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("IPPLB_FUSED_CFG");
+        cfg           = e ? atoi(e) : 0;
+    }
+    return cfg;
+}
 
 }  // namespace ipplb
 
@@ -636,16 +670,17 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         A.rmax[d] = region_max ? region_max[d] : 0.0;
     }
     IPPLB_CUDA(cudaMemsetAsync(b->misc(), 0, sizeof(int) * 4, ctx->stream));
-    using S   = StepSmem<F_NT, F_K>;
-    auto kern = fused_step_kernel<F_NT, F_K, F_MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IPPLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
-        attr_set = true;
+    int rc;
+    switch (fused_cfg()) {
+        case 1: rc = launch_fused<256, 2, 3>(ctx, A); break;
+        case 2: rc = launch_fused<512, 2, 1>(ctx, A); break;
+        case 3: rc = launch_fused<768, 2, 1>(ctx, A); break;
+        case 4: rc = launch_fused<256, 2, 2>(ctx, A); break;
+        default: rc = launch_fused<384, 2, 2>(ctx, A); break;
     }
-    kern<<<ctx->num_sms * F_MINB, F_NT + 32, sizeof(S), ctx->stream>>>(A);
-    IPPLB_CHECK_LAUNCH(ctx);
-    int rc = bins_plan(ctx, b, o);
+    if (rc) return rc;
+    rc = bins_plan(ctx, b, o);
+
     if (rc) return rc;
     b->cur        = o;
     nxt->q        = nullptr;
