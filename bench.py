@@ -194,7 +194,7 @@ def main():
         parts.arr[k][:n_local].normal_(0.0, 1.0, generator=g)
     parts.n = n_local
     off = ctx.offsets_buffer(mesh)
-    bins = ib.Bins(ctx, mesh, cap) if (world == 1 and args.mode == 2) else None
+    bins = ib.Bins(ctx, mesh, cap) if args.mode == 2 else None
     rho, ef = ctx.field(mesh), ctx.field(mesh, 3)
 
     # ---- self-consistent E from one solve (single GPU); synthetic smooth E on N > 1 (solver is non-owned)
@@ -223,11 +223,23 @@ def main():
         else:
             ctx.halo_fill_periodic(mesh, ef, 3)
 
+    exit_cap = max(n_local // 16, 1 << 16)
+    exit_buf = torch.zeros(6 * exit_cap, dtype=torch.float64, device=dev) if (bins is not None and world > 1) else None
+    region = list(reg) if world > 1 else None
+
     def step(first=False):
         fill_e_halo()
         push = ib.leapfrog_push(dt, kick2=0 if first else 1)
-        if world == 1:
-            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=args.mode, bins=bins)
+        if bins is not None and world == 1:
+            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=2, bins=bins)
+        elif bins is not None:
+            # fused step with ownership test -> NCCL migration (arrivals appended + deposited) -> accumulateHalo
+            ctx.field_fill(rho, 0.0)
+            bins.step(push, parts, scratch, ef, rho, exit_buf=exit_buf, region=region)
+            bins.migrate(parts, exit_buf, rho)
+            ctx.halo_exchange(rho, 1, "accumulate")
+        elif world == 1:
+            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=args.mode)
         else:
             ctx.gather_push(mesh, push, parts, ef)
             ctx.update(parts)
@@ -266,7 +278,7 @@ def main():
     launches = ctx.launches - l0
     clocks = sampler.stop() if rank == 0 else None
     ms = t0.elapsed_time(t1)
-    n_now = parts.n
+    n_now = bins.status()[0] if bins is not None else parts.n
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -295,15 +307,23 @@ def main():
     ncell_int = mesh.nl[0] * mesh.nl[1] * mesh.nl[2]
     if bins is not None:
         nloc, ntail, nexit, flags = bins.status()
-        assert nloc == n_local and nexit == 0 and (flags & 7) == 0, f"fused store lost particles: {bins.status()}"
-        kern["fused_step"] = timed(lambda: bins.step(push, parts, scratch, ef, rho), reps=5)
+        assert (flags & 7) == 0 and (world > 1 or (nloc == n_local and nexit == 0)), f"fused store lost particles: {bins.status()}"
+        if world == 1:
+            kern["fused_step"] = timed(lambda: bins.step(push, parts, scratch, ef, rho), reps=5)
+        else:
+            def fused_and_migrate():
+                bins.step(push, parts, scratch, ef, rho, exit_buf=exit_buf, region=region)
+                bins.migrate(parts, exit_buf, rho)
+            t_all = timed(fused_and_migrate, reps=3)
+            kern["fused_step+migrate"] = t_all
+            kern["fused_step"] = t_all  # (the migration part is host-synchronous; see halo/migrate split below)
         kern["rho_zero"] = timed(lambda: ctx.field_fill(rho, 0.0))
         kern["halo_accumulate"] = timed(lambda: ctx.halo_accumulate_periodic(mesh, rho))
         kern["halo_fill_E"] = timed(fill_e_halo)
         rk = "fused_step"
         # the fused kernel does all per-particle work of the step: SURVEY 8d algorithmic bytes, 120 B/particle
         # (96 gather+push, 24 scatter with a uniform scalar charge) + E read and rho written once per cell
-        alg_bytes = {rk: float(BYTES_PER_PARTICLE_STEP) * n_local + 32.0 * ncell_int}
+        alg_bytes = {rk: float(BYTES_PER_PARTICLE_STEP) * nloc + 32.0 * ncell_int}
         dom = rk
         tail_frac = ntail / max(nloc, 1)
     else:

@@ -254,6 +254,13 @@ int ipplb_bins_status(ipplb_ctx* ctx, ipplb_bins* bins, long* n_local, long* n_t
 /* Appends `count` particles (device SoA pointers src[6]) to the tail of `cur` (migration arrivals). */
 int ipplb_bins_append(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, const double* const src[6],
                       long count);
+/* ParticleSpatialLayout::update for the bucketed store (src/Particle/ParticleSpatialLayout.hpp:115-314): the
+ * leavers the last ipplb_bins_step wrote to exit_buf get their destination rank (reference search order incl.
+ * the inclusive fallback, :372-395), are exchanged over NCCL and appended to the tail of `cur`; arrivals are
+ * deposited into rho (may be NULL).  Updates cur->n; per-rank counts in sent_host / recv_host (may be NULL).
+ * Synchronises the stream.  With one rank it only refreshes cur->n. */
+int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, const double* exit_buf,
+                       int exit_cap, double* rho, long* sent_host, long* recv_host);
 /* Contiguous copy (bucket order, then tail) of the bucketed `cur` into out[0..n). Sets out->n (syncs). */
 int ipplb_bins_compact(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* cur,
                        ipplb_particles* out);

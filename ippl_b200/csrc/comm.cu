@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "bins.h"
 #include "cic.cuh"
 #include "layout.h"
 
@@ -107,7 +108,8 @@ __device__ __forceinline__ bool in_region_incl(const double* __restrict__ R, dou
 __global__ void __launch_bounds__(256)
 locate_kernel(const double* __restrict__ regions, int nranks, int me, long n,
               const double* __restrict__ x, const double* __restrict__ y,
-              const double* __restrict__ z, int* __restrict__ dest, int* __restrict__ counts) {
+              const double* __restrict__ z, int* __restrict__ dest, int* __restrict__ counts,
+              int count_self = 0) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long)gridDim.x * blockDim.x) {
         const double px = x[i], py = y[i], pz = z[i];
@@ -119,7 +121,7 @@ locate_kernel(const double* __restrict__ regions, int nranks, int me, long n,
             if (in_region_incl(regions + 6 * r, px, py, pz)) d = r;
         if (d < 0) d = me;
         dest[i] = d;
-        if (d != me) atomicAdd(&counts[d], 1);
+        if (d != me || count_self) atomicAdd(&counts[d], 1);
     }
 }
 
@@ -135,11 +137,11 @@ struct AttrPtrs {
 __global__ void __launch_bounds__(256)
 pack_leavers_kernel(long n, int me, const int* __restrict__ dest, const int* __restrict__ send_off,
                     const int* __restrict__ send_cnt, int* __restrict__ cursor, AttrPtrs A,
-                    double* __restrict__ sendbuf, int* __restrict__ holes) {
+                    double* __restrict__ sendbuf, int* __restrict__ holes, int pack_self = 0) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long)gridDim.x * blockDim.x) {
         const int d = dest[i];
-        if (d == me) continue;
+        if (d == me && !pack_self) continue;
         const int k   = atomicAdd(&cursor[d], 1);
         const long b  = (long)send_off[d] * A.n;
         const int cnt = send_cnt[d];
@@ -465,6 +467,98 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
         IPPLB_CHECK_LAUNCH(ctx);
     }
     p->n = n_new;
+    return IPPLB_OK;
+}
+
+// Migration for the bucketed store: the fused step already applied the BC and the ownership test and left
+// the leavers in exit_buf; here they get their destination rank (same search order as ipplb_update), travel as
+// SoA segments over NCCL, and the arrivals are appended to the tail of `cur` and deposited into rho (the
+// reference scatters after update(), so arrivals belong to this step's rho: AlpineManager.h:157-175).
+int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, const double* exit_buf,
+                       int exit_cap, double* rho, long* sent_host, long* recv_host) {
+    IPPLB_REQUIRE(ctx && b && cur, "bins_migrate: bad arguments");
+    const int nr = ctx->nranks, me = ctx->rank;
+    if (sent_host) std::fill(sent_host, sent_host + nr, 0L);
+    if (recv_host) std::fill(recv_host, recv_host + nr, 0L);
+    long n_local = 0, n_exit = 0;
+    int flags = 0, rc;
+    if ((rc = ipplb_bins_status(ctx, b, &n_local, nullptr, &n_exit, &flags))) return rc;
+    if (flags & (IPPLB_FLAG_EXIT_OVERFLOW | IPPLB_FLAG_CAPACITY | IPPLB_FLAG_INTERNAL)) {
+        set_error("bins_migrate: the last fused step raised flags 0x%x (exit buffer %d, capacity %ld)", flags,
+                  exit_cap, b->capacity);
+        return IPPLB_ERR_CAPACITY;
+    }
+    cur->n = n_local;
+    if (nr < 2) {
+        IPPLB_REQUIRE(n_exit == 0, "bins_migrate: leavers on a single rank");
+        return IPPLB_OK;
+    }
+    CommPlan* P = (CommPlan*)ctx->plan;
+    IPPLB_REQUIRE(P && ctx->nccl && exit_buf, "bins_migrate: no layout/communicator/exit buffer bound");
+    const long n = n_exit;
+    if (P->dest_cap < n + 1) {
+        if (P->d_dest) { IPPLB_CUDA(cudaStreamSynchronize(ctx->stream)); IPPLB_CUDA(cudaFree(P->d_dest)); }
+        P->dest_cap = n + n / 4 + 1024;
+        IPPLB_CUDA(cudaMalloc(&P->d_dest, sizeof(int) * P->dest_cap));
+    }
+    int* cnt = P->d_counts;    // [nr] send counts (own rank included: inclusive-fallback hits stay here)
+    int* cursor = cnt + nr;    // [nr]
+    int* soff = cnt + 2 * nr;  // [nr+1]
+    IPPLB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (4 * nr + 16), ctx->stream));
+    const double* ex[6];
+    for (int a = 0; a < 6; ++a) ex[a] = exit_buf + (size_t)a * exit_cap;
+    if (n > 0) {
+        locate_kernel<<<grid1d(n), 256, 0, ctx->stream>>>(P->d_regions, nr, me, n, ex[0], ex[1], ex[2], P->d_dest,
+                                                          cnt, 1);
+        IPPLB_CHECK_LAUNCH(ctx);
+    }
+    IPPLB_NCCL(ncclAllGather(cnt, P->d_matrix, nr, ncclInt, (ncclComm_t)ctx->nccl, ctx->stream));
+    ctx->launches++;
+    IPPLB_CUDA(cudaMemcpyAsync(P->h_matrix, P->d_matrix, sizeof(int) * nr * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> h_soff(nr + 1, 0), h_roff(nr + 1, 0), h_rcnt(nr, 0), h_scnt(nr, 0);
+    for (int r = 0; r < nr; ++r) {
+        h_scnt[r] = P->h_matrix[me * nr + r];
+        h_rcnt[r] = P->h_matrix[r * nr + me];
+        h_soff[r + 1] = h_soff[r] + h_scnt[r];
+        h_roff[r + 1] = h_roff[r] + h_rcnt[r];
+        if (sent_host) sent_host[r] = r == me ? 0 : h_scnt[r];
+        if (recv_host) recv_host[r] = r == me ? 0 : h_rcnt[r];
+    }
+    const int nh = h_soff[nr], na = h_roff[nr];
+    if (nh == 0 && na == 0) return IPPLB_OK;
+    AttrPtrs A;
+    A.n = 6;
+    for (int a = 0; a < 6; ++a) A.a[a] = const_cast<double*>(ex[a]);
+    if ((rc = ensure(ctx, ctx->send, sizeof(double) * ((size_t)nh * 6 + 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->recv, sizeof(double) * ((size_t)na * 6 + 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->misc, sizeof(int) * ((size_t)nh + 64)))) return rc;
+    double* sb = (double*)ctx->send.ptr; double* rb = (double*)ctx->recv.ptr;
+    IPPLB_CUDA(cudaMemcpyAsync(soff, h_soff.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nh > 0) {
+        pack_leavers_kernel<<<grid1d(n), 256, 0, ctx->stream>>>(n, me, P->d_dest, soff, cnt, cursor, A, sb,
+                                                                (int*)ctx->misc.ptr, 1);
+        IPPLB_CHECK_LAUNCH(ctx);
+    }
+    IPPLB_NCCL(ncclGroupStart());
+    for (int r = 0; r < nr; ++r) {
+        if (r == me) continue;
+        if (h_scnt[r]) IPPLB_NCCL(ncclSend(sb + (size_t)h_soff[r] * 6, (size_t)h_scnt[r] * 6, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
+        if (h_rcnt[r]) IPPLB_NCCL(ncclRecv(rb + (size_t)h_roff[r] * 6, (size_t)h_rcnt[r] * 6, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
+    }
+    IPPLB_NCCL(ncclGroupEnd());
+    ctx->launches++;
+    for (int r = 0; r < nr; ++r) {
+        const long c = h_rcnt[r];
+        if (!c) continue;
+        const double* blk = (r == me ? sb + (size_t)h_soff[r] * 6 : rb + (size_t)h_roff[r] * 6);
+        const double* src[6];
+        for (int a = 0; a < 6; ++a) src[a] = blk + (size_t)a * c;
+        if ((rc = ipplb_bins_append(ctx, b, cur, src, c))) return rc;
+        if (rho && (rc = ipplb_scatter_cic(ctx, &b->mesh, 0, c, src[0], src[1], src[2], nullptr, cur->q_scalar,
+                                           nullptr, rho)))
+            return rc;
+    }
     return IPPLB_OK;
 }
 

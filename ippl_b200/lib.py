@@ -367,6 +367,16 @@ class Bins:
         _check(lib().ipplb_bins_append(self.ctx._h, self._h, C.byref(s), arr, C.c_long(count)))
         cur.n += count
 
+    def migrate(self, cur, exit_buf, rho=None):
+        """ipplb_bins_migrate: exchange the leavers of the last step, append + deposit the arrivals"""
+        s = cur.struct()
+        nr = self.ctx.nranks
+        sent, recv = (C.c_long * nr)(), (C.c_long * nr)()
+        cap = 0 if exit_buf is None else exit_buf.numel() // 6
+        _check(lib().ipplb_bins_migrate(self.ctx._h, self._h, C.byref(s), _ptr(exit_buf), cap, _ptr(rho), sent, recv))
+        cur.n = int(s.n)
+        return list(sent), list(recv)
+
     def compact(self, cur, out):
         s, d = cur.struct(), out.struct()
         _check(lib().ipplb_bins_compact(self.ctx._h, self._h, C.byref(s), C.byref(d)))

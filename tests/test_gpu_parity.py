@@ -646,3 +646,20 @@ def test_fused_step_exit_buffer_subdomain(ctx):
     assert np.array_equal(_canon(list(ex)), _canon([a[~stay] for a in Ro]))
     assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
     bins.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_fused_step(world):
+    """The fused step + NCCL migration + halo exchange on `world` GPUs of this box against the oracle
+    (tests/mgpu_check.py under torchrun): bit-exact ownership / counts / particles, rho and E to 1e-12."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(here, "mgpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and f"MGPU_CHECK_OK world={world}" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
