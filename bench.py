@@ -6,8 +6,10 @@
 
 Workload (BASELINE.json configs[1]): LandauDamping, 128^3 cells and 2^27 fp64 particles PER GPU
 (weak scaling: the mesh doubles along x, y, z as N = 2, 4, 8; FieldLayout decomposition), CIC,
-LeapFrog.  A "step" is one pass of the owned path: [fillHalo(E)] -> gather E + kick + kick + drift +
-periodic BC (one fused kernel) -> [particle update] -> cell sort -> rho = 0 -> scatter -> accumulateHalo.
+LeapFrog.  A "step" is one pass of the owned path: fillHalo(E) -> rho = 0 -> ONE fused kernel (gather E +
+kick + kick + drift + periodic BC + re-bucketing + charge deposit, ipplb_bins_step) -> [NCCL migration of
+the leavers, N > 1] -> accumulateHalo(rho).  --mode 1 runs the unfused baseline (gather_push, counting sort,
+sorted scatter).
 The FFT field solve is a non-owned stage: it is run once before the timed region to produce a
 self-consistent E and is timed separately (`solve_ms`).  Inputs (6.4 GB of particles) are far larger
 than the 126 MB L2, so no explicit flush is needed between iterations.
@@ -347,6 +349,9 @@ def main():
         rk = "gather_push"
         tail_frac = None
     achieved = alg_bytes[rk] / (kern[rk] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one fused_step_kernel launch on this exact workload, from the
+    # committed `ncu --set full` capture (profiles/r1_fused_ncu_full.md: 6.608 GB + 6.504 GB); null otherwise
+    traffic = 13.112e9 if (bins is not None and world == 1 and args.log2_particles == 27) else None
     step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * ncell_int
     step_achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
 
@@ -365,7 +370,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes[rk], "ms_per_launch": kern[rk]},
         "step_roofline": {"bytes_per_particle": BYTES_PER_PARTICLE_STEP, "achieved": step_achieved, "peak": peak,
                           "unit": "GB/s", "frac": step_achieved / peak},
