@@ -9,106 +9,153 @@ namespace ipplb {
 
 __device__ __forceinline__ int round16(int v) { return (v + 15) & ~15; }
 
-// ---- planning: one CTA (ntiles is a few 10^4) ------------------------------------------------------------
+// ---- planning (PLAN_CTAS co-resident CTAs with two grid barriers; any number of tiles) ------------------------
 // o = buffer that was just written: its cursor counts every particle that WANTED the tile, including those
 // that overflowed into the tail.  i = the other buffer, planned here as the next output: every bucket gets
 // room for the tile's current total plus slack (the flux through a tile's faces is a few per cent per step).
-__global__ void __launch_bounds__(1024)
-bins_plan_kernel(int nt, const int* __restrict__ cap_o, int* __restrict__ count_o, int* __restrict__ state_o,
-                 int* __restrict__ start_i, int* __restrict__ cap_i, int* __restrict__ count_i,
-                 int* __restrict__ state_i, int* __restrict__ misc, int capacity, int slack_div,
-                 int slack_sqrt, int slack_const, int tail_reserve) {
-    __shared__ long long red[3][32];
-    __shared__ long long tot[3];
-    __shared__ long long wsum[32];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int per = (nt + 1023) / 1024;
-    const int j0 = min(nt, t * per), j1 = min(nt, j0 + per);
-    long long s0 = 0, s1 = 0, nb = 0;
-    for (int j = j0; j < j1; ++j) {
-        const int total = count_o[j];
-        const int c     = min(total, cap_o[j]);
-        count_o[j]      = c;      // particles really stored in the bucket
-        cap_i[j]        = total;  // scratch for the second phase (same thread)
-        s0 += round16(total);
-        s1 += total / slack_div + slack_sqrt * (int)sqrtf((float)total) + slack_const;
-        nb += c;
+constexpr int PLAN_CTAS = 64, PLAN_NT = 256;
+
+struct PlanArgs {
+    int nt;
+    const int* cap_o;
+    int *count_o, *state_o, *start_i, *cap_i, *count_i, *state_i, *misc;
+    long long* scratch;  // [PLAN_CTAS][4] partial sums, then [4] barrier words (as long long)
+    int capacity, slack_div, slack_sqrt, slack_const, tail_reserve;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (atomicAdd(bar, 0u) < target) {
+        }
+        __threadfence();
     }
-    long long v[3] = {s0, s1, nb};
+    __syncthreads();
+}
+
+template <int N>
+__device__ __forceinline__ void block_sum(long long (&v)[N], long long (*red)[PLAN_NT / 32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < N; ++k) {
         long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) red[k][warp] = x;
     }
     __syncthreads();
-    if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            long long x = red[k][lane];
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0) tot[k] = x;
-        }
+    for (int k = 0; k < N; ++k) {
+        long long x = 0;
+        for (int w = 0; w < PLAN_NT / 32; ++w) x += red[k][w];
+        v[k] = x;
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(PLAN_NT) bins_plan_kernel(const PlanArgs a) {
+    __shared__ long long red[3][PLAN_NT / 32];
+    __shared__ long long wsum[PLAN_NT / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, b = blockIdx.x, G = gridDim.x;
+    unsigned int* bar = reinterpret_cast<unsigned int*>(a.scratch + (size_t)PLAN_CTAS * 4);
+    const int per = (a.nt + G - 1) / G;
+    const int j0 = min(a.nt, b * per), j1 = min(a.nt, j0 + per);
+    // phase 1: clamp the counts of the buffer just written, sums for the capacity budget
+    long long v[3] = {0, 0, 0};
+    for (int j = j0 + t; j < j1; j += PLAN_NT) {
+        const int total = a.count_o[j];
+        const int c     = min(total, a.cap_o[j]);
+        a.count_o[j]    = c;      // particles really stored in the bucket
+        a.cap_i[j]      = total;  // scratch for phase 2
+        v[0] += round16(total);
+        v[1] += total / a.slack_div + a.slack_sqrt * (int)sqrtf((float)total) + a.slack_const;
+        v[2] += c;
+    }
+    block_sum(v, red);
+    if (t < 3) a.scratch[b * 4 + t] = v[t];
+    grid_barrier(bar, G);
+    long long tot[3] = {0, 0, 0};
+    for (int g = 0; g < G; ++g) {
+        tot[0] += __ldcg(&a.scratch[g * 4 + 0]);
+        tot[1] += __ldcg(&a.scratch[g * 4 + 1]);
+        tot[2] += __ldcg(&a.scratch[g * 4 + 2]);
+    }
     int flags = 0;
-    const long long avail = (long long)capacity - tail_reserve - tot[0];
+    const long long avail = (long long)a.capacity - a.tail_reserve - tot[0];
     double scale = 1.0;
     if (tot[1] > avail) {
         scale = avail > 0 ? (double)avail / (double)tot[1] : 0.0;
         flags |= IPPLB_FLAG_SLACK_SCALED;
     }
-    long long mine = 0;
-    for (int j = j0; j < j1; ++j) {
-        const int total = cap_i[j];
-        const int slack = total / slack_div + slack_sqrt * (int)sqrtf((float)total) + slack_const;
+    // phase 2: wanted capacities, per-CTA sums
+    long long mine[1] = {0};
+    for (int j = j0 + t; j < j1; j += PLAN_NT) {
+        const int total = a.cap_i[j];
+        const int slack = total / a.slack_div + a.slack_sqrt * (int)sqrtf((float)total) + a.slack_const;
         const int want  = round16(total + (int)(slack * scale));
-        cap_i[j]        = want;
-        mine += want;
+        a.cap_i[j]      = want;
+        mine[0] += want;
     }
-    // block-wide exclusive scan of the per-thread sums
-    long long inc = mine;
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += y;
+    block_sum(mine, red);
+    if (t == 0) a.scratch[b * 4 + 3] = mine[0];
+    grid_barrier(bar + 1, G);
+    long long run = 0, all = 0;
+    for (int g = 0; g < G; ++g) {
+        const long long sgm = __ldcg(&a.scratch[g * 4 + 3]);
+        if (g < b) run += sgm;
+        all += sgm;
     }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        long long w = wsum[lane], wi = w;
+    // phase 3: exclusive scan inside my segment, batches of PLAN_NT tiles
+    for (int base = j0; base < j1; base += PLAN_NT) {
+        const int j    = base + t;
+        const int want = j < j1 ? a.cap_i[j] : 0;
+        long long inc  = want;
         for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += y;
+            const long long y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
         }
-        wsum[lane] = wi - w;
-        if (lane == 31) tot[0] = wi;  // sum of all wants
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        long long off = 0, bt = 0;
+        for (int w = 0; w < PLAN_NT / 32; ++w) {
+            if (w < warp) off += wsum[w];
+            bt += wsum[w];
+        }
+        if (j < j1) {
+            // never plan a bucket beyond the arrays: what does not fit overflows into the tail / is flagged
+            long long s = run + off + inc - want;
+            if (s > a.capacity) s = a.capacity;
+            a.start_i[j] = (int)s;
+            a.cap_i[j]   = (int)(s + want <= a.capacity ? want : a.capacity - s);
+            a.count_i[j] = 0;
+        }
+        run += bt;
+        __syncthreads();
     }
-    __syncthreads();
-    long long run = wsum[warp] + inc - mine;
-    for (int j = j0; j < j1; ++j) {
-        const int want = cap_i[j];
-        // never plan a bucket beyond the arrays: what does not fit overflows into the tail / is flagged
-        const long long s = run < capacity ? run : capacity;
-        start_i[j]        = (int)s;
-        cap_i[j]          = (int)(s + want <= capacity ? want : capacity - s);
-        count_i[j]        = 0;
-        run += want;
-    }
-    if (t == 0) {
-        const long long all = tot[0];
-        if (all > capacity) flags |= IPPLB_FLAG_CAPACITY;
-        state_i[BS_TAIL_START] = (int)(all < capacity ? all : capacity);
-        state_i[BS_TAIL_COUNT] = 0;
+    if (b == 0 && t == 0) {
+        if (all > a.capacity) flags |= IPPLB_FLAG_CAPACITY;
+        a.state_i[BS_TAIL_START] = (int)(all < a.capacity ? all : a.capacity);
+        a.state_i[BS_TAIL_COUNT] = 0;
         // tail of the buffer just written: clamp the cursor to what fitted
-        int tc = state_o[BS_TAIL_COUNT];
-        const int room = capacity - state_o[BS_TAIL_START];
+        int tc         = a.state_o[BS_TAIL_COUNT];
+        const int room = a.capacity - a.state_o[BS_TAIL_START];
         if (tc > room) tc = room > 0 ? room : 0;
-        state_o[BS_TAIL_COUNT] = tc;
-        misc[BM_ST_TOTAL]      = (int)(tot[2] + tc);
-        misc[BM_ST_BUCKETED]   = (int)tot[2];
-        misc[BM_ST_TAIL]       = tc;
-        misc[BM_ST_EXIT]       = misc[BM_EXIT];
-        misc[BM_ST_FLAGS]      = misc[BM_FLAGS] | flags;
+        a.state_o[BS_TAIL_COUNT] = tc;
+        a.misc[BM_ST_TOTAL]      = (int)(tot[2] + tc);
+        a.misc[BM_ST_BUCKETED]   = (int)tot[2];
+        a.misc[BM_ST_TAIL]       = tc;
+        a.misc[BM_ST_EXIT]       = a.misc[BM_EXIT];
+        a.misc[BM_ST_FLAGS]      = a.misc[BM_FLAGS] | flags;
+    }
+    // the last CTA to get here resets the barrier words for the next launch
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 2, 1u) == (unsigned)G - 1) {
+            bar[0] = 0;
+            bar[1] = 0;
+            bar[2] = 0;
+        }
     }
 }
 
@@ -209,11 +256,18 @@ bins_compact_kernel(int nt, const int* __restrict__ start, const int* __restrict
 
 int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o) {
     const int i = 1 - o;
-    const int reserve = (int)(b->capacity / 50) + 1024;
-    bins_plan_kernel<<<1, 1024, 0, ctx->stream>>>(b->ntiles, b->cap(o), b->count(o), b->state(o), b->start(i),
-                                                  b->cap(i), b->count(i), b->state(i), b->misc(),
-                                                  (int)b->capacity, b->slack_div, b->slack_sqrt,
-                                                  b->slack_const, reserve);
+    PlanArgs a;
+    a.nt = b->ntiles;
+    a.cap_o = b->cap(o); a.count_o = b->count(o); a.state_o = b->state(o);
+    a.start_i = b->start(i); a.cap_i = b->cap(i); a.count_i = b->count(i); a.state_i = b->state(i);
+    a.misc = b->misc();
+    a.scratch = b->d_plan;
+    a.capacity = (int)b->capacity;
+    a.slack_div = b->slack_div; a.slack_sqrt = b->slack_sqrt; a.slack_const = b->slack_const;
+    a.tail_reserve = (int)(b->capacity / 50) + 1024;
+    // all PLAN_CTAS CTAs are co-resident (64 <= SM count, launched after the previous kernel of the stream
+    // has drained), which is what the in-kernel grid barriers rely on
+    bins_plan_kernel<<<PLAN_CTAS, PLAN_NT, 0, ctx->stream>>>(a);
     IPPLB_CHECK_LAUNCH(ctx);
     return IPPLB_OK;
 }
@@ -244,6 +298,8 @@ int ipplb_bins_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, long capacity, ipp
     b->capacity = capacity & ~15L;
     cudaError_t e = cudaMalloc(&b->d_tab, sizeof(int) * b->tab_words());
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cell, sizeof(int) * (size_t)(b->ncells + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_plan, sizeof(long long) * (PLAN_CTAS * 4 + 4));
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_plan, 0, sizeof(long long) * (PLAN_CTAS * 4 + 4), ctx->stream);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_status, sizeof(int) * BM_WORDS);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_tab, 0, sizeof(int) * b->tab_words(), ctx->stream);
     if (e != cudaSuccess) {
@@ -259,6 +315,7 @@ int ipplb_bins_destroy(ipplb_bins* b) {
     if (!b) return IPPLB_OK;
     if (b->d_tab) cudaFree(b->d_tab);
     if (b->d_cell) cudaFree(b->d_cell);
+    if (b->d_plan) cudaFree(b->d_plan);
     if (b->h_status) cudaFreeHost(b->h_status);
     delete b;
     return IPPLB_OK;

@@ -24,6 +24,7 @@ struct ipplb_bins {
     bool built    = false;
     int* d_tab    = nullptr;  // start[2][nt] cap[2][nt] count[2][nt] state[2][BS_WORDS] misc[BM_WORDS]
     int* d_cell   = nullptr;  // build scratch: per-cell offsets [ncells + 1]
+    long long* d_plan = nullptr;  // planning kernel scratch (partial sums + grid barrier words)
     int* h_status = nullptr;  // pinned [BM_WORDS]
     // slack = total / slack_div + slack_sqrt * sqrt(total) + slack_const  (elements per bucket)
     int slack_div = 32, slack_sqrt = 4, slack_const = 16;
