@@ -20,6 +20,8 @@ struct PlanArgs {
     const int* cap_o;
     int *count_o, *state_o, *start_i, *cap_i, *count_i, *state_i, *misc;
     long long* scratch;  // [PLAN_CTAS][4] partial sums, then [4] barrier words (as long long)
+    const int* exit_cnt;  // leavers per destination rank
+    int exit_ranks, seg_cap;
     int capacity, slack_div, slack_sqrt, slack_const, tail_reserve;
 };
 
@@ -145,7 +147,13 @@ __global__ void __launch_bounds__(PLAN_NT) bins_plan_kernel(const PlanArgs a) {
         a.misc[BM_ST_TOTAL]      = (int)(tot[2] + tc);
         a.misc[BM_ST_BUCKETED]   = (int)tot[2];
         a.misc[BM_ST_TAIL]       = tc;
-        a.misc[BM_ST_EXIT]       = a.misc[BM_EXIT];
+        int nexit = 0;
+        for (int r = 0; r < a.exit_ranks; ++r) {
+            nexit += a.exit_cnt[r];
+            if (a.exit_cnt[r] > a.seg_cap) flags |= IPPLB_FLAG_EXIT_OVERFLOW;
+        }
+        a.misc[BM_ST_EXIT]       = nexit;
+        a.misc[BM_ST_TAIL_START] = a.state_o[BS_TAIL_START];
         a.misc[BM_ST_FLAGS]      = a.misc[BM_FLAGS] | flags;
     }
     // the last CTA to get here resets the barrier words for the next launch
@@ -254,7 +262,7 @@ bins_compact_kernel(int nt, const int* __restrict__ start, const int* __restrict
     }
 }
 
-int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o) {
+int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o, int seg_cap) {
     const int i = 1 - o;
     PlanArgs a;
     a.nt = b->ntiles;
@@ -262,6 +270,7 @@ int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o) {
     a.start_i = b->start(i); a.cap_i = b->cap(i); a.count_i = b->count(i); a.state_i = b->state(i);
     a.misc = b->misc();
     a.scratch = b->d_plan;
+    a.exit_cnt = b->d_exit_cnt; a.exit_ranks = b->exit_ranks; a.seg_cap = seg_cap;
     a.capacity = (int)b->capacity;
     a.slack_div = b->slack_div; a.slack_sqrt = b->slack_sqrt; a.slack_const = b->slack_const;
     a.tail_reserve = (int)(b->capacity / 50) + 1024;
@@ -300,7 +309,9 @@ int ipplb_bins_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, long capacity, ipp
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cell, sizeof(int) * (size_t)(b->ncells + 1));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_plan, sizeof(long long) * (PLAN_CTAS * 4 + 4));
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_plan, 0, sizeof(long long) * (PLAN_CTAS * 4 + 4), ctx->stream);
-    if (e == cudaSuccess) e = cudaMallocHost(&b->h_status, sizeof(int) * BM_WORDS);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_exit_cnt, sizeof(int) * MAX_RANKS);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_exit_cnt, 0, sizeof(int) * MAX_RANKS, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_status, sizeof(int) * (BM_WORDS + MAX_RANKS));
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_tab, 0, sizeof(int) * b->tab_words(), ctx->stream);
     if (e != cudaSuccess) {
         set_error("bins_create: %s", cudaGetErrorString(e));
@@ -316,6 +327,7 @@ int ipplb_bins_destroy(ipplb_bins* b) {
     if (b->d_tab) cudaFree(b->d_tab);
     if (b->d_cell) cudaFree(b->d_cell);
     if (b->d_plan) cudaFree(b->d_plan);
+    if (b->d_exit_cnt) cudaFree(b->d_exit_cnt);
     if (b->h_status) cudaFreeHost(b->h_status);
     delete b;
     return IPPLB_OK;

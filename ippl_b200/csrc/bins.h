@@ -6,10 +6,11 @@ namespace ipplb {
 
 // per-buffer state words (device): where the unsorted tail starts and how many particles it holds
 enum { BS_TAIL_START = 0, BS_TAIL_COUNT = 1, BS_WORDS = 8 };
+constexpr int MAX_RANKS = 64;  // ranks of one NVSwitch domain the exit buffer is segmented for
 // misc words (device): step scratch [0..3] (zeroed before every step) and the status block the plan kernel writes
 enum {
     BM_WORK = 0, BM_EXIT = 1, BM_FLAGS = 2, BM_SPARE = 3,
-    BM_ST_TOTAL = 8, BM_ST_TAIL = 9, BM_ST_EXIT = 10, BM_ST_FLAGS = 11, BM_ST_BUCKETED = 12,
+    BM_ST_TOTAL = 8, BM_ST_TAIL = 9, BM_ST_EXIT = 10, BM_ST_FLAGS = 11, BM_ST_BUCKETED = 12, BM_ST_TAIL_START = 13,
     BM_WORDS = 16
 };
 
@@ -25,6 +26,8 @@ struct ipplb_bins {
     int* d_tab    = nullptr;  // start[2][nt] cap[2][nt] count[2][nt] state[2][BS_WORDS] misc[BM_WORDS]
     int* d_cell   = nullptr;  // build scratch: per-cell offsets [ncells + 1]
     long long* d_plan = nullptr;  // planning kernel scratch (partial sums + grid barrier words)
+    int* d_exit_cnt = nullptr;    // [MAX_RANKS] leavers per destination rank of the last step
+    int exit_ranks  = 1;          // how many of them the last step used
     int* h_status = nullptr;  // pinned [BM_WORDS]
     // slack = total / slack_div + slack_sqrt * sqrt(total) + slack_const  (elements per bucket)
     int slack_div = 32, slack_sqrt = 4, slack_const = 16;
@@ -40,5 +43,5 @@ struct ipplb_bins {
 namespace ipplb {
 // clamps count[o] to cap[o], plans start/cap of the other buffer from the totals, zeroes its cursors, writes
 // the status block.  Enqueued on the context's stream.
-int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o);
+int bins_plan(ipplb_ctx* ctx, ipplb_bins* b, int o, int seg_cap = 0x7fffffff);
 }  // namespace ipplb

@@ -324,6 +324,7 @@ int ipplb_ctx_set_layout(ipplb_ctx* ctx, const ipplb_layout* l, const double ori
     P->L.regions(origin, h, regs.data());
     IPPLB_CUDA(cudaMalloc(&P->d_regions, sizeof(double) * 6 * nr));
     IPPLB_CUDA(cudaMemcpy(P->d_regions, regs.data(), sizeof(double) * 6 * nr, cudaMemcpyHostToDevice));
+    ctx->d_regions = P->d_regions;
     IPPLB_CUDA(cudaMalloc(&P->d_counts, sizeof(int) * (4 * nr + 16)));
     IPPLB_CUDA(cudaMalloc(&P->d_matrix, sizeof(int) * nr * nr));
     IPPLB_CUDA(cudaMallocHost(&P->h_counts, sizeof(int) * (4 * nr + 16)));
@@ -470,95 +471,91 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
     return IPPLB_OK;
 }
 
-// Migration for the bucketed store: the fused step already applied the BC and the ownership test and left
-// the leavers in exit_buf; here they get their destination rank (same search order as ipplb_update), travel as
-// SoA segments over NCCL, and the arrivals are appended to the tail of `cur` and deposited into rho (the
-// reference scatters after update(), so arrivals belong to this step's rho: AlpineManager.h:157-175).
+// Migration for the bucketed store.  The fused step already applied the BC and the ownership test, found every
+// leaver's destination rank (reference search order) and grouped the leavers per destination in exit_buf
+// [nranks][6][exit_cap / nranks].  Here: one all-gather of the per-destination counts, ONE host sync (counts +
+// tail position), one grouped ncclSend/ncclRecv that lands the arrivals directly in the tail of `cur`, one
+// commit kernel, and one scatter that deposits the arrivals into rho (the reference scatters after update(), so
+// arrivals belong to this step's rho: AlpineManager.h:157-175).
+__global__ void migrate_commit_kernel(int add, int* __restrict__ state, int* __restrict__ misc) {
+    state[BS_TAIL_COUNT] += add;
+    misc[BM_ST_TOTAL] += add;
+    misc[BM_ST_TAIL] += add;
+}
+
+}  // extern "C"  (kernel above has C++ linkage)
+extern "C" {
+
 int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, const double* exit_buf,
                        int exit_cap, double* rho, long* sent_host, long* recv_host) {
     IPPLB_REQUIRE(ctx && b && cur, "bins_migrate: bad arguments");
     const int nr = ctx->nranks, me = ctx->rank;
     if (sent_host) std::fill(sent_host, sent_host + nr, 0L);
     if (recv_host) std::fill(recv_host, recv_host + nr, 0L);
-    long n_local = 0, n_exit = 0;
-    int flags = 0, rc;
-    if ((rc = ipplb_bins_status(ctx, b, &n_local, nullptr, &n_exit, &flags))) return rc;
+    CommPlan* P = (CommPlan*)ctx->plan;
+    int* h = b->h_status;
+    if (nr >= 2) {
+        IPPLB_REQUIRE(P && ctx->nccl && exit_buf, "bins_migrate: no layout/communicator/exit buffer bound");
+        IPPLB_REQUIRE(b->exit_ranks == nr, "bins_migrate: the last step was not run with this layout");
+        IPPLB_NCCL(ncclAllGather(b->d_exit_cnt, P->d_matrix, nr, ncclInt, (ncclComm_t)ctx->nccl, ctx->stream));
+        ctx->launches++;
+        IPPLB_CUDA(cudaMemcpyAsync(P->h_matrix, P->d_matrix, sizeof(int) * nr * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    IPPLB_CUDA(cudaMemcpyAsync(h, b->misc(), sizeof(int) * BM_WORDS, cudaMemcpyDeviceToHost, ctx->stream));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int flags = h[BM_ST_FLAGS];
     if (flags & (IPPLB_FLAG_EXIT_OVERFLOW | IPPLB_FLAG_CAPACITY | IPPLB_FLAG_INTERNAL)) {
         set_error("bins_migrate: the last fused step raised flags 0x%x (exit buffer %d, capacity %ld)", flags,
                   exit_cap, b->capacity);
         return IPPLB_ERR_CAPACITY;
     }
-    cur->n = n_local;
+    cur->n = h[BM_ST_TOTAL];
     if (nr < 2) {
-        IPPLB_REQUIRE(n_exit == 0, "bins_migrate: leavers on a single rank");
+        IPPLB_REQUIRE(h[BM_ST_EXIT] == 0, "bins_migrate: leavers on a single rank");
         return IPPLB_OK;
     }
-    CommPlan* P = (CommPlan*)ctx->plan;
-    IPPLB_REQUIRE(P && ctx->nccl && exit_buf, "bins_migrate: no layout/communicator/exit buffer bound");
-    const long n = n_exit;
-    if (P->dest_cap < n + 1) {
-        if (P->d_dest) { IPPLB_CUDA(cudaStreamSynchronize(ctx->stream)); IPPLB_CUDA(cudaFree(P->d_dest)); }
-        P->dest_cap = n + n / 4 + 1024;
-        IPPLB_CUDA(cudaMalloc(&P->d_dest, sizeof(int) * P->dest_cap));
-    }
-    int* cnt = P->d_counts;    // [nr] send counts (own rank included: inclusive-fallback hits stay here)
-    int* cursor = cnt + nr;    // [nr]
-    int* soff = cnt + 2 * nr;  // [nr+1]
-    IPPLB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (4 * nr + 16), ctx->stream));
-    const double* ex[6];
-    for (int a = 0; a < 6; ++a) ex[a] = exit_buf + (size_t)a * exit_cap;
-    if (n > 0) {
-        locate_kernel<<<grid1d(n), 256, 0, ctx->stream>>>(P->d_regions, nr, me, n, ex[0], ex[1], ex[2], P->d_dest,
-                                                          cnt, 1);
-        IPPLB_CHECK_LAUNCH(ctx);
-    }
-    IPPLB_NCCL(ncclAllGather(cnt, P->d_matrix, nr, ncclInt, (ncclComm_t)ctx->nccl, ctx->stream));
-    ctx->launches++;
-    IPPLB_CUDA(cudaMemcpyAsync(P->h_matrix, P->d_matrix, sizeof(int) * nr * nr, cudaMemcpyDeviceToHost, ctx->stream));
-    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> h_soff(nr + 1, 0), h_roff(nr + 1, 0), h_rcnt(nr, 0), h_scnt(nr, 0);
+    const int seg = exit_cap / nr;
+    long na = 0, nh = 0;
+    std::vector<long> roff(nr + 1, 0);
     for (int r = 0; r < nr; ++r) {
-        h_scnt[r] = P->h_matrix[me * nr + r];
-        h_rcnt[r] = P->h_matrix[r * nr + me];
-        h_soff[r + 1] = h_soff[r] + h_scnt[r];
-        h_roff[r + 1] = h_roff[r] + h_rcnt[r];
-        if (sent_host) sent_host[r] = r == me ? 0 : h_scnt[r];
-        if (recv_host) recv_host[r] = r == me ? 0 : h_rcnt[r];
+        const int sc = P->h_matrix[me * nr + r], rc_ = P->h_matrix[r * nr + me];
+        roff[r + 1] = roff[r] + rc_;
+        nh += sc;
+        if (sent_host) sent_host[r] = r == me ? 0 : sc;
+        if (recv_host) recv_host[r] = r == me ? 0 : rc_;
     }
-    const int nh = h_soff[nr], na = h_roff[nr];
-    if (nh == 0 && na == 0) return IPPLB_OK;
-    AttrPtrs A;
-    A.n = 6;
-    for (int a = 0; a < 6; ++a) A.a[a] = const_cast<double*>(ex[a]);
-    if ((rc = ensure(ctx, ctx->send, sizeof(double) * ((size_t)nh * 6 + 1)))) return rc;
-    if ((rc = ensure(ctx, ctx->recv, sizeof(double) * ((size_t)na * 6 + 1)))) return rc;
-    if ((rc = ensure(ctx, ctx->misc, sizeof(int) * ((size_t)nh + 64)))) return rc;
-    double* sb = (double*)ctx->send.ptr; double* rb = (double*)ctx->recv.ptr;
-    IPPLB_CUDA(cudaMemcpyAsync(soff, h_soff.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice, ctx->stream));
-    if (nh > 0) {
-        pack_leavers_kernel<<<grid1d(n), 256, 0, ctx->stream>>>(n, me, P->d_dest, soff, cnt, cursor, A, sb,
-                                                                (int*)ctx->misc.ptr, 1);
-        IPPLB_CHECK_LAUNCH(ctx);
+    na = roff[nr];
+    if (na == 0 && nh == 0) return IPPLB_OK;
+    const long tail_pos = (long)h[BM_ST_TAIL_START] + h[BM_ST_TAIL];
+    if (tail_pos + na > b->capacity) {
+        set_error("bins_migrate: %ld arrivals do not fit behind the tail (%ld of %ld used)", na, tail_pos, b->capacity);
+        return IPPLB_ERR_CAPACITY;
     }
+    double* dst[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
     IPPLB_NCCL(ncclGroupStart());
     for (int r = 0; r < nr; ++r) {
+        const int sc = P->h_matrix[me * nr + r], rc_ = P->h_matrix[r * nr + me];
         if (r == me) continue;
-        if (h_scnt[r]) IPPLB_NCCL(ncclSend(sb + (size_t)h_soff[r] * 6, (size_t)h_scnt[r] * 6, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
-        if (h_rcnt[r]) IPPLB_NCCL(ncclRecv(rb + (size_t)h_roff[r] * 6, (size_t)h_rcnt[r] * 6, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
+        for (int a = 0; a < 6; ++a) {
+            if (sc) IPPLB_NCCL(ncclSend(exit_buf + ((size_t)r * 6 + a) * seg, (size_t)sc, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
+            if (rc_) IPPLB_NCCL(ncclRecv(dst[a] + tail_pos + roff[r], (size_t)rc_, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
+        }
     }
     IPPLB_NCCL(ncclGroupEnd());
     ctx->launches++;
-    for (int r = 0; r < nr; ++r) {
-        const long c = h_rcnt[r];
-        if (!c) continue;
-        const double* blk = (r == me ? sb + (size_t)h_soff[r] * 6 : rb + (size_t)h_roff[r] * 6);
-        const double* src[6];
-        for (int a = 0; a < 6; ++a) src[a] = blk + (size_t)a * c;
-        if ((rc = ipplb_bins_append(ctx, b, cur, src, c))) return rc;
-        if (rho && (rc = ipplb_scatter_cic(ctx, &b->mesh, 0, c, src[0], src[1], src[2], nullptr, cur->q_scalar,
-                                           nullptr, rho)))
+    const int self = P->h_matrix[me * nr + me];  // inclusive-fallback hits that stay here
+    for (int a = 0; self && a < 6; ++a)
+        IPPLB_CUDA(cudaMemcpyAsync(dst[a] + tail_pos + roff[me], exit_buf + ((size_t)me * 6 + a) * seg,
+                                   sizeof(double) * (size_t)self, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (na > 0) {
+        migrate_commit_kernel<<<1, 1, 0, ctx->stream>>>((int)na, b->state(b->cur), b->misc());
+        IPPLB_CHECK_LAUNCH(ctx);
+        int rc;
+        if (rho && (rc = ipplb_scatter_cic(ctx, &b->mesh, tail_pos, tail_pos + na, cur->x, cur->y, cur->z, nullptr,
+                                           cur->q_scalar, nullptr, rho)))
             return rc;
     }
+    cur->n += na;
     return IPPLB_OK;
 }
 

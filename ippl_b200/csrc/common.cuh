@@ -89,6 +89,7 @@ struct ipplb_ctx {
     ncclComm* nccl = nullptr;
     int rank = 0, nranks = 1;
     void* plan = nullptr;  // ipplb::CommPlan*
+    const double* d_regions = nullptr;  // [nranks][6] physical regions (device), set by ipplb_ctx_set_layout
 };
 
 namespace ipplb {

@@ -55,8 +55,11 @@ struct StepArgs {
     const double* ef;
     double* rho;
     double q;
-    double* exit_buf;
-    int exit_cap;
+    double* exit_buf;  // [nranks][6][seg_cap]: leavers grouped by destination rank
+    int* exit_cnt;     // [nranks]
+    int seg_cap;
+    const double* regions;  // [nranks][6] (device) or nullptr on a single rank
+    int nranks, me;
     int capacity;
     int ntx, nty, ntz, ntiles;
     int check_owner;
@@ -132,16 +135,38 @@ __device__ __forceinline__ void win_seg(int w, int& s, int& l, int& wd) {
 }
 
 // ---- slow paths ------------------------------------------------------------------------------------------
+// A particle that left the rank's region: destination rank by the reference's search (every other rank's strict
+// region, then the inclusive fallback, else stay -- ParticleSpatialLayout.hpp:372-395; the own strict test has
+// already failed), appended to that rank's segment of the exit buffer.  Lanes of a warp that leave for the same
+// rank share one atomic.
 __device__ __forceinline__ void place_exit(const StepArgs& A, const double r[3], const double p[3]) {
-    const int e = atomicAdd(&A.misc[BM_EXIT], 1);
-    if (e < A.exit_cap) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            A.exit_buf[(long)d * A.exit_cap + e]       = r[d];
-            A.exit_buf[(long)(3 + d) * A.exit_cap + e] = p[d];
+    int d = 0;
+    if (A.regions) {
+        d = -1;
+        for (int k = 0; d < 0 && k < A.nranks; ++k) {
+            const double* R = A.regions + 6 * k;
+            if (r[0] > R[0] && r[1] > R[1] && r[2] > R[2] && r[0] <= R[3] && r[1] <= R[4] && r[2] <= R[5]) d = k;
         }
-    } else {
-        atomicOr(&A.misc[BM_FLAGS], IPPLB_FLAG_EXIT_OVERFLOW);
+        for (int k = 0; d < 0 && k < A.nranks; ++k) {
+            const double* R = A.regions + 6 * k;
+            if (r[0] >= R[0] && r[1] >= R[1] && r[2] >= R[2] && r[0] <= R[3] && r[1] <= R[4] && r[2] <= R[5]) d = k;
+        }
+        if (d < 0) d = A.me;
+    }
+    const unsigned peers = __match_any_sync(__activemask(), d);
+    const int leader     = __ffs(peers) - 1;
+    const int lane       = threadIdx.x & 31;
+    int base             = 0;
+    if (lane == leader) base = atomicAdd(&A.exit_cnt[d], __popc(peers));
+    base        = __shfl_sync(peers, base, leader);
+    const int e = base + __popc(peers & ((1u << lane) - 1u));
+    if (e < A.seg_cap) {
+        double* seg = A.exit_buf + (size_t)d * 6 * A.seg_cap;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            seg[(size_t)k * A.seg_cap + e]       = r[k];
+            seg[(size_t)(3 + k) * A.seg_cap + e] = p[k];
+        }
     }
 }
 
@@ -660,8 +685,15 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
     A.ef         = efield;
     A.rho        = rho;
     A.q          = cur->q_scalar;
+    const int nrk = ctx->d_regions ? ctx->nranks : 1;
+    IPPLB_REQUIRE(nrk <= MAX_RANKS, "bins_step: too many ranks for the exit buffer segmentation");
     A.exit_buf   = exit_buf;
-    A.exit_cap   = exit_buf ? exit_cap : 0;
+    A.exit_cnt   = b->d_exit_cnt;
+    A.seg_cap    = exit_buf ? exit_cap / nrk : 0;
+    A.regions    = ctx->d_regions;
+    A.nranks     = nrk;
+    A.me         = ctx->rank;
+    b->exit_ranks = nrk;
     A.capacity   = (int)b->capacity;
     A.ntx = b->ntx; A.nty = b->nty; A.ntz = b->ntz; A.ntiles = b->ntiles;
     A.check_owner = (region_min && region_max) ? 1 : 0;
@@ -670,6 +702,7 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         A.rmax[d] = region_max ? region_max[d] : 0.0;
     }
     IPPLB_CUDA(cudaMemsetAsync(b->misc(), 0, sizeof(int) * 4, ctx->stream));
+    IPPLB_CUDA(cudaMemsetAsync(b->d_exit_cnt, 0, sizeof(int) * nrk, ctx->stream));
     int rc;
     switch (fused_cfg()) {
         case 1: rc = launch_fused<256, 2, 3>(ctx, A); break;
@@ -679,7 +712,7 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         default: rc = launch_fused<384, 2, 2>(ctx, A); break;
     }
     if (rc) return rc;
-    rc = bins_plan(ctx, b, o);
+    rc = bins_plan(ctx, b, o, A.seg_cap);
 
     if (rc) return rc;
     b->cur        = o;
