@@ -1,0 +1,745 @@
+// Ippl.h -- host-side C++ mirror of IPPL's API for the particle-mesh hot path, on top of the C-ABI
+// (include/ippl_b200.h).  Same names, argument meaning and error behaviour as the reference for the path
+// SURVEY.md section 8 scopes (paths below are relative to the reference tree):
+//
+//   ippl::Vector                    src/Types/Vector.h
+//   ippl::Index / NDIndex           src/Index/Index.h, src/Index/NDIndex.h
+//   ippl::FieldLayout               src/FieldLayout/FieldLayout.h           (boxes from ipplb_layout_*)
+//   ippl::UniformCartesian          src/Meshes/UniformCartesian.h
+//   ippl::Field (BareField)         src/Field/BareField.h / .hpp            (= scalar, sum, accumulateHalo, fillHalo)
+//   ippl::ParticleAttrib            src/Particle/ParticleAttrib.h / .hpp    (scatter, gather, = expression)
+//   ippl::ParticleSpatialLayout     src/Particle/ParticleSpatialLayout.h    (update: BC + migration)
+//   ippl::ParticleBase              src/Particle/ParticleBase.h             (create, addAttribute, update)
+//   ippl::scatter / ippl::gather    src/Particle/ParticleAttrib.hpp:304-358
+//   ippl::FFTPeriodicPoissonSolver  src/PoissonSolvers/FFTPeriodicPoissonSolver.h (non-owned stage, cuFFT)
+//   IpplTimings, Inform, IpplException, ippl::Comm, ippl::initialize / finalize
+//
+// Differences, all behind the same API: particle vectors are stored SoA on the device (the reference stores
+// AoS Kokkos::View<Vector<T,3>*>); host access goes through getHostMirror() + ippl::deep_copy like the
+// reference's create_mirror_view / deep_copy; there is no Kokkos, so driver-side KOKKOS_LAMBDA kernels are out
+// of this header's scope.  Header-only, C++17, links libippl_b200.so + libcudart.  No CPU fallback: every
+// operation ends in an ipplb_* call and throws IpplException when that fails.
+#ifndef IPPL_B200_FACADE_H
+#define IPPL_B200_FACADE_H
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../ippl_b200.h"
+
+// ---- errors (src/Utility/IpplException.h) ---------------------------------------------------------------------
+class IpplException : public std::runtime_error {
+public:
+    IpplException(const std::string& meth, const std::string& descr)
+        : std::runtime_error(meth + ": " + descr), meth_(meth), descr_(descr) {}
+    const std::string& where() const { return meth_; }
+    const std::string& what_str() const { return descr_; }
+
+private:
+    std::string meth_, descr_;
+};
+
+// ---- Inform (src/Utility/Inform.h): rank-0 message stream ------------------------------------------------------
+class Inform {
+public:
+    explicit Inform(const char* name = nullptr) : name_(name ? name : "") {}
+    template <typename T>
+    Inform& operator<<(const T& v) {
+        buf_ << v;
+        return *this;
+    }
+    Inform& operator<<(Inform& (*f)(Inform&)) { return f(*this); }
+    void flush() {
+        if (level_on()) std::cout << (name_.empty() ? "" : name_ + "> ") << buf_.str() << std::endl;
+        buf_.str("");
+    }
+    static bool& level_on() {
+        static bool on = true;
+        return on;
+    }
+
+private:
+    std::string name_;
+    std::ostringstream buf_;
+};
+inline Inform& endl(Inform& m) {
+    m.flush();
+    return m;
+}
+
+namespace ippl {
+
+namespace detail {
+    using size_type = std::size_t;
+}
+
+// ---- runtime: one context per process/GPU (src/Ippl.cpp, src/Communicate/Communicator.h) -------------------------
+namespace b200 {
+    inline ipplb_ctx*& ctx_ref() {
+        static ipplb_ctx* c = nullptr;
+        return c;
+    }
+    inline ipplb_ctx* ctx() {
+        if (!ctx_ref()) throw IpplException("ippl::b200::ctx", "ippl::initialize has not been called");
+        return ctx_ref();
+    }
+    inline void check(int rc, const char* where) {
+        if (rc != IPPLB_OK) throw IpplException(where, ipplb_last_error());
+    }
+    inline void cuda_check(cudaError_t e, const char* where) {
+        if (e != cudaSuccess) throw IpplException(where, cudaGetErrorString(e));
+    }
+    template <typename T>
+    T* device_alloc(std::size_t n) {
+        T* p = nullptr;
+        cuda_check(cudaMalloc(&p, sizeof(T) * std::max<std::size_t>(n, 1)), "cudaMalloc");
+        return p;
+    }
+}  // namespace b200
+
+class Communicator {
+public:
+    int rank() const { return rank_; }
+    int size() const { return size_; }
+    void barrier() { b200::check(ipplb_sync(b200::ctx()), "Comm::barrier"); }
+    [[noreturn]] void abort() {
+        std::cerr << "ippl::Comm->abort()" << std::endl;
+        std::abort();
+    }
+    double getDefaultOverallocation() const { return overalloc_; }
+    void setDefaultOverallocation(double f) { overalloc_ = f; }
+    // reduce / allreduce of one value over ranks (single rank: identity; multi rank: NCCL through the C-ABI)
+    template <typename T, typename Op>
+    void reduce(const T& in, T& out, int /*count*/, Op, int /*root*/ = 0) {
+        out = in;
+        if (size_ > 1) allreduce_sum(out);
+    }
+    template <typename T, typename Op>
+    void allreduce(T& inout, int /*count*/, Op) {
+        if (size_ > 1) allreduce_sum(inout);
+    }
+    void set(int rank, int size) {
+        rank_ = rank;
+        size_ = size;
+    }
+
+private:
+    void allreduce_sum(double& v) { b200::check(ipplb_allreduce_sum_f64(b200::ctx(), &v), "Comm::allreduce"); }
+    void allreduce_sum(std::size_t& v) {
+        long t = (long)v;
+        b200::check(ipplb_allreduce_sum_i64(b200::ctx(), &t), "Comm::allreduce");
+        v = (std::size_t)t;
+    }
+    int rank_ = 0, size_ = 1;
+    double overalloc_ = 1.0;
+};
+inline std::unique_ptr<Communicator>& comm_holder() {
+    static std::unique_ptr<Communicator> c;
+    return c;
+}
+inline Communicator* Comm = nullptr;
+
+inline void initialize(int& argc, char**& argv) {
+    int device = 0;
+    if (const char* lr = std::getenv("LOCAL_RANK")) device = std::atoi(lr);
+    b200::cuda_check(cudaSetDevice(device), "ippl::initialize");
+    // the CUDA default stream: the facade's blocking cudaMemcpy calls and the kernels stay ordered
+    b200::check(ipplb_ctx_create(&b200::ctx_ref(), device, nullptr, 0), "ippl::initialize");
+    comm_holder() = std::make_unique<Communicator>();
+    Comm          = comm_holder().get();
+    for (int i = 1; i < argc; ++i) {  // global flags of src/Ippl.cpp:35-92 that matter here
+        const std::string a = argv[i];
+        if (a == "--overallocate" && i + 1 < argc) Comm->setDefaultOverallocation(std::atof(argv[i + 1]));
+        if (a == "--info" && i + 1 < argc) Inform::level_on() = std::atoi(argv[i + 1]) > 0;
+    }
+}
+inline void finalize() {
+    if (b200::ctx_ref()) ipplb_ctx_destroy(b200::ctx_ref());
+    b200::ctx_ref() = nullptr;
+}
+inline void fence() { b200::check(ipplb_sync(b200::ctx()), "ippl::fence"); }
+
+// ---- Vector (src/Types/Vector.h) -----------------------------------------------------------------------------------
+template <typename T, unsigned Dim>
+class Vector {
+public:
+    Vector() { data_.fill(T()); }
+    Vector(const T& v) { data_.fill(v); }
+    Vector(std::initializer_list<T> l) {
+        data_.fill(T());
+        std::copy_n(l.begin(), std::min<std::size_t>(l.size(), Dim), data_.begin());
+    }
+    T& operator[](unsigned i) { return data_[i]; }
+    const T& operator[](unsigned i) const { return data_[i]; }
+    T* begin() { return data_.data(); }
+    T* end() { return data_.data() + Dim; }
+    const T* begin() const { return data_.data(); }
+    const T* end() const { return data_.data() + Dim; }
+#define IPPL_VEC_OP(op)                                                   \
+    Vector& operator op##=(const Vector& o) {                             \
+        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = o.data_[i];    \
+        return *this;                                                     \
+    }                                                                     \
+    Vector& operator op##=(const T& s) {                                  \
+        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = s;             \
+        return *this;                                                     \
+    }                                                                     \
+    friend Vector operator op(Vector a, const Vector& b) { return a op## = b; } \
+    friend Vector operator op(Vector a, const T& s) { return a op## = s; }
+    IPPL_VEC_OP(+)
+    IPPL_VEC_OP(-)
+    IPPL_VEC_OP(*)
+    IPPL_VEC_OP(/)
+#undef IPPL_VEC_OP
+    friend Vector operator*(const T& s, Vector a) { return a *= s; }
+    friend Vector operator/(const T& s, const Vector& a) {
+        Vector r;
+        for (unsigned i = 0; i < Dim; ++i) r[i] = s / a[i];
+        return r;
+    }
+    friend std::ostream& operator<<(std::ostream& os, const Vector& v) {
+        os << "( ";
+        for (unsigned i = 0; i < Dim; ++i) os << v[i] << (i + 1 < Dim ? " , " : " )");
+        return os;
+    }
+
+private:
+    std::array<T, Dim> data_;
+};
+
+// ---- Index / NDIndex (src/Index) -------------------------------------------------------------------------------------
+class Index {
+public:
+    Index() : first_(0), length_(0) {}
+    explicit Index(int n) : first_(0), length_(n) {}
+    Index(int first, int last) : first_(first), length_(last - first + 1) {}
+    int first() const { return first_; }
+    int last() const { return first_ + length_ - 1; }
+    int length() const { return length_; }
+
+private:
+    int first_, length_;
+};
+template <unsigned Dim>
+class NDIndex {
+public:
+    NDIndex() = default;
+    template <typename... Idx>
+    NDIndex(const Idx&... i) : idx_{i...} {}
+    Index& operator[](unsigned d) { return idx_[d]; }
+    const Index& operator[](unsigned d) const { return idx_[d]; }
+    std::size_t size() const {
+        std::size_t s = 1;
+        for (auto& i : idx_) s *= i.length();
+        return s;
+    }
+
+private:
+    std::array<Index, Dim> idx_;
+};
+
+enum BC { PERIODIC, REFLECTIVE, SINK, NO };
+
+// ---- FieldLayout (src/FieldLayout/FieldLayout.h) ----------------------------------------------------------------------
+template <unsigned Dim>
+class FieldLayout {
+    static_assert(Dim == 3, "the B200 path is three-dimensional");
+
+public:
+    FieldLayout() = default;
+    // FieldLayout(comm, domain, isParallel, isAllPeriodic): FieldLayout.hpp:76-134 (comm is implicit: ippl::Comm)
+    template <typename CommT>
+    FieldLayout(const CommT&, const NDIndex<Dim>& domain, std::array<bool, Dim> decomp, bool isAllPeriodic = false) {
+        initialize(domain, decomp, isAllPeriodic);
+    }
+    ~FieldLayout() {
+        if (h_) ipplb_layout_destroy(h_);
+    }
+    FieldLayout(const FieldLayout&)            = delete;
+    FieldLayout& operator=(const FieldLayout&) = delete;
+    void initialize(const NDIndex<Dim>& domain, std::array<bool, Dim> decomp, bool isAllPeriodic, int nghost = 1) {
+        domain_   = domain;
+        periodic_ = isAllPeriodic;
+        int ng[3], par[3];
+        for (unsigned d = 0; d < Dim; ++d) {
+            ng[d]  = domain[d].length();
+            par[d] = decomp[d];
+        }
+        b200::check(ipplb_layout_create(&h_, ng, par, Comm->size(), isAllPeriodic, nghost), "FieldLayout::initialize");
+        std::vector<int> boxes(6 * Comm->size());
+        b200::check(ipplb_layout_boxes(h_, boxes.data()), "FieldLayout::initialize");
+        const int* b = &boxes[6 * Comm->rank()];
+        local_       = NDIndex<Dim>(Index(b[0], b[3]), Index(b[1], b[4]), Index(b[2], b[5]));
+    }
+    const NDIndex<Dim>& getDomain() const { return domain_; }
+    const NDIndex<Dim>& getLocalNDIndex() const { return local_; }
+    bool isAllPeriodic() const { return periodic_; }
+    ipplb_layout* handle() const { return h_; }
+
+private:
+    ipplb_layout* h_ = nullptr;
+    NDIndex<Dim> domain_, local_;
+    bool periodic_ = false;
+};
+
+// ---- UniformCartesian (src/Meshes/UniformCartesian.h) ------------------------------------------------------------------
+struct Cell {};
+template <typename T, unsigned Dim>
+class UniformCartesian {
+public:
+    using DefaultCentering = Cell;
+    using vector_type      = Vector<T, Dim>;
+    UniformCartesian() = default;
+    UniformCartesian(const NDIndex<Dim>& domain, const vector_type& hx, const vector_type& origin) {
+        initialize(domain, hx, origin);
+    }
+    void initialize(const NDIndex<Dim>& domain, const vector_type& hx, const vector_type& origin) {
+        domain_ = domain;
+        hx_     = hx;
+        origin_ = origin;
+    }
+    const vector_type& getMeshSpacing() const { return hx_; }
+    const vector_type& getOrigin() const { return origin_; }
+    T getCellVolume() const { return std::accumulate(hx_.begin(), hx_.end(), T(1), std::multiplies<T>()); }
+    const NDIndex<Dim>& getGridsize() const { return domain_; }
+
+private:
+    NDIndex<Dim> domain_;
+    vector_type hx_, origin_;
+};
+
+namespace detail {
+    template <typename T>
+    struct ncomp_of {
+        static constexpr int value = 1;
+    };
+    template <typename T, unsigned D>
+    struct ncomp_of<Vector<T, D>> {
+        static constexpr int value = (int)D;
+    };
+}  // namespace detail
+
+namespace detail {
+    // field / scalar and field - scalar: the two expressions AlpineManager::getDensity assigns (AlpineManager.h:225-245)
+    template <class F>
+    struct FieldAffine {
+        const F* f;
+        double divisor, shift;
+    };
+}  // namespace detail
+
+// ---- Field / BareField (src/Field/BareField.h, BareField.hpp) --------------------------------------------------------------
+template <typename T, unsigned Dim, class Mesh = UniformCartesian<double, Dim>, class Centering = Cell>
+class Field {
+    static_assert(Dim == 3, "the B200 path is three-dimensional");
+
+public:
+    using Mesh_t   = Mesh;
+    using Layout_t = FieldLayout<Dim>;
+    static constexpr int ncomp = detail::ncomp_of<T>::value;
+    Field() = default;
+    Field(Mesh& m, Layout_t& l, int nghost = 1) { initialize(m, l, nghost); }
+    ~Field() {
+        if (data_) cudaFree(data_);
+    }
+    Field(const Field&)            = delete;
+    Field& operator=(const Field&) = delete;
+    void initialize(Mesh& m, Layout_t& l, int nghost = 1) {
+        mesh_p_   = &m;
+        layout_p_ = &l;
+        nghost_   = nghost;
+        double o[3], h[3];
+        for (int d = 0; d < 3; ++d) {
+            o[d] = m.getOrigin()[d];
+            h[d] = m.getMeshSpacing()[d];
+        }
+        b200::check(ipplb_layout_mesh(l.handle(), Comm->rank(), o, h, &mesh_), "Field::initialize");
+        cells_ = 1;
+        for (int d = 0; d < 3; ++d) cells_ *= mesh_.nl[d] + 2 * nghost;
+        if (data_) cudaFree(data_);
+        data_ = b200::device_alloc<double>(cells_ * ncomp);
+        *this = 0.0;
+    }
+    // field = scalar (BareField.hpp:182-185)
+    Field& operator=(double v) {
+        b200::check(ipplb_field_fill(b200::ctx(), data_, (long)(cells_ * ncomp), v), "Field::operator=");
+        return *this;
+    }
+    // field = field / c  and  field = field - s on the interior (expression assignment, BareField.hpp:187-205)
+    Field& operator=(const detail::FieldAffine<Field>& e) {
+        if (e.f != this) throw IpplException("Field::operator=", "only f = f / c and f = f - s are supported by the facade");
+        b200::check(ipplb_field_density(b200::ctx(), &mesh_, data_, e.divisor, e.shift), "Field::operator=");
+        return *this;
+    }
+    friend detail::FieldAffine<Field> operator/(const Field& f, double c) { return {&f, c, 0.0}; }
+    friend detail::FieldAffine<Field> operator-(const Field& f, double s) { return {&f, 1.0, s}; }
+    // rho.sum(): interior cells, reduced over ranks (BareField.hpp:224-240)
+    double sum() const {
+        double s = 0;
+        b200::check(ipplb_field_sum(b200::ctx(), &mesh_, data_, &s), "Field::sum");
+        double g = s;
+        Comm->allreduce(g, 1, std::plus<double>());
+        return g;
+    }
+    // BareField::accumulateHalo / fillHalo (BareField.hpp:152-172): exchange, then in-rank periodic wrap
+    void accumulateHalo() { halo(1); }
+    void fillHalo() { halo(0); }
+    int getNghost() const { return nghost_; }
+    Mesh& get_mesh() const { return *mesh_p_; }
+    Layout_t& getLayout() const { return *layout_p_; }
+    const ipplb_mesh& b200_mesh() const { return mesh_; }
+    double* data() const { return data_; }
+    std::size_t cells() const { return cells_; }
+    // host copy of the ghosted storage (x fastest), ncomp values per cell -- Kokkos::create_mirror_view_and_copy
+    std::vector<double> getHostMirror() const {
+        std::vector<double> h(cells_ * ncomp);
+        fence();
+        b200::cuda_check(cudaMemcpy(h.data(), data_, sizeof(double) * h.size(), cudaMemcpyDeviceToHost), "Field::getHostMirror");
+        return h;
+    }
+
+private:
+    void halo(int accumulate) {
+        if (Comm->size() > 1) {
+            b200::check(ipplb_halo_exchange(b200::ctx(), data_, ncomp, accumulate), "Field::halo");
+        } else {
+            int mask = 0;
+            for (int d = 0; d < 3; ++d)
+                if (mesh_.nl[d] == mesh_.ng[d] && layout_p_->isAllPeriodic()) mask |= 1 << d;
+            b200::check(accumulate ? ipplb_halo_accumulate_periodic(b200::ctx(), &mesh_, data_, ncomp, mask)
+                                   : ipplb_halo_fill_periodic(b200::ctx(), &mesh_, data_, ncomp, mask),
+                        "Field::halo");
+        }
+    }
+    Mesh* mesh_p_       = nullptr;
+    Layout_t* layout_p_ = nullptr;
+    ipplb_mesh mesh_{};
+    int nghost_        = 1;
+    std::size_t cells_ = 0;
+    double* data_      = nullptr;
+};
+
+// ---- ParticleAttrib (src/Particle/ParticleAttrib.h / .hpp) ----------------------------------------------------------------------
+namespace detail {
+    class ParticleAttribBase {
+    public:
+        virtual ~ParticleAttribBase()                 = default;
+        virtual void create(std::size_t n)            = 0;
+        virtual void setCount(std::size_t n)          = 0;
+        void set_name(const std::string& n) { name_ = n; }
+        const std::string& get_name() const { return name_; }
+
+    protected:
+        std::string name_;
+    };
+    // a * attrib  and  attrib +/- a * attrib : the expressions the alpine pushes are made of
+    template <class A>
+    struct Scaled {
+        double a;
+        const A* x;
+    };
+    template <class A>
+    struct Axpy {
+        const A* y;
+        double a;
+        const A* x;
+    };
+}  // namespace detail
+
+template <typename T>
+class ParticleAttrib : public detail::ParticleAttribBase {
+public:
+    static constexpr int ncomp = detail::ncomp_of<T>::value;
+    using value_type           = T;
+    ParticleAttrib()           = default;
+    ~ParticleAttrib() override {
+        for (auto p : d_)
+            if (p) cudaFree(p);
+    }
+    // create(n): grows with the communicator's over-allocation factor truncated to int (ParticleAttrib.hpp:37-49)
+    void create(std::size_t n) override {
+        const std::size_t need = count_ + n;
+        if (need > capacity_) {
+            const int over         = std::max(1, (int)Comm->getDefaultOverallocation());
+            const std::size_t ncap = need * over;
+            for (int c = 0; c < ncomp; ++c) {
+                double* p = b200::device_alloc<double>(ncap);
+                if (d_[c]) {
+                    b200::cuda_check(cudaMemcpy(p, d_[c], sizeof(double) * count_, cudaMemcpyDeviceToDevice), "ParticleAttrib::create");
+                    cudaFree(d_[c]);
+                }
+                d_[c] = p;
+            }
+            capacity_ = ncap;
+        }
+        count_ = need;
+    }
+    void setCount(std::size_t n) override { count_ = n; }
+    std::size_t size() const { return capacity_; }
+    std::size_t getParticleCount() const { return count_; }
+    double* component(int c) const { return d_[c]; }
+    // attrib = scalar (ParticleAttrib.hpp:105-116)
+    ParticleAttrib& operator=(const T& v) {
+        for (int c = 0; c < ncomp; ++c)
+            b200::check(ipplb_field_fill(b200::ctx(), d_[c], (long)count_, comp(v, c)), "ParticleAttrib::operator=");
+        return *this;
+    }
+    // attrib = expression (ParticleAttrib.hpp:118-130) for y = y +/- a * x: one axpy per component, same rounding
+    // as the reference's per-particle y - (a * x)
+    ParticleAttrib& operator=(const detail::Axpy<ParticleAttrib>& e) {
+        if (e.y != this) throw IpplException("ParticleAttrib::operator=", "only y = y + a * x is supported by the facade");
+        for (int c = 0; c < ncomp; ++c)
+            b200::check(ipplb_axpy(b200::ctx(), (long)count_, e.a, e.x->d_[c], d_[c]), "ParticleAttrib::operator=");
+        return *this;
+    }
+    // sum over local particles (then ranks): ParticleAttrib.hpp:511-532
+    double sum(int c = 0) const {
+        // reuse the interior-sum kernel on a 1-D "mesh" of count_ cells without ghosts
+        ipplb_mesh m{};
+        m.ng[0] = m.nl[0] = (int)count_;
+        m.ng[1] = m.nl[1] = m.ng[2] = m.nl[2] = 1;
+        m.nghost                                = 0;
+        m.h[0] = m.h[1] = m.h[2] = 1.0;
+        double s = 0;
+        b200::check(ipplb_field_sum(b200::ctx(), &m, d_[c], &s), "ParticleAttrib::sum");
+        Comm->allreduce(s, 1, std::plus<double>());
+        return s;
+    }
+    // host mirror (AoS of T like the reference's view(i)); deep_copy moves it to / from the device SoA
+    using HostMirror = std::vector<T>;
+    HostMirror getHostMirror() const { return HostMirror(count_); }
+    void copyFromHost(const HostMirror& h) {
+        std::vector<double> tmp(count_);
+        for (int c = 0; c < ncomp; ++c) {
+            for (std::size_t i = 0; i < count_; ++i) tmp[i] = comp(h[i], c);
+            b200::cuda_check(cudaMemcpy(d_[c], tmp.data(), sizeof(double) * count_, cudaMemcpyHostToDevice), "deep_copy");
+        }
+    }
+    void copyToHost(HostMirror& h) const {
+        h.resize(count_);
+        std::vector<double> tmp(count_);
+        fence();
+        for (int c = 0; c < ncomp; ++c) {
+            b200::cuda_check(cudaMemcpy(tmp.data(), d_[c], sizeof(double) * count_, cudaMemcpyDeviceToHost), "deep_copy");
+            for (std::size_t i = 0; i < count_; ++i) comp(h[i], c) = tmp[i];
+        }
+    }
+    // scatter / gather members (ParticleAttrib.hpp:132-246)
+    template <typename Field, typename PT>
+    void scatter(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp) const {
+        static_assert(ncomp == 1, "scatter deposits a scalar attribute");
+        b200::check(ipplb_scatter_cic(b200::ctx(), &f.b200_mesh(), 0, (long)pp.getParticleCount(), pp.component(0),
+                                      pp.component(1), pp.component(2), d_[0], 0.0, nullptr, f.data()),
+                    "ParticleAttrib::scatter");
+        f.accumulateHalo();
+    }
+    template <typename Field, typename PT>
+    void gather(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp, bool addToAttribute = false) {
+        f.fillHalo();
+        double* out[3] = {d_[0], ncomp > 1 ? d_[1] : nullptr, ncomp > 2 ? d_[2] : nullptr};
+        b200::check(ipplb_gather_cic(b200::ctx(), &f.b200_mesh(), (long)pp.getParticleCount(), pp.component(0),
+                                     pp.component(1), pp.component(2), f.data(), Field::ncomp, out, addToAttribute),
+                    "ParticleAttrib::gather");
+    }
+
+private:
+    static double comp(const double& v, int) { return v; }
+    static double& comp(double& v, int) { return v; }
+    template <typename U, unsigned D>
+    static double comp(const Vector<U, D>& v, int c) { return v[c]; }
+    template <typename U, unsigned D>
+    static double& comp(Vector<U, D>& v, int c) { return v[c]; }
+    std::array<double*, 3> d_{nullptr, nullptr, nullptr};
+    std::size_t count_ = 0, capacity_ = 0;
+};
+
+template <typename T>
+detail::Scaled<ParticleAttrib<T>> operator*(double a, const ParticleAttrib<T>& x) { return {a, &x}; }
+template <class A>
+detail::Scaled<A> operator*(double a, const detail::Scaled<A>& s) { return {a * s.a, s.x}; }
+template <typename T>
+detail::Axpy<ParticleAttrib<T>> operator+(const ParticleAttrib<T>& y, const detail::Scaled<ParticleAttrib<T>>& s) { return {&y, s.a, s.x}; }
+template <typename T>
+detail::Axpy<ParticleAttrib<T>> operator-(const ParticleAttrib<T>& y, const detail::Scaled<ParticleAttrib<T>>& s) { return {&y, -s.a, s.x}; }
+
+template <typename T>
+void deep_copy(ParticleAttrib<T>& dst, const typename ParticleAttrib<T>::HostMirror& src) { dst.copyFromHost(src); }
+template <typename T>
+void deep_copy(typename ParticleAttrib<T>::HostMirror& dst, const ParticleAttrib<T>& src) { src.copyToHost(dst); }
+
+// free functions (ParticleAttrib.hpp:304-358)
+template <typename Attrib1, typename Field, typename Attrib2>
+void scatter(const Attrib1& attrib, Field& f, const Attrib2& pp) { attrib.scatter(f, pp); }
+template <typename Attrib1, typename Field, typename Attrib2>
+void gather(Attrib1& attrib, Field& f, const Attrib2& pp, bool addToAttribute = false) { attrib.gather(f, pp, addToAttribute); }
+
+// ---- ParticleSpatialLayout (src/Particle/ParticleSpatialLayout.h / .hpp) -----------------------------------------------------------
+template <typename T, unsigned Dim, class Mesh = UniformCartesian<T, Dim>>
+class ParticleSpatialLayout {
+    static_assert(Dim == 3, "the B200 path is three-dimensional");
+
+public:
+    using vector_type            = Vector<T, Dim>;
+    using particle_position_type = ParticleAttrib<vector_type>;
+    ParticleSpatialLayout(FieldLayout<Dim>& fl, Mesh& mesh, bool /*fem*/ = false) : fl_(&fl), mesh_(&mesh) {
+        if (Comm->size() > 1) {
+            double o[3], h[3];
+            for (int d = 0; d < 3; ++d) {
+                o[d] = mesh.getOrigin()[d];
+                h[d] = mesh.getMeshSpacing()[d];
+            }
+            b200::check(ipplb_ctx_set_layout(b200::ctx(), fl.handle(), o, h), "ParticleSpatialLayout");
+        }
+    }
+    void setParticleBC(BC bc) { bc_ = bc; }
+    // update(): applyBC (ParticleLayout.hpp:34-74, PeriodicBC ParticleBC.h:73-76), early return on one rank
+    // (ParticleSpatialLayout.hpp:128), else ownership + exchange + compaction (ipplb_update)
+    template <class PC>
+    void update(PC& pc) {
+        auto& R = pc.R;
+        long n  = (long)pc.getLocalNum();
+        double lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+            lo[d] = 0 * mesh_->getMeshSpacing()[d] + mesh_->getOrigin()[d];
+            hi[d] = fl_->getDomain()[d].length() * mesh_->getMeshSpacing()[d] + mesh_->getOrigin()[d];
+        }
+        if (bc_ == PERIODIC)
+            b200::check(ipplb_apply_periodic_bc(b200::ctx(), n, R.component(0), R.component(1), R.component(2), lo, hi, 7),
+                        "ParticleSpatialLayout::update");
+        if (Comm->size() < 2) return;
+        pc.migrate();
+    }
+
+private:
+    FieldLayout<Dim>* fl_;
+    Mesh* mesh_;
+    BC bc_ = NO;
+};
+
+// ---- ParticleBase (src/Particle/ParticleBase.h / .hpp) -------------------------------------------------------------------------------
+template <class PLayout>
+class ParticleBase {
+public:
+    using particle_position_type = typename PLayout::particle_position_type;
+    using vector_type            = typename PLayout::vector_type;
+    particle_position_type R;
+    ParticleBase() { attributes_.push_back(&R); }
+    explicit ParticleBase(PLayout& l) : ParticleBase() { initialize(l); }
+    virtual ~ParticleBase() = default;
+    void initialize(PLayout& l) { layout_ = &l; }
+    void addAttribute(detail::ParticleAttribBase& a) { attributes_.push_back(&a); }
+    void setParticleBC(BC bc) { layout_->setParticleBC(bc); }
+    void create(std::size_t nLocal) {
+        for (auto* a : attributes_) a->create(nLocal);
+        localNum_ += nLocal;
+    }
+    std::size_t getLocalNum() const { return localNum_; }
+    std::size_t getTotalNum() const {
+        std::size_t t = localNum_;
+        Comm->allreduce(t, 1, std::plus<std::size_t>());
+        return t;
+    }
+    void setLocalNum(std::size_t n) {
+        localNum_ = n;
+        for (auto* a : attributes_) a->setCount(n);
+    }
+    void update() { layout_->update(*this); }
+    // multi-rank exchange of R and the attributes a derived container exposes through migration_bundle()
+    virtual void migrate() { throw IpplException("ParticleBase::migrate", "container does not expose a migration bundle"); }
+
+protected:
+    PLayout* layout_ = nullptr;
+    std::vector<detail::ParticleAttribBase*> attributes_;
+    std::size_t localNum_ = 0;
+};
+
+// ---- FFTPeriodicPoissonSolver (src/PoissonSolvers/FFTPeriodicPoissonSolver.h; non-owned stage, cuFFT) ------------------------------------
+template <class FieldLHS, class FieldRHS>
+class FFTPeriodicPoissonSolver {
+public:
+    enum OutputType { SOL = 1, GRAD = 2, SOL_AND_GRAD = 3 };
+    FFTPeriodicPoissonSolver() = default;
+    FFTPeriodicPoissonSolver(FieldLHS& lhs, FieldRHS& rhs) {
+        setLhs(lhs);
+        setRhs(rhs);
+    }
+    ~FFTPeriodicPoissonSolver() {
+        if (h_) ipplb_poisson_destroy(h_);
+    }
+    void setRhs(FieldRHS& rhs) {
+        rhs_ = &rhs;
+        if (Comm->size() > 1) throw IpplException("FFTPeriodicPoissonSolver", "the cuFFT stand-in is single-GPU");
+        if (h_) ipplb_poisson_destroy(h_);
+        b200::check(ipplb_poisson_create(b200::ctx(), &rhs.b200_mesh(), &h_), "FFTPeriodicPoissonSolver::setRhs");
+    }
+    void setLhs(FieldLHS& lhs) { lhs_ = &lhs; }
+    // solve(): GRAD output -- E written to lhs interior, rho clobbered like the reference (:53-169)
+    void solve() { b200::check(ipplb_poisson_solve(h_, rhs_->data(), lhs_->data()), "FFTPeriodicPoissonSolver::solve"); }
+
+private:
+    ipplb_poisson* h_ = nullptr;
+    FieldLHS* lhs_    = nullptr;
+    FieldRHS* rhs_    = nullptr;
+};
+
+}  // namespace ippl
+
+// ---- IpplTimings (src/Utility/IpplTimings.h): named wall timers with a stream fence on start/stop -----------------------------------------------
+class IpplTimings {
+public:
+    using TimerRef = int;
+    static TimerRef getTimer(const char* name) {
+        auto& s = state();
+        auto it = s.index.find(name);
+        if (it != s.index.end()) return it->second;
+        s.names.push_back(name);
+        s.total.push_back(0.0);
+        s.start.push_back({});
+        return s.index[name] = (int)s.names.size() - 1;
+    }
+    static void startTimer(TimerRef t) {
+        if (ippl::b200::ctx_ref()) ipplb_sync(ippl::b200::ctx_ref());
+        state().start[t] = std::chrono::steady_clock::now();
+    }
+    static void stopTimer(TimerRef t) {
+        if (ippl::b200::ctx_ref()) ipplb_sync(ippl::b200::ctx_ref());
+        state().total[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - state().start[t]).count();
+    }
+    static double seconds(TimerRef t) { return state().total[t]; }
+    static void print(std::ostream& os = std::cout) {
+        auto& s = state();
+        os << "---------------------------------------------\n     Timings (wall, stream-fenced)\n";
+        for (std::size_t i = 0; i < s.names.size(); ++i)
+            os << s.names[i] << std::string(s.names[i].size() < 24 ? 24 - s.names[i].size() : 1, '.') << " " << s.total[i] << " s\n";
+        os << "---------------------------------------------" << std::endl;
+    }
+
+private:
+    struct State {
+        std::map<std::string, int> index;
+        std::vector<std::string> names;
+        std::vector<double> total;
+        std::vector<std::chrono::steady_clock::time_point> start;
+    };
+    static State& state() {
+        static State s;
+        return s;
+    }
+};
+
+#endif  // IPPL_B200_FACADE_H
