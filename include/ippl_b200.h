@@ -285,6 +285,14 @@ int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push
                         double* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
                         ipplb_bins* bins, double* rho_dev);
 
+/* The same through a sequence of `nbatch` independent host batches (host_arrays[nbatch][6], rho_host[nbatch] or
+ * NULL): upload of batch k+1, compute of batch k and download of batch k-1 overlap (three streams, two device
+ * slots: dev[2], scratch[2], bins[2], rho_dev[2]).  Returns when every batch is back in host memory. */
+int ipplb_pic_step_host_batches(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, long n, int nbatch,
+                                double* const* host_arrays, double q_scalar, const double* efield_dev,
+                                double* const* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
+                                ipplb_bins* const* bins, double* const* rho_dev);
+
 #ifdef __cplusplus
 }
 #endif

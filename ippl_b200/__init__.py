@@ -8,7 +8,7 @@ include/ippl/.  There is NO CPU fallback: without the library or without a CUDA 
 compute call raises.
 """
 from .lib import (Bins, Context, IpplbError, Layout, Mesh, Particles, Poisson, Push, lib, lib_path,  # noqa: F401
-                  exported_symbols, leapfrog_push, nccl_unique_id, penning_push)
+                  exported_symbols, leapfrog_push, lib_particles_array, nccl_unique_id, penning_push)
 
 __all__ = ["Bins", "Context", "IpplbError", "Layout", "Mesh", "Particles", "Poisson", "Push", "lib", "lib_path",
            "exported_symbols", "leapfrog_push", "nccl_unique_id", "penning_push"]

@@ -264,6 +264,15 @@ int ipplb_ctx_destroy(ipplb_ctx* ctx) {
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_in) {
+        cudaStreamDestroy(ctx->s_in);
+        cudaStreamDestroy(ctx->s_out);
+        for (int s = 0; s < 2; ++s) {
+            cudaEventDestroy(ctx->ev_in[s]);
+            cudaEventDestroy(ctx->ev_comp[s]);
+            cudaEventDestroy(ctx->ev_out[s]);
+        }
+    }
     delete ctx;
     return IPPLB_OK;
 }

@@ -90,6 +90,9 @@ struct ipplb_ctx {
     int rank = 0, nranks = 1;
     void* plan = nullptr;  // ipplb::CommPlan*
     const double* d_regions = nullptr;  // [nranks][6] physical regions (device), set by ipplb_ctx_set_layout
+    // copy streams + events of the host-buffer pipeline (ipplb_pic_step_host_batches), created on first use
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 namespace ipplb {

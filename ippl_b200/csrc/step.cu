@@ -87,4 +87,71 @@ int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push
     return IPPLB_OK;
 }
 
+// Pipelined variant over a sequence of independent batches (a "step" = one pass of the hot path over one batch):
+// upload of batch k+1, compute of batch k and download of batch k-1 overlap on three streams, two device slots.
+// Per slot: H2D -> dev; build dev -> scratch; fused step scratch -> dev; compact dev -> scratch; D2H <- scratch.
+int ipplb_pic_step_host_batches(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, long n, int nbatch,
+                                double* const* host_arrays, double q_scalar, const double* efield_dev,
+                                double* const* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
+                                ipplb_bins* const* bins, double* const* rho_dev) {
+    IPPLB_REQUIRE(ctx && mesh && push && host_arrays && dev && scratch && bins && rho_dev && nbatch >= 0,
+                  "pic_step_host_batches: bad arguments");
+    if (!ctx->s_in) {
+        IPPLB_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        IPPLB_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) {
+            IPPLB_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[s], cudaEventDisableTiming));
+            IPPLB_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[s], cudaEventDisableTiming));
+            IPPLB_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming));
+        }
+    }
+    const long cells = ghosted_cells(mesh);
+    auto upload = [&](int k) -> int {
+        const int s = k & 1;
+        IPPLB_REQUIRE(dev[s].capacity >= n && scratch[s].capacity >= n, "pic_step_host_batches: device capacity too small");
+        // the slot's `dev` bundle is free once the compute of batch k-2 is done; callers may also hand the same host
+        // buffers to batches k-2 and k, so wait for that download as well (no-ops for the first two batches)
+        if (k >= 2) {
+            IPPLB_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[s], 0));
+            IPPLB_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[s], 0));
+        }
+        double* d[6] = {dev[s].x, dev[s].y, dev[s].z, dev[s].px, dev[s].py, dev[s].pz};
+        for (int a = 0; a < 6; ++a)
+            IPPLB_CUDA(cudaMemcpyAsync(d[a], host_arrays[6 * k + a], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice,
+                                       ctx->s_in));
+        IPPLB_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+        return IPPLB_OK;
+    };
+    int rc;
+    if (nbatch > 0 && (rc = upload(0))) return rc;
+    for (int k = 0; k < nbatch; ++k) {
+        const int s = k & 1;
+        if (k + 1 < nbatch && (rc = upload(k + 1))) return rc;
+        // compute: needs this batch's upload and (for `scratch`) the download of batch k-2
+        IPPLB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+        if (k >= 2) IPPLB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));
+        ipplb_particles a = dev[s], b = scratch[s];
+        a.n = n; a.q = nullptr; a.q_scalar = q_scalar;
+        if ((rc = ipplb_bins_build(ctx, bins[s], &a, &b))) return rc;
+        if ((rc = ipplb_pic_step(ctx, mesh, push, &b, &a, nullptr, bins[s], efield_dev, rho_dev[s], 2))) return rc;
+        // after the swap inside pic_step `b` names the bucketed result (storage of dev[s]) and `a` the spare one
+        if ((rc = ipplb_bins_compact(ctx, bins[s], &b, &a))) return rc;
+        IPPLB_REQUIRE(a.n == n, "pic_step_host_batches: particle count changed");
+        IPPLB_CUDA(cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+        // download from the compacted bundle (storage of scratch[s]) + rho
+        IPPLB_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[s], 0));
+        double* o[6] = {a.x, a.y, a.z, a.px, a.py, a.pz};
+        for (int c = 0; c < 6; ++c)
+            IPPLB_CUDA(cudaMemcpyAsync(host_arrays[6 * k + c], o[c], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost,
+                                       ctx->s_out));
+        if (rho_host && rho_host[k])
+            IPPLB_CUDA(cudaMemcpyAsync(rho_host[k], rho_dev[s], sizeof(double) * (size_t)cells, cudaMemcpyDeviceToHost,
+                                       ctx->s_out));
+        IPPLB_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->s_out));
+    }
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->s_out));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IPPLB_OK;
+}
+
 }  // extern "C"

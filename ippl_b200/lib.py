@@ -157,6 +157,14 @@ class Particles:
         return [self.arr[k][: self.n].cpu().numpy() for k in names]
 
 
+def lib_particles_array(structs):
+    """ctypes array of ipplb_particles from a list of structs (for the *_batches entry points)"""
+    arr = (_Particles * len(structs))()
+    for i, st in enumerate(structs):
+        arr[i] = st
+    return arr
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 

@@ -663,3 +663,58 @@ def test_multi_gpu_fused_step(world):
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(here, "mgpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and f"MGPU_CHECK_OK world={world}" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_host_batches_pipeline_vs_oracle(ctx):
+    """ipplb_pic_step_host_batches (bench.py's e2e path): three independent host batches through the overlapped
+    upload / compute / download pipeline; every batch comes back with the oracle's particles (bit-exact
+    multiset) and rho (1e-12)."""
+    import ctypes as C
+    import torch
+    import ippl_b200 as ib
+    nr, n, nb = (16, 16, 16), 30000, 3
+    L = 4 * np.pi
+    h = [L / 16] * 3
+    mo, mg = oracle.Mesh.make(nr, (0, 0, 0), h), ib.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(21)
+    ef = 0.1 * rng.normal(size=mg.cells * 3)
+    oracle.halo_periodic(ef, mo.ext, 3, 1, (1, 1, 1), "fill")
+    dt, q = 0.5 * h[0], 0.3
+    push = ib.leapfrog_push(dt)
+    host, want_p, want_rho = [], [], []
+    for k in range(nb):
+        R = [rng.uniform(0, L, n) for _ in range(3)]
+        P = normal_velocities(n, seed=30 + k)
+        Ro, Po = [r.copy() for r in R], [p.copy() for p in P]
+        E = [np.zeros(n) for _ in range(3)]
+        oracle.gather_cic(mo, *Ro, ef, E)
+        for d in range(3):
+            oracle.kick(Po[d], E[d], 0.5 * dt)
+            oracle.kick(Po[d], E[d], 0.5 * dt)
+            oracle.drift(Ro[d], Po[d], dt)
+            oracle.periodic_bc(Ro[d], 0.0, L)
+        rho = oracle.field_zeros(mo)
+        oracle.scatter_cic(mo, *Ro, q, rho)
+        oracle.halo_periodic(rho, mo.ext, 1, 1, (1, 1, 1), "accumulate")
+        host.append([torch.from_numpy(a.copy()).pin_memory() for a in R + P])
+        want_p.append(Ro + Po)
+        want_rho.append(rho)
+    cap = 2 * n
+    slots_p = [ib.Particles(cap, ctx.device, q=q) for _ in range(2)]
+    slots_s = [ib.Particles(cap, ctx.device, q=q) for _ in range(2)]
+    slots_b = [ib.Bins(ctx, mg, cap) for _ in range(2)]
+    slots_r = [ctx.field(mg) for _ in range(2)]
+    rho_host = [torch.empty(mg.cells, dtype=torch.float64).pin_memory() for _ in range(nb)]
+    harr = (C.c_void_p * (6 * nb))(*[host[k][a].data_ptr() for k in range(nb) for a in range(6)])
+    rarr = (C.c_void_p * nb)(*[r.data_ptr() for r in rho_host])
+    rc = ib.lib().ipplb_pic_step_host_batches(
+        ctx._h, C.byref(mg), C.byref(push), C.c_long(n), nb, harr, C.c_double(q), C.c_void_p(_dev(ctx, ef).data_ptr()), rarr,
+        ib.lib_particles_array([p.struct() for p in slots_p]), ib.lib_particles_array([p.struct() for p in slots_s]),
+        (C.c_void_p * 2)(*[b._h.value for b in slots_b]), (C.c_void_p * 2)(*[r.data_ptr() for r in slots_r]))
+    assert rc == 0, ib.lib().ipplb_last_error().decode()
+    for k in range(nb):
+        got = [a.numpy() for a in host[k]]
+        assert np.array_equal(_canon(got), _canon(want_p[k])), f"batch {k}"
+        assert rel_l2(rho_host[k].numpy(), want_rho[k]) <= TOL_SUM, f"batch {k}"
+    for b in slots_b:
+        b.close()
