@@ -349,9 +349,9 @@ def main():
         rk = "gather_push"
         tail_frac = None
     achieved = alg_bytes[rk] / (kern[rk] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one fused_step_kernel launch on this exact workload, from the
-    # committed `ncu --set full` capture (profiles/r1_fused_ncu_full.md: 6.608 GB + 6.504 GB); null otherwise
-    traffic = 13.112e9 if (bins is not None and world == 1 and args.log2_particles == 27) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one fused_step3_kernel launch on this exact workload, from the
+    # committed `ncu --set full` capture (profiles/r1_fused3_ncu_full.md: 6.603 GB + 6.454 GB); null otherwise
+    traffic = 13.056e9 if (bins is not None and world == 1 and args.log2_particles == 27) else None
     step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * ncell_int
     step_achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
 
