@@ -668,6 +668,108 @@ protected:
     std::size_t localNum_ = 0;
 };
 
+// ---- RegionLayout (src/Region/RegionLayout.h): physical region of every rank ---------------------------------------------------------
+namespace detail {
+    template <typename T, unsigned Dim, class Mesh = UniformCartesian<T, Dim>>
+    class RegionLayout {
+    public:
+        RegionLayout() = default;
+        RegionLayout(const FieldLayout<Dim>& fl, const Mesh& mesh, bool /*fem*/ = false) {
+            double o[3], h[3];
+            for (int d = 0; d < 3; ++d) {
+                o[d] = mesh.getOrigin()[d];
+                h[d] = mesh.getMeshSpacing()[d];
+            }
+            regions_.resize(6 * (std::size_t)Comm->size());
+            b200::check(ipplb_layout_regions(fl.handle(), o, h, regions_.data()), "RegionLayout");
+        }
+        const std::vector<double>& regions() const { return regions_; }  // [rank][min 3, max 3]
+
+    private:
+        std::vector<double> regions_;
+    };
+}  // namespace detail
+
+// ---- Random (src/Random/Distribution.h, NormalDistribution.h, InverseTransformSampling.h, Randn.h) on the device sampler ------------------
+namespace random {
+    // Distribution<T, Dim, 2 * Dim, Functions>: the reference takes host/device functors (CDF, PDF, Estimate); the
+    // facade names the three families the alpine managers use (one per dimension) and the device evaluates them
+    enum Kind { UNIFORM = IPPLB_DIST_UNIFORM, COSINE = IPPLB_DIST_COSINE, NORMAL = IPPLB_DIST_NORMAL };
+    template <typename T, unsigned Dim>
+    class Distribution {
+        static_assert(Dim == 3, "the B200 path is three-dimensional");
+
+    public:
+        Distribution(const std::array<Kind, Dim>& kind, const T* par_p) {
+            for (unsigned d = 0; d < Dim; ++d) {
+                d_.kind[d]        = kind[d];
+                d_.par[2 * d]     = par_p[2 * d];
+                d_.par[2 * d + 1] = par_p[2 * d + 1];
+            }
+        }
+        const ipplb_dist& handle() const { return d_; }
+
+    private:
+        ipplb_dist d_{};
+    };
+    template <typename T, unsigned Dim>
+    class NormalDistribution : public Distribution<T, Dim> {
+    public:
+        explicit NormalDistribution(const T* par_p) : Distribution<T, Dim>({NORMAL, NORMAL, NORMAL}, par_p) {}
+    };
+
+    // InverseTransformSampling<T, Dim, DeviceType, Distribution> (InverseTransformSampling.h:30-256).  generate()
+    // takes a seed instead of a Kokkos::Random_XorShift64_Pool: the stream is counter based (Philox4x32-10).
+    template <typename T, unsigned Dim, class DeviceType, class Dist>
+    class InverseTransformSampling {
+    public:
+        using size_type = detail::size_type;
+        template <class RegionLayout>
+        InverseTransformSampling(Dist& dist, Vector<T, Dim>& rmax, Vector<T, Dim>& rmin, const RegionLayout& rlayout,
+                                 size_type ntotal)
+            : dist_(dist) {
+            const int nr = Comm->size();
+            std::vector<long> nloc(nr);
+            std::vector<double> ub(6 * (std::size_t)nr);
+            double lo[3], hi[3];
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = rmin[d];
+                hi[d] = rmax[d];
+            }
+            b200::check(ipplb_sample_counts(&dist.handle(), lo, hi, rlayout.regions().data(), nr, (long)ntotal, nloc.data(),
+                                            ub.data()),
+                        "InverseTransformSampling");
+            nlocal_ = (size_type)nloc[Comm->rank()];
+            for (int d = 0; d < 3; ++d) {
+                umin_[d] = ub[6 * Comm->rank() + d];
+                umax_[d] = ub[6 * Comm->rank() + 3 + d];
+            }
+        }
+        size_type getLocalSamplesNum() const { return nlocal_; }
+        void setLocalSamplesNum(size_type n) { nlocal_ = n; }
+        // generate(view, rand_pool64), :235-244
+        void generate(ParticleAttrib<Vector<T, Dim>>& R, std::uint64_t seed) { generate(R, 0, nlocal_, seed); }
+        void generate(ParticleAttrib<Vector<T, Dim>>& R, size_type begin, size_type end, std::uint64_t seed) {
+            b200::check(ipplb_sample_positions(b200::ctx(), &dist_.handle(), umin_, umax_, seed, (long)begin, (long)(end - begin),
+                                               R.component(0) + begin, R.component(1) + begin, R.component(2) + begin),
+                        "InverseTransformSampling::generate");
+        }
+
+    private:
+        Dist dist_;
+        size_type nlocal_ = 0;
+        double umin_[3], umax_[3];
+    };
+
+    // Kokkos::parallel_for(RangePolicy(begin, end), randn<T, Dim>(P, pool, mu, sd)), Randn.h:30-94
+    template <typename T, unsigned Dim>
+    void randn(ParticleAttrib<Vector<T, Dim>>& P, std::uint64_t seed, const T* mu, const T* sd, std::size_t begin, std::size_t end) {
+        b200::check(ipplb_sample_normal(b200::ctx(), mu, sd, seed, (long)begin, (long)(end - begin), P.component(0) + begin,
+                                        P.component(1) + begin, P.component(2) + begin),
+                    "random::randn");
+    }
+}  // namespace random
+
 // ---- FFTPeriodicPoissonSolver (src/PoissonSolvers/FFTPeriodicPoissonSolver.h; non-owned stage, cuFFT) ------------------------------------
 template <class FieldLHS, class FieldRHS>
 class FFTPeriodicPoissonSolver {

@@ -264,9 +264,84 @@ int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, c
 /* Contiguous copy (bucket order, then tail) of the bucketed `cur` into out[0..n). Sets out->n (syncs). */
 int ipplb_bins_compact(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* cur,
                        ipplb_particles* out);
+/* the same reduction as ipplb_particles_kinetic over the bucketed store (buckets + tail), no compaction needed */
+int ipplb_bins_kinetic(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* cur, double* out_host);
 /* read-only access for tests: copies start/cap/count of the current buffer to host arrays [ntiles] */
 int ipplb_bins_ntiles(const ipplb_bins* bins);
 int ipplb_bins_tables(ipplb_ctx* ctx, ipplb_bins* bins, int* start_host, int* cap_host, int* count_host);
+
+/* ---- diagnostics of the alpine dumps ------------------------------------------ */
+/* Field part of PenningTrapManager::dumpData (demos/alpine/PenningTrapManager.h:346-389), LandauDampingManager::
+ * dumpLandau (LandauDampingManager.h:339-366) and BumponTailInstabilityManager::dumpBumponTailInstability
+ * (BumponTailInstabilityManager.h:448-480) in one pass over the interior of the ghosted AoS-3 field:
+ *   out_host[0..2] = sum(E_d^2), out_host[3..5] = max|E_d|, out_host[6] = sum(dot(E,E)) (= rho.sum() after
+ *   rho = dot(E,E), PenningTrapManager.h:350-352).  Local to the rank (chain ipplb_allreduce_sum_f64). */
+int ipplb_field_energy_stats(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* efield, double out_host[7]);
+/* norm(rho) ingredients (src/Field/BareField.hpp innerProduct/norm, p = 2): out_host[0] = sum over the interior of
+ * f^2, out_host[1] = max|f| */
+int ipplb_field_norm_stats(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* field, double out_host[2]);
+/* "Particle Kinetic Energy" reduction, PenningTrapManager.h:354-362: out_host[0] = sum_i dot(P_i, P_i) (the caller
+ * multiplies by 0.5 like the reference) over contiguous arrays. */
+int ipplb_particles_kinetic(ipplb_ctx* ctx, long n, const double* px, const double* py, const double* pz,
+                            double* out_host);
+
+/* ---- particle initialisation on the device ------------------------------------ */
+/* Distribution<T, Dim, 2*Dim, Functions> of the alpine managers, one kind per dimension, parameters par[2d],
+ * par[2d+1] (src/Random/Distribution.h:60-110):
+ *   UNIFORM  cdf x, pdf 1, estimate u                                   (src/Random/UniformDistribution.h:17-26)
+ *   COSINE   cdf x + (a/k) sin(k x), pdf 1 + a cos(k x), estimate u; a = par[2d], k = par[2d+1]
+ *            (demos/alpine/LandauDampingManager.h:21-44, BumponTailInstabilityManager.h:23-52)
+ *   NORMAL   cdf 0.5 (1 + erf((x-mu)/(sd sqrt 2))), pdf gaussian, estimate mu; mu = par[2d], sd = par[2d+1]
+ *            (src/Random/NormalDistribution.h:11-28) */
+enum { IPPLB_DIST_UNIFORM = 0, IPPLB_DIST_COSINE = 1, IPPLB_DIST_NORMAL = 2 };
+typedef struct ipplb_dist {
+    int kind[3];
+    double par[6];
+} ipplb_dist;
+/* InverseTransformSampling(dist, rmax, rmin, rlayout, ntotal) for every rank at once (host only),
+ * src/Random/InverseTransformSampling.h:48-61, 106-131: nlocal_out[r] = (size_t)(prod_d (cdf(locmax)-cdf(locmin)) /
+ * prod_d (cdf(rmax)-cdf(rmin)) * ntotal), the first (ntotal - sum) ranks get one more; ubounds_out[r][6] = umin[3],
+ * umax[3] = cdf of the rank's region bounds.  regions[nranks][6] = min[3], max[3] (ipplb_layout_regions). */
+int ipplb_sample_counts(const ipplb_dist* dist, const double rmin[3], const double rmax[3], const double* regions,
+                        int nranks, long ntotal, long* nlocal_out, double* ubounds_out);
+/* InverseTransformSampling::generate, :172-244: per dimension u = drand(umin, umax), x = estimate(u), then
+ * NewtonRaphson::solve (src/Random/Utility.h:27-60: while iter < 20 && |cdf(x) - u| > 1e-12: x -= (cdf(x) - u) /
+ * pdf(x)).  The uniform stream is counter based (Philox4x32-10, key = seed, counter = (first_id + i, dimension)):
+ * reproducible on any decomposition of the id range, unlike Kokkos::Random_XorShift64_Pool whose stream assignment
+ * is backend dependent.  Writes x,y,z[0..n). */
+int ipplb_sample_positions(ipplb_ctx* ctx, const ipplb_dist* dist, const double umin[3], const double umax[3],
+                           uint64_t seed, long first_id, long n, double* x, double* y, double* z);
+/* ippl::random::randn<T, Dim> (src/Random/Randn.h:82-94): p_d = mu[d] + sd[d] * N(0,1); normals by Box-Muller on
+ * the same counter-based stream (dimensions 3, 4 of the counter).  Writes px,py,pz[0..n). */
+int ipplb_sample_normal(ipplb_ctx* ctx, const double mu[3], const double sd[3], uint64_t seed, long first_id,
+                        long n, double* px, double* py, double* pz);
+/* rho = distR.getFullPdf(xvec) on the interior, xvec = (global cell index + 0.5) * h + origin: the weight field of the
+ * first repartition (LandauDampingManager.h:188-199; Distribution.h:104-112 product of the per-dimension pdfs) */
+int ipplb_field_fill_pdf(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_dist* dist, double* field);
+
+/* ---- orthogonal recursive bisection -------------------------------------------- */
+/* OrthogonalRecursiveBisection::binaryRepartition, src/Decomposition/OrthogonalRecursiveBisection.hpp:14-105, as a
+ * host state machine (findCutAxis :107-116, findMedian :185-216, cutDomain :218-232) fed with the globally reduced
+ * plane weights of perpendicularReduction (:118-183), which is the only device work:
+ *   ipplb_orb_begin -> { ipplb_orb_next (domain + axis to reduce) -> plane sums -> ipplb_orb_cut } ... -> ipplb_orb_finish */
+typedef struct ipplb_orb ipplb_orb;
+int ipplb_orb_begin(ipplb_orb** out, const int ng[3], int nranks);
+/* *pending = 1 while a cut is pending: dom_lo/dom_hi (inclusive global indices) and the cut axis of the next cut */
+int ipplb_orb_next(ipplb_orb* orb, int dom_lo[3], int dom_hi[3], int* axis, int* pending);
+/* feeds the reduced plane weights (n = length of the domain along the axis) and performs the cut */
+int ipplb_orb_cut(ipplb_orb* orb, const double* reduced_host, int n);
+/* boxes_out[nranks][6] = lo[3], hi[3]; *ok = 0 when a box has an axis of length 1 (the reference then keeps the old
+ * layout, :93-99).  Destroys the state. */
+int ipplb_orb_finish(ipplb_orb* orb, int* boxes_out, int* ok);
+/* perpendicularReduction + allreduce: out_host[k] = sum over ranks of the sum of `field`'s interior cells in plane
+ * dom_lo[axis] + k of the domain (cells outside the rank's box contribute nothing). */
+int ipplb_orb_plane_sums(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* field, int axis, const int dom_lo[3],
+                         const int dom_hi[3], double* out_host);
+/* the whole of binaryRepartition on the weight field (collective): new boxes into `boxes_out`; the caller applies
+ * them with ipplb_layout_set_boxes + ipplb_ctx_set_layout, re-lays its fields and calls ipplb_update, like
+ * LoadBalancer::updateLayout (demos/alpine/LoadBalancer.hpp:54-88). */
+int ipplb_orb_repartition(ipplb_ctx* ctx, const ipplb_mesh* mesh, int nranks, const double* weight_field,
+                          int* boxes_out, int* ok);
 
 /* ---- whole-step conveniences used by bench.py / the facade ---------------------------------- */
 /* One PIC step of the metric (scatter + push + gather) on resident particles, single rank:

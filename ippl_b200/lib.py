@@ -111,6 +111,61 @@ def penning_push(dt, origin, length, Bext=5.0, kick2=1, kick1=1, drift=1, bc=1):
     return p
 
 
+class Dist(C.Structure):
+    """ipplb_dist: per-dimension distribution kind (0 uniform, 1 cosine, 2 normal) + parameters par[2d], par[2d+1]"""
+    _fields_ = [("kind", C.c_int * 3), ("par", C.c_double * 6)]
+
+    @staticmethod
+    def make(kind, par):
+        d = Dist()
+        for k in range(3):
+            d.kind[k] = int(kind[k])
+        for k in range(6):
+            d.par[k] = float(par[k])
+        return d
+
+
+def sample_counts(dist, rmin, rmax, regions, ntotal):
+    """InverseTransformSampling::updateBounds for every rank (host only): (nlocal[nranks], ubounds[nranks][6])"""
+    import numpy as np
+    reg = np.ascontiguousarray(regions, dtype=np.float64)
+    nr = reg.shape[0]
+    nloc = (C.c_long * nr)()
+    ub = np.zeros((nr, 6), dtype=np.float64)
+    _check(lib().ipplb_sample_counts(C.byref(dist), (C.c_double * 3)(*rmin), (C.c_double * 3)(*rmax),
+                                     reg.ctypes.data_as(C.c_void_p), nr, C.c_long(ntotal), nloc,
+                                     ub.ctypes.data_as(C.c_void_p)))
+    return list(nloc), ub
+
+
+class Orb:
+    """Host state machine of OrthogonalRecursiveBisection::binaryRepartition (works without a GPU)."""
+
+    def __init__(self, ng, nranks):
+        self._h = C.c_void_p()
+        self.nranks = nranks
+        _check(lib().ipplb_orb_begin(C.byref(self._h), (C.c_int * 3)(*ng), nranks))
+
+    def next(self):
+        """(lo[3], hi[3], axis) of the pending cut, or None"""
+        lo, hi, ax, pend = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int(), C.c_int()
+        _check(lib().ipplb_orb_next(self._h, lo, hi, C.byref(ax), C.byref(pend)))
+        return (list(lo), list(hi), ax.value) if pend.value else None
+
+    def cut(self, reduced):
+        import numpy as np
+        w = np.ascontiguousarray(reduced, dtype=np.float64)
+        _check(lib().ipplb_orb_cut(self._h, w.ctypes.data_as(C.c_void_p), len(w)))
+
+    def finish(self):
+        import numpy as np
+        boxes = np.zeros((self.nranks, 6), dtype=np.int32)
+        ok = C.c_int()
+        _check(lib().ipplb_orb_finish(self._h, boxes.ctypes.data_as(C.c_void_p), C.byref(ok)))
+        self._h = C.c_void_p()
+        return boxes, bool(ok.value)
+
+
 class Particles:
     """SoA fp64 particle bundle in device memory (torch tensors own the storage)."""
 
@@ -294,6 +349,53 @@ class Context:
             parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
         parts.n = int(s.n)
 
+    # -- diagnostics, sampling, ORB -----------------------------------------------
+    def field_energy_stats(self, mesh, ef):
+        """(sum E_d^2 [3], max|E_d| [3], sum dot(E,E)) over the interior"""
+        out = (C.c_double * 7)()
+        _check(lib().ipplb_field_energy_stats(self._h, C.byref(mesh), _ptr(ef), out))
+        return list(out[0:3]), list(out[3:6]), out[6]
+
+    def field_norm_stats(self, mesh, f):
+        out = (C.c_double * 2)()
+        _check(lib().ipplb_field_norm_stats(self._h, C.byref(mesh), _ptr(f), out))
+        return out[0], out[1]
+
+    def particles_kinetic(self, parts, n=None):
+        out = C.c_double()
+        n = parts.n if n is None else n
+        _check(lib().ipplb_particles_kinetic(self._h, C.c_long(n), _ptr(parts.arr["px"]), _ptr(parts.arr["py"]),
+                                             _ptr(parts.arr["pz"]), C.byref(out)))
+        return out.value
+
+    def sample_positions(self, dist, umin, umax, seed, first_id, n, parts):
+        _check(lib().ipplb_sample_positions(self._h, C.byref(dist), (C.c_double * 3)(*umin), (C.c_double * 3)(*umax),
+                                            C.c_uint64(seed), C.c_long(first_id), C.c_long(n), _ptr(parts.arr["x"]),
+                                            _ptr(parts.arr["y"]), _ptr(parts.arr["z"])))
+
+    def sample_normal(self, mu, sd, seed, first_id, n, parts):
+        _check(lib().ipplb_sample_normal(self._h, (C.c_double * 3)(*mu), (C.c_double * 3)(*sd), C.c_uint64(seed),
+                                         C.c_long(first_id), C.c_long(n), _ptr(parts.arr["px"]), _ptr(parts.arr["py"]),
+                                         _ptr(parts.arr["pz"])))
+
+    def field_fill_pdf(self, mesh, dist, f):
+        _check(lib().ipplb_field_fill_pdf(self._h, C.byref(mesh), C.byref(dist), _ptr(f)))
+
+    def orb_plane_sums(self, mesh, f, axis, lo, hi):
+        import numpy as np
+        out = np.zeros(hi[axis] - lo[axis] + 1, dtype=np.float64)
+        _check(lib().ipplb_orb_plane_sums(self._h, C.byref(mesh), _ptr(f), axis, (C.c_int * 3)(*lo), (C.c_int * 3)(*hi),
+                                          out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def orb_repartition(self, mesh, nranks, weight):
+        import numpy as np
+        boxes = np.zeros((nranks, 6), dtype=np.int32)
+        ok = C.c_int()
+        _check(lib().ipplb_orb_repartition(self._h, C.byref(mesh), nranks, _ptr(weight), boxes.ctypes.data_as(C.c_void_p),
+                                           C.byref(ok)))
+        return boxes, bool(ok.value)
+
     # -- multi-GPU ---------------------------------------------------------------------------
     def comm_init(self, rank, nranks, id_bytes=None):
         self.rank, self.nranks = rank, nranks
@@ -390,6 +492,13 @@ class Bins:
         _check(lib().ipplb_bins_compact(self.ctx._h, self._h, C.byref(s), C.byref(d)))
         out.n, out.q_scalar = int(d.n), cur.q_scalar
         return out.n
+
+    def kinetic(self, cur):
+        """sum_i dot(P_i, P_i) over the bucketed store (no compaction)"""
+        out = C.c_double()
+        s = cur.struct()
+        _check(lib().ipplb_bins_kinetic(self.ctx._h, self._h, C.byref(s), C.byref(out)))
+        return out.value
 
     def tables(self):
         import numpy as np

@@ -16,15 +16,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "demos", "LandauDamping")
 
 
-def _run(tmp_path, name, extra=()):
+def _run(tmp_path, name, extra=(), app="LandauDamping", csv="FieldLandau_1_manager.csv", grid=16, np_=10000000, nt=25):
     d = tmp_path / name
     d.mkdir()
-    if not os.path.exists(EXE):
+    exe = os.path.join(ROOT, "demos", app)
+    if not os.path.exists(exe):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "demos"), "-s"])
-    cmd = [EXE, "16", "16", "16", "10000000", "25", "FFT", "0.01", "LeapFrog", "--overallocate", "2.0", "--info", "0", *extra]
+    cmd = [exe, str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
+           "--info", "0", *extra]
     out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    return np.loadtxt(d / "data" / "FieldLandau_1_manager.csv", skiprows=1), out.stdout
+    return np.loadtxt(d / "data" / csv, skiprows=1), out.stdout
 
 
 def test_landau_facade_matches_reference_golden_and_fused(tmp_path):
@@ -38,3 +40,40 @@ def test_landau_facade_matches_reference_golden_and_fused(tmp_path):
     fused, log2 = _run(tmp_path, "fused", extra=("--fused",))
     assert np.max(np.abs(fused[:, 1:] - got[:, 1:]) / np.abs(got[:, 1:])) <= 1e-9
     assert "fusedStep" in log2 and "pushVelocity" in log
+
+
+def test_bumpontail_facade_fused_matches_unfused_and_linear_theory(tmp_path):
+    """BumponTailInstability (demos/alpine/BumponTailInstabilityManager.h): device-side sampling (uniform x, y;
+    1 + delta cos(k z) in z; bulk + beam Gaussians), Ez energy CSV.  At t = 0 the field is the imposed perturbation:
+    E_z = (delta / k) sin(k z) -> energy = 0.5 (delta / k)^2 L^3 (plus particle noise)."""
+    kw = dict(app="BumponTailInstability", csv="FieldBumponTail_1_manager.csv", grid=16, np_=4000000, nt=10)
+    got, log = _run(tmp_path, "bt_unfused", **kw)
+    fused, log2 = _run(tmp_path, "bt_fused", extra=("--fused",), **kw)
+    assert got.shape == fused.shape == (11, 3)
+    assert np.max(np.abs(fused[:, 1:] - got[:, 1:]) / np.abs(got[:, 1:])) <= 1e-9
+    k, delta = 0.21, 0.01
+    L = 2 * np.pi / k
+    theory = 0.5 * (delta / k) ** 2 * L ** 3
+    assert 0.8 * theory <= got[0, 1] <= 1.6 * theory, (got[0, 1], theory)
+    assert "fusedStep" in log2 and "pushVelocity" in log
+
+
+def test_penningtrap_facade_fused_matches_unfused(tmp_path):
+    """PenningTrap (demos/alpine/PenningTrapManager.h): Gaussian blob sampled on the device, Kick1 / drift / Kick2 in
+    the external fields, dumpData CSV.  The fused step (IPPLB_PUSH_PENNING) reproduces the field columns of the
+    reference-shaped sequence; its kinetic column is taken before the closing kick (documented), so it is compared
+    at a looser tolerance."""
+    kw = dict(app="PenningTrap", csv="ParticleField_1_manager.csv", grid=32, np_=2000000, nt=12)
+    got, log = _run(tmp_path, "pt_unfused", **kw)
+    fused, log2 = _run(tmp_path, "pt_fused", extra=("--fused",), **kw)
+    assert got.shape == fused.shape == (13, 8)
+    fields = [1, 4, 5, 6, 7]   # potential energy, rho norm, |Ex|, |Ey|, |Ez|
+    assert np.max(np.abs(fused[:, fields] - got[:, fields]) / np.abs(got[:, fields])) <= 1e-8
+    assert np.max(np.abs(fused[:, 2] - got[:, 2]) / got[:, 2]) <= 2e-2
+    assert np.isfinite(got).all() and (got[:, 1:] > 0).all()
+    # v ~ N(0, 1) per component: kinetic energy 0.5 sum |P|^2 = 1.5 N at t = 0
+    assert abs(got[0, 2] / (1.5 * 2000000) - 1.0) <= 5e-3
+    # the potential energy column is 0.5 h^3 sum |E|^2 = 0.5 h^3 (|Ex|^2 + |Ey|^2 + |Ez|^2)
+    h3 = (20.0 / 32) ** 3
+    assert np.allclose(got[:, 1], 0.5 * h3 * (got[:, 5] ** 2 + got[:, 6] ** 2 + got[:, 7] ** 2), rtol=1e-8)
+    assert "fusedStep" in log2
