@@ -8,7 +8,11 @@ ParticleSpatialLayout::update, scatter, halo accumulate -- the reference order) 
 with what the CUDA path produced over NCCL:
   * ownership and migration counts: bit-exact (sent / received per rank pair, particles per rank),
   * the particles a rank holds after the step: the same multiset, bit for bit,
-  * rho after accumulateHalo and E after fillHalo: relative L2 <= 1e-12 (north_star tolerance).
+  * rho after accumulateHalo and E after fillHalo: relative L2 <= 1e-12 (north_star tolerance),
+  * then one orthogonal-recursive-bisection repartition (scatterR weights, plane sums reduced over
+    NCCL, findMedian cuts) whose boxes equal the oracle's binaryRepartition, followed by LoadBalancer::updateLayout
+    (new FieldLayout, re-laid fields, ParticleSpatialLayout::update to the new owners, re-bucketing) and two more
+    steps on the new decomposition held to the same checks.
 Used by tests/test_gpu_parity.py::test_multi_gpu_fused_step (skipped with fewer than 2 GPUs)."""
 import os
 import sys
@@ -62,6 +66,7 @@ def main():
     n = 60000
     rng = np.random.default_rng(2024)
     R = [rng.uniform(0, Lg[d], n) for d in range(3)]
+    R[0] = np.clip(np.mod(rng.normal(0.3 * Lg[0], 0.2 * Lg[0], n), Lg[0]), 1e-9, Lg[0])  # off-centre blob: ORB has work to do
     R[0][:4] = [0.0, Lg[0], regs[0][3], np.nextafter(regs[0][3], np.inf)]  # on region / domain boundaries
     P = [2.0 * p for p in normal_velocities(n, seed=5)]
     dt, q = 0.5 * h[0], -0.01
@@ -85,8 +90,8 @@ def main():
     exit_buf = torch.zeros(6 * exit_cap, dtype=torch.float64, device=dev)
     region = list(regs[rank])
 
-    nsteps = 3
-    for it in range(nsteps):
+    def step(it):
+        nonlocal parts_o
         # oracle, all ranks: fillHalo(E); gather; kick, kick, drift; update (BC + migrate); scatter; accumulateHalo
         oracle.halo_full(ng, boxes, ef_o, 3, "fill")
         for r in range(world):
@@ -140,6 +145,63 @@ def main():
         assert int(tot[0]) == n
         if rank == 0:
             print(f"step {it}: ok  sent={sent} recv={recv} n_local={nloc} tail={ntail} rho_rel_l2={err:.2e}", flush=True)
+
+    for it in range(3):
+        step(it)
+
+    # ---- ORB repartition (OrthogonalRecursiveBisection::binaryRepartition + LoadBalancer::updateLayout) ----------
+    from oracle import extras as ox
+    nloc = bins.status()[0]
+    flat = ib.Particles(cap, dev, q=q)
+    assert bins.compact(cur, flat) == nloc
+    w = ctx.field(mesh)
+    ctx.scatter(mesh, flat.arr["x"][:nloc], flat.arr["y"][:nloc], flat.arr["z"][:nloc], 1.0, w)   # scatterR: weight 1
+    ctx.halo_exchange(w, 1, "accumulate")
+    new_boxes, ok = ctx.orb_repartition(mesh, world, w)
+    w_o = [oracle.field_zeros(m) for m in meshes_o]
+    for r in range(world):
+        p = parts_o[r]
+        oracle.scatter_cic(meshes_o[r], p["x"], p["y"], p["z"], 1.0, w_o[r])
+    oracle.halo_full(ng, boxes, w_o, 1, "accumulate")
+    W = np.zeros(ng[::-1])
+    for r in range(world):
+        b = boxes[r]
+        W[b[2]:b[5] + 1, b[1]:b[4] + 1, b[0]:b[3] + 1] = oracle.interior(w_o[r], meshes_o[r])
+    want_boxes, want_ok = ox.orb_repartition(ng, world, W)
+    assert ok and want_ok, "ORB could not repartition"
+    assert np.array_equal(new_boxes, np.asarray(want_boxes, dtype=np.int32)), f"ORB boxes {new_boxes.tolist()} != oracle {want_boxes}"
+    assert not np.array_equal(new_boxes, boxes), "the blob should have moved the cut"
+    # LoadBalancer::updateLayout: fields and particle layout follow the new FieldLayout, then pc->update()
+    layout.set_boxes(new_boxes)
+    boxes = layout.boxes()
+    mesh = layout.mesh(rank, origin, h)
+    ctx.set_layout(layout, origin, h)
+    regs = layout.regions(origin, h)
+    assert np.array_equal(regs, oracle.regions(ng, boxes, origin, h))
+    region = list(regs[rank])
+    meshes_o = [oracle.Mesh.make(ng, origin, h, first=tuple(boxes[r, :3]), nl=tuple(boxes[r, 3:] - boxes[r, :3] + 1))
+                for r in range(world)]
+    ef_o = [0.1 * np.random.default_rng(200 + r).normal(size=m.ext[0] * m.ext[1] * m.ext[2] * 3) for r, m in enumerate(meshes_o)]
+    before = [len(p["x"]) for p in parts_o]
+    parts_o = oracle.update(ng, boxes, origin, h, parts_o)
+    flat.n = nloc
+    sent, recv = ctx.update(flat)
+    assert flat.n == len(parts_o[rank]["x"]), (flat.n, len(parts_o[rank]["x"]))
+    want = [parts_o[rank][k] for k in ("x", "y", "z", "px", "py", "pz")]
+    assert np.array_equal(canon(flat.host()), canon(want)), f"rank {rank}: particles after the ORB update differ from the oracle"
+    imb_old = max(before) / (n / world)
+    imb_new = max(len(p["x"]) for p in parts_o) / (n / world)
+    assert imb_new < imb_old, (imb_old, imb_new)
+    bins.close()
+    bins = ib.Bins(ctx, mesh, cap)
+    bins.build(flat, cur)
+    ef = torch.from_numpy(ef_o[rank].copy()).to(dev)
+    rho = ctx.field(mesh)
+    if rank == 0:
+        print(f"ORB: boxes {boxes.tolist()} imbalance {imb_old:.3f} -> {imb_new:.3f}, moved {sum(sent)} particles from rank 0", flush=True)
+    for it in range(3, 5):
+        step(it)
+
     dist.barrier()
     if rank == 0:
         print(f"MGPU_CHECK_OK world={world}")
