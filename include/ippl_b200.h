@@ -241,7 +241,8 @@ int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* in
  * (rho +=; caller zeroes rho and chains the halo accumulate).  Asynchronous on the context's stream.
  * Input is streamed with bulk async copies (TMA, cp.async.bulk + mbarrier) by a producer warp.
  * Particles that left the rank's region (multi-GPU: reference ownership test, ParticleSpatialLayout.hpp:
- * 316-330) go to exit_buf[6][exit_cap] (x,y,z,px,py,pz) and are not deposited.
+ * 316-330) are not deposited: each is appended as one record (x,y,z,px,py,pz) to its destination rank's segment of
+ * exit_buf[nranks][exit_cap / nranks][6] (16-byte aligned; one rank: exit_buf[exit_cap][6]).
  * Replaces, for one step: ParticleAttrib::operator= x3 (ParticleAttrib.hpp:118-130), applyBC
  * (ParticleLayout.hpp:34-74), gather (:193-246) and scatter (:132-184). */
 int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_push* push, const ipplb_particles* cur,

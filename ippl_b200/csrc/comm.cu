@@ -463,7 +463,7 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
     IPPLB_NCCL(ncclGroupEnd());
     ctx->launches++;
     if (na > 0) {
-        unpack_arrivals_kernel<<<grid1d(na), 256, 0, ctx->stream>>>(nr, d_roff, d_rcnt, na, rb, A, holes, nh, n);
+        unpack_arrivals_kernel<<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(nr, d_roff, d_rcnt, na, rb, A, holes, nh, n);
         IPPLB_CHECK_LAUNCH(ctx);
     }
     if (nh > na) {
@@ -481,15 +481,35 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
 }
 
 // Migration for the bucketed store.  The fused step already applied the BC and the ownership test, found every
-// leaver's destination rank (reference search order) and grouped the leavers per destination in exit_buf
-// [nranks][6][exit_cap / nranks].  Here: one all-gather of the per-destination counts, ONE host sync (counts +
-// tail position), one grouped ncclSend/ncclRecv that lands the arrivals directly in the tail of `cur`, one
-// commit kernel, and one scatter that deposits the arrivals into rho (the reference scatters after update(), so
-// arrivals belong to this step's rho: AlpineManager.h:157-175).
-__global__ void migrate_commit_kernel(int add, int* __restrict__ state, int* __restrict__ misc) {
-    state[BS_TAIL_COUNT] += add;
-    misc[BM_ST_TOTAL] += add;
-    misc[BM_ST_TAIL] += add;
+// leaver's destination rank (reference search order) and appended it as one 48-byte record to that rank's segment
+// of exit_buf [nranks][exit_cap / nranks][6].  Here: one all-gather of the per-destination counts, ONE host sync
+// (counts + tail position), ONE ncclSend + ncclRecv per peer (a segment is one contiguous message) into a staging
+// buffer, and ONE kernel that turns the arrived records into SoA slots behind the tail of `cur`, commits the tail
+// count and deposits the arrivals into rho (the reference scatters after update(), so arrivals belong to this
+// step's rho: AlpineManager.h:157-175).
+__global__ void __launch_bounds__(256)
+arrivals_kernel(MeshDev m, const double* __restrict__ recs, int na, long tail_pos, double* __restrict__ x,
+                double* __restrict__ y, double* __restrict__ z, double* __restrict__ px, double* __restrict__ py,
+                double* __restrict__ pz, double q, double* __restrict__ rho, int* __restrict__ state,
+                int* __restrict__ misc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        state[BS_TAIL_COUNT] += na;
+        misc[BM_ST_TOTAL] += na;
+        misc[BM_ST_TAIL] += na;
+    }
+    if (i >= na) return;
+    const double2* rec = reinterpret_cast<const double2*>(recs + (size_t)i * 6);
+    const double2 a = rec[0], b = rec[1], c = rec[2];
+    const long g = tail_pos + i;
+    x[g] = a.x; y[g] = a.y; z[g] = b.x;
+    px[g] = b.y; py[g] = c.x; pz[g] = c.y;
+    if (rho) {
+        Cic cc;
+        cic_setup(m, a.x, a.y, b.x, cc);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) atomicAdd(&rho[cic_node(m, cc.a, n)], ipplb::dmul(q, cic_weight(cc.whi, n)));
+    }
 }
 
 }  // extern "C"  (kernel above has C++ linkage)
@@ -540,29 +560,27 @@ int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, cons
         set_error("bins_migrate: %ld arrivals do not fit behind the tail (%ld of %ld used)", na, tail_pos, b->capacity);
         return IPPLB_ERR_CAPACITY;
     }
-    double* dst[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
+    int rc;
+    if ((rc = ensure(ctx, ctx->recv, sizeof(double) * (size_t)(6 * na + 2)))) return rc;
+    double* stage = (double*)ctx->recv.ptr;
     IPPLB_NCCL(ncclGroupStart());
     for (int r = 0; r < nr; ++r) {
         const int sc = P->h_matrix[me * nr + r], rc_ = P->h_matrix[r * nr + me];
         if (r == me) continue;
-        for (int a = 0; a < 6; ++a) {
-            if (sc) IPPLB_NCCL(ncclSend(exit_buf + ((size_t)r * 6 + a) * seg, (size_t)sc, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
-            if (rc_) IPPLB_NCCL(ncclRecv(dst[a] + tail_pos + roff[r], (size_t)rc_, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
-        }
+        if (sc) IPPLB_NCCL(ncclSend(exit_buf + (size_t)r * 6 * seg, (size_t)6 * sc, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
+        if (rc_) IPPLB_NCCL(ncclRecv(stage + 6 * roff[r], (size_t)6 * rc_, ncclDouble, r, (ncclComm_t)ctx->nccl, ctx->stream));
     }
     IPPLB_NCCL(ncclGroupEnd());
     ctx->launches++;
     const int self = P->h_matrix[me * nr + me];  // inclusive-fallback hits that stay here
-    for (int a = 0; self && a < 6; ++a)
-        IPPLB_CUDA(cudaMemcpyAsync(dst[a] + tail_pos + roff[me], exit_buf + ((size_t)me * 6 + a) * seg,
-                                   sizeof(double) * (size_t)self, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (self)
+        IPPLB_CUDA(cudaMemcpyAsync(stage + 6 * roff[me], exit_buf + (size_t)me * 6 * seg, sizeof(double) * 6 * (size_t)self,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
     if (na > 0) {
-        migrate_commit_kernel<<<1, 1, 0, ctx->stream>>>((int)na, b->state(b->cur), b->misc());
+        arrivals_kernel<<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(make_mesh_dev(&b->mesh), stage, (int)na, tail_pos, cur->x, cur->y,
+                                                             cur->z, cur->px, cur->py, cur->pz, cur->q_scalar, rho,
+                                                             b->state(b->cur), b->misc());
         IPPLB_CHECK_LAUNCH(ctx);
-        int rc;
-        if (rho && (rc = ipplb_scatter_cic(ctx, &b->mesh, tail_pos, tail_pos + na, cur->x, cur->y, cur->z, nullptr,
-                                           cur->q_scalar, nullptr, rho)))
-            return rc;
     }
     cur->n += na;
     return IPPLB_OK;

@@ -55,7 +55,7 @@ struct StepArgs {
     const double* ef;
     double* rho;
     double q;
-    double* exit_buf;  // [nranks][6][seg_cap]: leavers grouped by destination rank
+    double* exit_buf;  // [nranks][seg_cap][6]: leavers grouped by destination rank, one (x y z px py pz) record each
     int* exit_cnt;     // [nranks]
     int seg_cap;
     const double* regions;  // [nranks][6] (device) or nullptr on a single rank
@@ -161,12 +161,11 @@ __device__ __forceinline__ void place_exit(const StepArgs& A, const double r[3],
     base        = __shfl_sync(peers, base, leader);
     const int e = base + __popc(peers & ((1u << lane) - 1u));
     if (e < A.seg_cap) {
-        double* seg = A.exit_buf + (size_t)d * 6 * A.seg_cap;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            seg[(size_t)k * A.seg_cap + e]       = r[k];
-            seg[(size_t)(3 + k) * A.seg_cap + e] = p[k];
-        }
+        // one 48-byte record per leaver: a destination's segment is one contiguous message
+        double2* rec = reinterpret_cast<double2*>(A.exit_buf + ((size_t)d * A.seg_cap + e) * 6);
+        rec[0]       = make_double2(r[0], r[1]);
+        rec[1]       = make_double2(r[2], p[0]);
+        rec[2]       = make_double2(p[1], p[2]);
     }
 }
 
@@ -1040,14 +1039,27 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
         if (lane == 0) mbar_arrive(&s.empty[st]);
 
         if (D.pad[0]) {
-            // ---- last chunk of the tile: moments -> node sums -> node lattice (8 conflict-free rounds) -> global
+            // ---- last chunk of the tile: moments -> node sums -> node lattice (8 conflict-free rounds) -> global.
+            //      The moments are read from tensor memory once and the accumulators re-zeroed at once; the rounds work
+            //      from registers.
+            double am[NSL][8];
+            const double z8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+                if (sl * NT + warp * 32 < WIN_CELLS) {
+                    tmem_ld8(tm0 + sl * 16, am[sl]);
+                    tmem_st8(tm0 + sl * 16, z8);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) am[sl][i] = 0.0;
+                }
+            }
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
 #pragma unroll
                 for (int sl = 0; sl < NSL; ++sl) {
                     if (sl * NT + warp * 32 < WIN_CELLS) {
-                        double a[8];
-                        tmem_ld8(tm0 + sl * 16, a);
+                        const double* a = am[sl];
                         if (a[0] != 0.0) {
                             const double s1 = a[1], s2 = a[2], s3 = a[3], s12 = a[4], s13 = a[5], s23 = a[6], s123 = a[7];
                             double nd;  // node n: bit d set -> lower node along d (weight 1 - w_d)
@@ -1068,12 +1080,6 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
                     }
                 }
                 consumer_sync<NT>();
-            }
-            {
-                const double z[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int sl = 0; sl < NSL; ++sl)
-                    if (sl * NT + warp * 32 < WIN_CELLS) tmem_st8(tm0 + sl * 16, z);
             }
             for (int i = t; i < LAT * LAT * LAT; i += NT) {
                 const double v = s.lat[i];
@@ -1155,6 +1161,7 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
     for (int a = 0; a < 6; ++a) {
         IPPLB_REQUIRE(in[a] && out[a] && in[a] != out[a], "bins_step: null or aliased particle arrays");
         IPPLB_REQUIRE(((uintptr_t)in[a] & 15) == 0, "bins_step: particle arrays must be 16-byte aligned");
+        IPPLB_REQUIRE(((uintptr_t)exit_buf & 15) == 0, "bins_step: the exit buffer must be 16-byte aligned");
         A.in[a]  = in[a];
         A.out[a] = out[a];
     }

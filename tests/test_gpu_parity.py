@@ -642,7 +642,7 @@ def test_fused_step_exit_buffer_subdomain(ctx):
     out = ib.Particles(n, ctx.device)
     assert bins.compact(pb, out) == nloc
     assert np.array_equal(_canon(out.host()), _canon([a[stay] for a in Ro]))
-    ex = exit_buf.view(6, exit_cap)[:, :nexit].cpu().numpy()
+    ex = exit_buf.view(exit_cap, 6)[:nexit].T.contiguous().cpu().numpy()   # one (x y z px py pz) record per leaver
     assert np.array_equal(_canon(list(ex)), _canon([a[~stay] for a in Ro]))
     assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
     bins.close()
