@@ -1206,8 +1206,9 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         case 13: rc = launch_fused3<512, 2, 1>(ctx, A); break;
         case 14: rc = launch_fused3<352, 2, 2>(ctx, A); break;
         case 15: rc = launch_fused3<320, 2, 2>(ctx, A); break;
+        case 17: rc = launch_fused3<416, 2, 2>(ctx, A); break;
         case 5: rc = launch_fused<384, 2, 2>(ctx, A); break;  // generation 2
-        default: rc = launch_fused3<384, 2, 2>(ctx, A); break;  // generation 3 (measured best)
+        default: rc = launch_fused3<448, 2, 2>(ctx, A); break;  // generation 3, 14 consumer warps (measured best)
     }
     if (rc) return rc;
     rc = bins_plan(ctx, b, o, A.seg_cap);
