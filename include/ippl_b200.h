@@ -164,6 +164,13 @@ int ipplb_field_ex_stats(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* e
  * Single-GPU: mesh must be the whole domain.  rho: ghosted scalar field (interior read; like the
  * reference, rho's interior is clobbered).  efield: ghosted AoS-3, interior written (halo NOT filled). */
 int ipplb_poisson_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, ipplb_poisson** out);
+/* Multi-rank variant: a REPLICATED solve over NVSwitch.  ipplb_poisson_solve then gathers every rank's rho interior on
+ * every rank (one grouped ncclBroadcast per rank box, so ORB boxes of unequal size work), solves the whole domain with
+ * the same cuFFT plan on every GPU and keeps this rank's box of E (halo NOT filled: chain ipplb_halo_exchange).  Replaces
+ * heFFTe's distributed transposes (src/FFT/Transform/RC.h) for grids that fit one GPU: 256^3 is 1.1 GB of work space,
+ * 512^3 is 8.6 GB.  `layout` is the current FieldLayout; needs ipplb_comm_init.  With one rank it equals the above. */
+int ipplb_poisson_create_dist(ipplb_ctx* ctx, const ipplb_layout* layout, const double origin[3], const double h[3],
+                              ipplb_poisson** out);
 int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* efield);
 int ipplb_poisson_destroy(ipplb_poisson* s);
 

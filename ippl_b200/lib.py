@@ -509,10 +509,17 @@ class Bins:
 
 
 class Poisson:
-    def __init__(self, ctx, mesh):
+    """cuFFT periodic Poisson solve (non-owned stage).  Single rank: Poisson(ctx, mesh) with the whole domain;
+    multi rank: Poisson(ctx, None, layout=layout, origin=..., h=...) = replicated solve over NCCL."""
+
+    def __init__(self, ctx, mesh, layout=None, origin=None, h=None):
         self.ctx = ctx
         self._h = C.c_void_p()
-        _check(lib().ipplb_poisson_create(ctx._h, C.byref(mesh), C.byref(self._h)))
+        if layout is not None:
+            _check(lib().ipplb_poisson_create_dist(ctx._h, layout._h, (C.c_double * 3)(*origin), (C.c_double * 3)(*h),
+                                                   C.byref(self._h)))
+        else:
+            _check(lib().ipplb_poisson_create(ctx._h, C.byref(mesh), C.byref(self._h)))
 
     def solve(self, rho, efield):
         _check(lib().ipplb_poisson_solve(self._h, _ptr(rho), _ptr(efield)))

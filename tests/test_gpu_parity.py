@@ -665,6 +665,25 @@ def test_multi_gpu_fused_step(world):
     assert out.returncode == 0 and f"MGPU_CHECK_OK world={world}" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_landau(world):
+    """BASELINE.json configs[0] (LandauDamping 32^3, 2^20 particles, 10 steps) end to end on `world` GPUs -- device-side
+    sampling per rank, fused step, NCCL migration + halos, replicated cuFFT solve -- against the single-process oracle
+    (tests/mgpu_landau.py under torchrun): energy and max-norm history <= 1e-10 relative."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29520 + world), os.path.join(here, "mgpu_landau.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="4")   # the oracle runs on every rank's host
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and f"MGPU_LANDAU_OK world={world}" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
 def test_host_batches_pipeline_vs_oracle(ctx):
     """ipplb_pic_step_host_batches (bench.py's e2e path): three independent host batches through the overlapped
     upload / compute / download pipeline; every batch comes back with the oracle's particles (bit-exact
