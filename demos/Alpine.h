@@ -100,6 +100,7 @@ public:
         if (bins_m) ipplb_bins_destroy(bins_m);
         for (auto* p : spare_m)
             if (p) cudaFree(p);
+        if (exit_buf_m) cudaFree(exit_buf_m);
     }
     int getNt() const { return nt_m; }
     void setTime(double t) { time_m = t; }
@@ -179,14 +180,14 @@ protected:
     void fusedStep(ipplb_push push) {
         static IpplTimings::TimerRef FTimer     = IpplTimings::getTimer("fusedStep");
         static IpplTimings::TimerRef SolveTimer = IpplTimings::getTimer("solve");
-        if (ippl::Comm->size() > 1) throw IpplException(TestName, "the facade's fused step is single-rank in this round");
         auto* ctx = ippl::b200::ctx();
+        const bool multi = ippl::Comm->size() > 1;
         auto& pc  = *pcontainer_m;
         auto& rho = fcontainer_m->getRho();
         auto& E   = fcontainer_m->getE();
         const long n = (long)pc.getLocalNum();
         if (!bins_m) {  // bucket the particles once; the fused step keeps them bucketed
-            const long cap = n + n / 4 + 65536;
+            const long cap = (multi ? 2 * n : n + n / 4) + 65536;  // migration head-room on several ranks
             ippl::b200::check(ipplb_bins_create(ctx, &rho.b200_mesh(), cap, &bins_m), "bins_create");
             for (int b = 0; b < 2; ++b)
                 for (int a = 0; a < 6; ++a) spare_m[6 * b + a] = ippl::b200::device_alloc<double>(cap);
@@ -195,15 +196,29 @@ protected:
             cur_m = bundle(0, cap);
             nxt_m = bundle(1, cap);
             ippl::b200::check(ipplb_bins_build(ctx, bins_m, &in, &cur_m), "bins_build");
+            if (multi) {  // leavers of a step: records per destination rank; this rank's physical region
+                exit_cap_m = (int)std::max<long>(n / 4, 1 << 16);
+                exit_buf_m = ippl::b200::device_alloc<double>(6 * (std::size_t)exit_cap_m);
+                ippl::detail::RegionLayout<double, D, Mesh_t<D>> rl(fcontainer_m->getFL(), fcontainer_m->getMesh());
+                for (int d = 0; d < 3; ++d) {
+                    region_m[d]     = rl.regions()[6 * ippl::Comm->rank() + d];
+                    region_m[3 + d] = rl.regions()[6 * ippl::Comm->rank() + 3 + d];
+                }
+            }
         }
         push.do_kick2 = it_m > 0;
         push.do_kick1 = push.do_drift = push.do_bc = 1;
         IpplTimings::startTimer(FTimer);
         E.fillHalo();
         rho = 0.0;
-        ippl::b200::check(ipplb_bins_step(ctx, bins_m, &push, &cur_m, &nxt_m, E.data(), rho.data(), nullptr, 0, nullptr, nullptr),
+        ippl::b200::check(ipplb_bins_step(ctx, bins_m, &push, &cur_m, &nxt_m, E.data(), rho.data(), exit_buf_m, exit_cap_m,
+                                          multi ? region_m : nullptr, multi ? region_m + 3 : nullptr),
                           "bins_step");
         std::swap(cur_m, nxt_m);
+        if (multi) {  // ParticleSpatialLayout::update for the bucketed store: exchange, append, deposit the arrivals
+            ippl::b200::check(ipplb_bins_migrate(ctx, bins_m, &cur_m, exit_buf_m, exit_cap_m, rho.data(), nullptr, nullptr), "bins_migrate");
+            pc.setLocalNum((size_type)cur_m.n);
+        }
         rho.accumulateHalo();
         IpplTimings::stopTimer(FTimer);
         finishScatter();
@@ -244,6 +259,9 @@ protected:
     ipplb_bins* bins_m = nullptr;
     ipplb_particles cur_m{}, nxt_m{};
     std::array<double*, 12> spare_m{};
+    double* exit_buf_m = nullptr;
+    int exit_cap_m     = 0;
+    double region_m[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // the reference's main() of the three drivers (demos/alpine/LandauDamping.cpp:38-95): same positional arguments

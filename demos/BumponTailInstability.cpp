@@ -157,8 +157,9 @@ public:
         auto& E = this->fcontainer_m->getE();
         double st[7];
         ippl::b200::check(ipplb_field_energy_stats(ippl::b200::ctx(), &E.b200_mesh(), E.data(), st), "dump");
-        double globaltemp = 0.0, EzAmp = st[3 + (D - 1)];
+        double globaltemp = 0.0, EzAmp = 0.0;
         ippl::Comm->reduce(st[D - 1], globaltemp, 1, std::plus<double>());
+        ippl::Comm->reduce(st[3 + (D - 1)], EzAmp, 1, std::greater<double>());
         double fieldEnergy = std::accumulate(this->hr_m.begin(), this->hr_m.end(), globaltemp, std::multiplies<double>());
         if (ippl::Comm->rank() == 0) {
             std::filesystem::create_directory("data");

@@ -128,8 +128,9 @@ public:
         auto& E = this->fcontainer_m->getE();
         double st[2];
         ippl::b200::check(ipplb_field_ex_stats(ippl::b200::ctx(), &E.b200_mesh(), E.data(), st), "dump");
-        double globaltemp = 0.0, ExAmp = st[1];
+        double globaltemp = 0.0, ExAmp = 0.0;
         ippl::Comm->reduce(st[0], globaltemp, 1, std::plus<double>());
+        ippl::Comm->reduce(st[1], ExAmp, 1, std::greater<double>());
         double fieldEnergy = std::accumulate(this->hr_m.begin(), this->hr_m.end(), globaltemp, std::multiplies<double>());
         if (ippl::Comm->rank() == 0) {
             std::filesystem::create_directory("data");

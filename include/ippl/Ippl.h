@@ -38,7 +38,11 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../ippl_b200.h"
 
@@ -65,12 +69,16 @@ public:
     }
     Inform& operator<<(Inform& (*f)(Inform&)) { return f(*this); }
     void flush() {
-        if (level_on()) std::cout << (name_.empty() ? "" : name_ + "> ") << buf_.str() << std::endl;
+        if (level_on() && rank_ref() == 0) std::cout << (name_.empty() ? "" : name_ + "> ") << buf_.str() << std::endl;
         buf_.str("");
     }
     static bool& level_on() {
         static bool on = true;
         return on;
+    }
+    static int& rank_ref() {  // set by ippl::initialize: only rank 0 prints, like the reference's Inform
+        static int r = 0;
+        return r;
     }
 
 private:
@@ -98,6 +106,10 @@ namespace b200 {
         if (!ctx_ref()) throw IpplException("ippl::b200::ctx", "ippl::initialize has not been called");
         return ctx_ref();
     }
+    inline std::string& id_file() {
+        static std::string f;
+        return f;
+    }
     inline void check(int rc, const char* where) {
         if (rc != IPPLB_OK) throw IpplException(where, ipplb_last_error());
     }
@@ -124,14 +136,21 @@ public:
     double getDefaultOverallocation() const { return overalloc_; }
     void setDefaultOverallocation(double f) { overalloc_ = f; }
     // reduce / allreduce of one value over ranks (single rank: identity; multi rank: NCCL through the C-ABI)
+    // std::plus -> sum, std::greater -> max (the two operations the alpine drivers reduce with)
     template <typename T, typename Op>
     void reduce(const T& in, T& out, int /*count*/, Op, int /*root*/ = 0) {
         out = in;
-        if (size_ > 1) allreduce_sum(out);
+        if (size_ > 1) {
+            if constexpr (std::is_same_v<Op, std::greater<T>>) allreduce_max(out);
+            else allreduce_sum(out);
+        }
     }
     template <typename T, typename Op>
     void allreduce(T& inout, int /*count*/, Op) {
-        if (size_ > 1) allreduce_sum(inout);
+        if (size_ > 1) {
+            if constexpr (std::is_same_v<Op, std::greater<T>>) allreduce_max(inout);
+            else allreduce_sum(inout);
+        }
     }
     void set(int rank, int size) {
         rank_ = rank;
@@ -140,6 +159,8 @@ public:
 
 private:
     void allreduce_sum(double& v) { b200::check(ipplb_allreduce_sum_f64(b200::ctx(), &v), "Comm::allreduce"); }
+    void allreduce_max(double& v) { b200::check(ipplb_allreduce_max_f64(b200::ctx(), &v), "Comm::allreduce"); }
+    void allreduce_max(std::size_t&) { throw IpplException("Comm::allreduce", "max over ranks is wired for double only"); }
     void allreduce_sum(std::size_t& v) {
         long t = (long)v;
         b200::check(ipplb_allreduce_sum_i64(b200::ctx(), &t), "Comm::allreduce");
@@ -162,6 +183,39 @@ inline void initialize(int& argc, char**& argv) {
     b200::check(ipplb_ctx_create(&b200::ctx_ref(), device, nullptr, 0), "ippl::initialize");
     comm_holder() = std::make_unique<Communicator>();
     Comm          = comm_holder().get();
+    // one process per GPU, launched like `torchrun --no-python --nproc-per-node N <driver> ...` (RANK / WORLD_SIZE /
+    // LOCAL_RANK in the environment).  The NCCL id is published by rank 0 through a file named after the launcher's pid
+    // (the reference uses MPI_Init + MPI_COMM_WORLD here, src/Ippl.cpp:24-33; MPI is not part of this build).
+    int rank = 0, size = 1;
+    if (const char* e = std::getenv("RANK")) rank = std::atoi(e);
+    if (const char* e = std::getenv("WORLD_SIZE")) size = std::atoi(e);
+    if (size > 1) {
+        std::string path = "/tmp/ipplb_nccl_id_" + std::to_string((long)getppid());
+        if (const char* e = std::getenv("IPPLB_NCCL_ID_FILE")) path = e;
+        char id[IPPLB_NCCL_ID_BYTES];
+        if (rank == 0) {
+            b200::check(ipplb_nccl_unique_id(id), "ippl::initialize");
+            const std::string tmp = path + ".tmp";
+            FILE* f               = std::fopen(tmp.c_str(), "wb");
+            if (!f || std::fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw IpplException("ippl::initialize", "cannot publish the NCCL id");
+            std::fclose(f);
+            std::rename(tmp.c_str(), path.c_str());
+        } else {
+            bool got = false;
+            for (int tries = 0; tries < 6000 && !got; ++tries) {  // up to 60 s
+                if (FILE* f = std::fopen(path.c_str(), "rb")) {
+                    got = std::fread(id, 1, sizeof(id), f) == sizeof(id);
+                    std::fclose(f);
+                }
+                if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+            }
+            if (!got) throw IpplException("ippl::initialize", "timed out waiting for the NCCL id of rank 0");
+        }
+        b200::check(ipplb_comm_init(b200::ctx_ref(), rank, size, id), "ippl::initialize");
+        Comm->set(rank, size);
+        b200::id_file() = rank == 0 ? path : "";
+    }
+    Inform::rank_ref() = rank;
     for (int i = 1; i < argc; ++i) {  // global flags of src/Ippl.cpp:35-92 that matter here
         const std::string a = argv[i];
         if (a == "--overallocate" && i + 1 < argc) Comm->setDefaultOverallocation(std::atof(argv[i + 1]));
@@ -171,6 +225,7 @@ inline void initialize(int& argc, char**& argv) {
 inline void finalize() {
     if (b200::ctx_ref()) ipplb_ctx_destroy(b200::ctx_ref());
     b200::ctx_ref() = nullptr;
+    if (!b200::id_file().empty()) std::remove(b200::id_file().c_str());
 }
 inline void fence() { b200::check(ipplb_sync(b200::ctx()), "ippl::fence"); }
 
@@ -785,9 +840,18 @@ public:
     }
     void setRhs(FieldRHS& rhs) {
         rhs_ = &rhs;
-        if (Comm->size() > 1) throw IpplException("FFTPeriodicPoissonSolver", "the cuFFT stand-in is single-GPU");
         if (h_) ipplb_poisson_destroy(h_);
-        b200::check(ipplb_poisson_create(b200::ctx(), &rhs.b200_mesh(), &h_), "FFTPeriodicPoissonSolver::setRhs");
+        h_ = nullptr;
+        if (Comm->size() > 1) {  // replicated solve over NCCL (ipplb_poisson_create_dist)
+            double o[3], h[3];
+            for (int d = 0; d < 3; ++d) {
+                o[d] = rhs.get_mesh().getOrigin()[d];
+                h[d] = rhs.get_mesh().getMeshSpacing()[d];
+            }
+            b200::check(ipplb_poisson_create_dist(b200::ctx(), rhs.getLayout().handle(), o, h, &h_), "FFTPeriodicPoissonSolver::setRhs");
+        } else {
+            b200::check(ipplb_poisson_create(b200::ctx(), &rhs.b200_mesh(), &h_), "FFTPeriodicPoissonSolver::setRhs");
+        }
     }
     void setLhs(FieldLHS& lhs) { lhs_ = &lhs; }
     // solve(): GRAD output -- E written to lhs interior, rho clobbered like the reference (:53-169)

@@ -217,6 +217,8 @@ int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv
 /* sum over ranks of one double / one long (rho.sum(), particle count: AlpineManager.h:169, 212) */
 int ipplb_allreduce_sum_f64(ipplb_ctx* ctx, double* value_host);
 int ipplb_allreduce_sum_i64(ipplb_ctx* ctx, long* value_host);
+/* max over ranks of one double (the dumps' max norms: Comm->reduce(..., std::greater<double>()), LandauDampingManager.h:360-366) */
+int ipplb_allreduce_max_f64(ipplb_ctx* ctx, double* value_host);
 
 /* ---- cell-ordered particle store + fused single-pass PIC step (the B200-first path) ------------------ */
 /* ipplb_bins keeps the particles of one rank grouped in per-tile buckets (tile = 4x4x4 key cells, key =

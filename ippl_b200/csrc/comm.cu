@@ -602,6 +602,22 @@ int ipplb_allreduce_sum_f64(ipplb_ctx* ctx, double* value_host) {
     return IPPLB_OK;
 }
 
+int ipplb_allreduce_max_f64(ipplb_ctx* ctx, double* value_host) {
+    IPPLB_REQUIRE(ctx && value_host, "allreduce: bad arguments");
+    if (ctx->nranks < 2) return IPPLB_OK;
+    int rc;
+    if ((rc = ensure(ctx, ctx->reduce, sizeof(double) * 2048))) return rc;
+    double* d = (double*)ctx->reduce.ptr + 1700;
+    ctx->reduce_host[24] = *value_host;
+    IPPLB_CUDA(cudaMemcpyAsync(d, ctx->reduce_host + 24, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    IPPLB_NCCL(ncclAllReduce(d, d, 1, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl, ctx->stream));
+    ctx->launches++;
+    IPPLB_CUDA(cudaMemcpyAsync(ctx->reduce_host + 24, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *value_host = ctx->reduce_host[24];
+    return IPPLB_OK;
+}
+
 int ipplb_allreduce_sum_i64(ipplb_ctx* ctx, long* value_host) {
     IPPLB_REQUIRE(ctx && value_host, "allreduce: bad arguments");
     if (ctx->nranks < 2) return IPPLB_OK;

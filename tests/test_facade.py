@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "demos", "LandauDamping")
 
 
-def _run(tmp_path, name, extra=(), app="LandauDamping", csv="FieldLandau_1_manager.csv", grid=16, np_=10000000, nt=25):
+def _run(tmp_path, name, extra=(), app="LandauDamping", csv="FieldLandau_1_manager.csv", grid=16, np_=10000000, nt=25,
+         ranks=1):
     d = tmp_path / name
     d.mkdir()
     exe = os.path.join(ROOT, "demos", app)
@@ -24,6 +25,10 @@ def _run(tmp_path, name, extra=(), app="LandauDamping", csv="FieldLandau_1_manag
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "demos"), "-s"])
     cmd = [exe, str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
            "--info", "0", *extra]
+    if ranks > 1:   # one process per GPU; the facade's ippl::initialize reads RANK / WORLD_SIZE / LOCAL_RANK
+        import sys
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={ranks}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29540 + ranks)] + cmd
     out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return np.loadtxt(d / "data" / csv, skiprows=1), out.stdout
@@ -77,3 +82,29 @@ def test_penningtrap_facade_fused_matches_unfused(tmp_path):
     h3 = (20.0 / 32) ** 3
     assert np.allclose(got[:, 1], 0.5 * h3 * (got[:, 5] ** 2 + got[:, 6] ** 2 + got[:, 7] ** 2), rtol=1e-8)
     assert "fusedStep" in log2
+
+
+@pytest.mark.parametrize("ranks", [2])
+def test_facade_drivers_on_several_gpus(tmp_path, ranks):
+    """The C++ drivers on `ranks` GPUs (torchrun --no-python; NCCL id exchanged by the facade's ippl::initialize):
+    LandauDamping reproduces the reference's known-answer CSV -- which the reference generated with 2 ranks
+    (demos/alpine/validation/CMakeLists.txt) -- on both the reference-shaped path (pc->update() over NCCL, halo exchange,
+    replicated FFT solve) and the fused path (ownership in the kernel + ipplb_bins_migrate), and agrees with the 1-rank
+    run to summation order; PenningTrap's fused and reference-shaped field columns agree."""
+    import torch
+    if torch.cuda.device_count() < ranks:
+        pytest.skip(f"needs {ranks} GPUs")
+    golden = np.loadtxt(os.path.join(ROOT, "tests", "golden", "FieldLandau_valid_result.csv"), skiprows=1)
+    csv = f"FieldLandau_{ranks}_manager.csv"
+    got, _ = _run(tmp_path, "landau_mr", csv=csv, ranks=ranks)
+    fused, _ = _run(tmp_path, "landau_mr_fused", csv=csv, ranks=ranks, extra=("--fused",))
+    assert got.shape == fused.shape == golden.shape
+    assert np.max(np.abs(got[:, 1:] - golden[:, 1:])) <= 0.4
+    assert np.max(np.abs(fused[:, 1:] - got[:, 1:]) / np.abs(got[:, 1:])) <= 1e-9
+    assert got[-1, 1] < 0.7 * got[0, 1]
+    kw = dict(app="PenningTrap", csv=f"ParticleField_{ranks}_manager.csv", grid=32, np_=2000000, nt=6, ranks=ranks)
+    pt, _ = _run(tmp_path, "pt_mr", **kw)
+    ptf, _ = _run(tmp_path, "pt_mr_fused", extra=("--fused",), **kw)
+    fields = [1, 4, 5, 6, 7]
+    assert np.max(np.abs(ptf[:, fields] - pt[:, fields]) / np.abs(pt[:, fields])) <= 1e-8
+    assert abs(pt[0, 2] / (1.5 * 2000000) - 1.0) <= 5e-3
