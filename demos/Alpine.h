@@ -85,6 +85,65 @@ private:
 };
 
 
+// demos/alpine/LoadBalancer.hpp
+template <typename T_, unsigned D>
+class LoadBalancer {
+    using Solver_t = ippl::FFTPeriodicPoissonSolver<VField_t<T_, D>, Field_t<D>>;
+    using ORB      = ippl::OrthogonalRecursiveBisection<Field_t<D>, T_>;
+
+public:
+    LoadBalancer(double lbs, std::shared_ptr<FieldContainer<T_, D>>& fc, std::shared_ptr<ParticleContainer<T_, D>>& pc,
+                 std::shared_ptr<Solver_t>& fs)
+        : loadbalancethreshold_m(lbs), rho_m(&fc->getRho()), E_m(&fc->getE()), pc_m(pc), fs_m(fs) {}
+    double getLoadBalanceThreshold() const { return loadbalancethreshold_m; }
+    void setLoadBalanceFreq(unsigned f) { loadbalancefreq_m = f; }
+
+    // :54-88
+    void updateLayout(FieldLayout_t<D>* fl, Mesh_t<D>* mesh, bool& isFirstRepartition) {
+        static IpplTimings::TimerRef tupdateLayout = IpplTimings::getTimer("updateLayout");
+        IpplTimings::startTimer(tupdateLayout);
+        (*E_m).updateLayout(*fl);
+        (*rho_m).updateLayout(*fl);
+        pc_m->getLayout().updateLayout(*fl, *mesh);
+        IpplTimings::stopTimer(tupdateLayout);
+        static IpplTimings::TimerRef tupdatePLayout = IpplTimings::getTimer("updatePB");
+        IpplTimings::startTimer(tupdatePLayout);
+        if (!isFirstRepartition) pc_m->update();
+        IpplTimings::stopTimer(tupdatePLayout);
+    }
+    void initializeORB(FieldLayout_t<D>* fl, Mesh_t<D>* mesh) { orb.initialize(*fl, *mesh, *rho_m); }
+    // :94-123
+    bool repartition(FieldLayout_t<D>* fl, Mesh_t<D>* mesh, bool& isFirstRepartition) {
+        bool res = orb.binaryRepartition(pc_m->R, *fl, isFirstRepartition);
+        if (res != true) {
+            std::cout << "Could not repartition!" << std::endl;
+            return false;
+        }
+        this->updateLayout(fl, mesh, isFirstRepartition);
+        fs_m->setRhs(*rho_m);
+        return true;
+    }
+    // :125-151 (the fixed-frequency branch is the reference's UniformPlasmaTest rule, selected here with --lb-every)
+    bool balance(size_type totalP, const unsigned int nstep) {
+        if (ippl::Comm->size() < 2 || loadbalancethreshold_m == 1.0) return false;
+        if (loadbalancefreq_m) return (nstep % loadbalancefreq_m == 0);
+        double equalPart = (double)totalP / ippl::Comm->size();
+        double dev       = std::abs((double)pc_m->getLocalNum() - equalPart) / totalP;
+        double local     = dev > loadbalancethreshold_m ? 1.0 : 0.0, any = 0.0;
+        ippl::Comm->reduce(local, any, 1, std::greater<double>());  // MPI_Allgather + any-of in the reference
+        return any > 0.0;
+    }
+
+private:
+    double loadbalancethreshold_m;
+    Field_t<D>* rho_m;
+    VField_t<T_, D>* E_m;
+    std::shared_ptr<ParticleContainer<T_, D>> pc_m;
+    std::shared_ptr<Solver_t> fs_m;
+    unsigned int loadbalancefreq_m = 0;
+    ORB orb;
+};
+
 // demos/alpine/AlpineManager.h
 template <typename T_, unsigned D>
 class AlpineManager {
@@ -96,12 +155,19 @@ public:
     AlpineManager(size_type totalP, int nt, Vector_t<int, D>& nr, double lbt, std::string solver, std::string stepMethod,
                   bool fused)
         : totalP_m(totalP), nt_m(nt), nr_m(nr), lbt_m(lbt), solver_m(solver), stepMethod_m(stepMethod), fused_m(fused) {}
-    virtual ~AlpineManager() {
+    virtual ~AlpineManager() { releaseBins(); }
+    void releaseBins() {
         if (bins_m) ipplb_bins_destroy(bins_m);
-        for (auto* p : spare_m)
+        bins_m = nullptr;
+        for (auto*& p : spare_m) {
             if (p) cudaFree(p);
+            p = nullptr;
+        }
         if (exit_buf_m) cudaFree(exit_buf_m);
+        exit_buf_m = nullptr;
     }
+    void setLoadBalanceFreq(unsigned f) { lbfreq_m = f; }
+    int repartitions() const { return repartitions_m; }
     int getNt() const { return nt_m; }
     void setTime(double t) { time_m = t; }
     virtual void pre_run() = 0;
@@ -161,6 +227,33 @@ protected:
         pcontainer_m = std::make_shared<ParticleContainer_t>(fcontainer_m->getMesh(), fcontainer_m->getFL());
         fcontainer_m->initializeFields();
         fsolver_m = std::make_shared<Solver_t>(fcontainer_m->getE(), fcontainer_m->getRho());
+        loadbalancer_m = std::make_shared<LoadBalancer<T_, D>>(lbt_m, fcontainer_m, pcontainer_m, fsolver_m);
+        loadbalancer_m->setLoadBalanceFreq(lbfreq_m);
+    }
+    // the first repartition of initializeParticles (LandauDampingManager.h:179-205): ORB on the analytic density
+    template <class DistT>
+    void firstRepartition(const DistT& distR) {
+        if ((lbt_m == 1.0) || (ippl::Comm->size() < 2)) return;
+        Inform m("Initialize Particles");
+        m << "Starting first repartition" << endl;
+        static IpplTimings::TimerRef domainDecomposition = IpplTimings::getTimer("loadBalance");
+        IpplTimings::startTimer(domainDecomposition);
+        isFirstRepartition_m = true;
+        distR.fillFullPdf(fcontainer_m->getRho());
+        loadbalancer_m->initializeORB(&fcontainer_m->getFL(), &fcontainer_m->getMesh());
+        loadbalancer_m->repartition(&fcontainer_m->getFL(), &fcontainer_m->getMesh(), isFirstRepartition_m);
+        IpplTimings::stopTimer(domainDecomposition);
+    }
+    // the balance check of LeapFrogStep (LandauDampingManager.h:290-298), reference-shaped path
+    void maybeRepartition() {
+        static IpplTimings::TimerRef domainDecomposition = IpplTimings::getTimer("loadBalance");
+        bool isFirstRepartition = false;
+        if (loadbalancer_m->balance(totalP_m, it_m + 1)) {
+            IpplTimings::startTimer(domainDecomposition);
+            loadbalancer_m->repartition(&fcontainer_m->getFL(), &fcontainer_m->getMesh(), isFirstRepartition);
+            IpplTimings::stopTimer(domainDecomposition);
+            ++repartitions_m;
+        }
     }
     void firstSolve() {
         fcontainer_m->getRho() = 0.0;
@@ -219,9 +312,29 @@ protected:
             ippl::b200::check(ipplb_bins_migrate(ctx, bins_m, &cur_m, exit_buf_m, exit_cap_m, rho.data(), nullptr, nullptr), "bins_migrate");
             pc.setLocalNum((size_type)cur_m.n);
         }
-        rho.accumulateHalo();
-        IpplTimings::stopTimer(FTimer);
-        finishScatter();
+        if (loadbalancer_m->balance(totalP_m, it_m + 1)) {
+            // LoadBalancer::repartition for the bucketed store: back to the contiguous attribute arrays, new layout,
+            // pc->update() to the new owners, rho re-deposited on the new boxes; the next step re-buckets.  (The closing
+            // kick of this step is still pending in P, exactly as it is inside the buckets.)
+            IpplTimings::stopTimer(FTimer);
+            static IpplTimings::TimerRef domainDecomposition = IpplTimings::getTimer("loadBalance");
+            IpplTimings::startTimer(domainDecomposition);
+            pc.setLocalNum((size_type)cur_m.n);  // grows R, P, E, q if the rank gained particles
+            ipplb_particles out{pc.R.component(0), pc.R.component(1), pc.R.component(2), pc.P.component(0), pc.P.component(1),
+                                pc.P.component(2), nullptr, Q_m / totalP_m, 0, (long)pc.R.size()};
+            ippl::b200::check(ipplb_bins_compact(ctx, bins_m, &cur_m, &out), "bins_compact");
+            pc.q = Q_m / totalP_m;
+            releaseBins();
+            bool isFirstRepartition = false;
+            loadbalancer_m->repartition(&fcontainer_m->getFL(), &fcontainer_m->getMesh(), isFirstRepartition);
+            ++repartitions_m;
+            IpplTimings::stopTimer(domainDecomposition);
+            par2grid();
+        } else {
+            rho.accumulateHalo();
+            IpplTimings::stopTimer(FTimer);
+            finishScatter();
+        }
         IpplTimings::startTimer(SolveTimer);
         fsolver_m->solve();
         IpplTimings::stopTimer(SolveTimer);
@@ -261,6 +374,10 @@ protected:
     std::array<double*, 12> spare_m{};
     double* exit_buf_m = nullptr;
     int exit_cap_m     = 0;
+    std::shared_ptr<LoadBalancer<T_, D>> loadbalancer_m;
+    bool isFirstRepartition_m = false;
+    unsigned lbfreq_m         = 0;
+    int repartitions_m        = 0;
     double region_m[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -284,13 +401,19 @@ int alpine_main(int argc, char* argv[]) {
             double lbt              = std::atof(argv[arg++]);
             std::string step_method = argv[arg++];
             bool fused              = false;
-            for (int i = arg; i < argc; ++i) fused |= std::string(argv[i]) == "--fused";
+            unsigned lbevery        = 0;
+            for (int i = arg; i < argc; ++i) {
+                fused |= std::string(argv[i]) == "--fused";
+                if (std::string(argv[i]) == "--lb-every" && i + 1 < argc) lbevery = (unsigned)std::atoi(argv[i + 1]);
+            }
             Manager manager(totalP, nt, nr, lbt, solver, step_method, fused);
+            manager.setLoadBalanceFreq(lbevery);
             manager.pre_run();
             manager.setTime(0.0);
             msg << "Starting iterations ..." << endl;
             manager.run(manager.getNt());
             msg << "End." << endl;
+            if (ippl::Comm->rank() == 0) std::cout << "ORB repartitions during the run: " << manager.repartitions() << std::endl;
             IpplTimings::stopTimer(mainTimer);
             IpplTimings::print();
         } catch (const IpplException& ex) {

@@ -69,6 +69,7 @@ public:
         }
         // CustomDistributionFunctions (:23-52): the perturbation acts along the last dimension only
         DistR_t distR({ippl::random::UNIFORM, ippl::random::UNIFORM, ippl::random::COSINE}, parR);
+        this->firstRepartition(distR);
         static IpplTimings::TimerRef particleCreation = IpplTimings::getTimer("particlesCreation");
         IpplTimings::startTimer(particleCreation);
         ippl::detail::RegionLayout<double, D, Mesh_t<D>> rlayout(*FL, *mesh);
@@ -142,6 +143,7 @@ public:
         IpplTimings::startTimer(updateTimer);
         pc->update();
         IpplTimings::stopTimer(updateTimer);
+        this->maybeRepartition();
         this->par2grid();
         IpplTimings::startTimer(SolveTimer);
         this->fsolver_m->solve();

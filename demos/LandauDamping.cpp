@@ -58,6 +58,7 @@ public:
             parR[i * 2 + 1] = this->kw_m[i];
         }
         DistR_t distR({ippl::random::COSINE, ippl::random::COSINE, ippl::random::COSINE}, parR);
+        this->firstRepartition(distR);
         static IpplTimings::TimerRef particleCreation = IpplTimings::getTimer("particlesCreation");
         IpplTimings::startTimer(particleCreation);
         ippl::detail::RegionLayout<double, D, Mesh_t<D>> rlayout(*FL, *mesh);
@@ -113,6 +114,7 @@ public:
         IpplTimings::startTimer(updateTimer);
         pc->update();
         IpplTimings::stopTimer(updateTimer);
+        this->maybeRepartition();
         this->par2grid();
         IpplTimings::startTimer(SolveTimer);
         this->fsolver_m->solve();

@@ -61,6 +61,7 @@ public:
             parR[i * 2 + 1] = sd[i];
         }
         DistR_t distR(parR);
+        this->firstRepartition(distR);
         static IpplTimings::TimerRef particleCreation = IpplTimings::getTimer("particlesCreation");
         IpplTimings::startTimer(particleCreation);
         ippl::detail::RegionLayout<double, D, Mesh_t<D>> rlayout(*FL, *mesh);
@@ -129,13 +130,15 @@ public:
         IpplTimings::startTimer(updateTimer);
         pc->update();
         IpplTimings::stopTimer(updateTimer);
+        this->maybeRepartition();
         this->par2grid();
         IpplTimings::startTimer(SolveTimer);
         this->fsolver_m->solve();
         IpplTimings::stopTimer(SolveTimer);
         this->grid2par();
         IpplTimings::startTimer(PTimer);
-        ippl::b200::check(ipplb_penning_kick(ippl::b200::ctx(), 2, &push, n, pc->R.component(0), pc->R.component(1), pc->R.component(2),
+        const long n2 = (long)pc->getLocalNum();  // update() / a repartition may have changed the local count
+        ippl::b200::check(ipplb_penning_kick(ippl::b200::ctx(), 2, &push, n2, pc->R.component(0), pc->R.component(1), pc->R.component(2),
                                              pc->P.component(0), pc->P.component(1), pc->P.component(2), pc->E.component(0),
                                              pc->E.component(1), pc->E.component(2)),
                           "Kick2");

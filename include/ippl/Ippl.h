@@ -341,6 +341,17 @@ public:
         const int* b = &boxes[6 * Comm->rank()];
         local_       = NDIndex<Dim>(Index(b[0], b[3]), Index(b[1], b[4]), Index(b[2], b[5]));
     }
+    // FieldLayout::updateLayout(domains), FieldLayout.hpp:136-160: the rank boxes of an ORB repartition
+    void updateLayout(const std::vector<NDIndex<Dim>>& domains) {
+        std::vector<int> boxes(6 * domains.size());
+        for (std::size_t r = 0; r < domains.size(); ++r)
+            for (unsigned d = 0; d < Dim; ++d) {
+                boxes[6 * r + d]     = domains[r][d].first();
+                boxes[6 * r + 3 + d] = domains[r][d].last();
+            }
+        b200::check(ipplb_layout_set_boxes(h_, boxes.data()), "FieldLayout::updateLayout");
+        local_ = domains[Comm->rank()];
+    }
     const NDIndex<Dim>& getDomain() const { return domain_; }
     const NDIndex<Dim>& getLocalNDIndex() const { return local_; }
     bool isAllPeriodic() const { return periodic_; }
@@ -429,6 +440,13 @@ public:
         if (data_) cudaFree(data_);
         data_ = b200::device_alloc<double>(cells_ * ncomp);
         *this = 0.0;
+    }
+    // BareField::updateLayout, BareField.hpp:124-129: storage follows the new local box (contents are not kept)
+    void updateLayout(Layout_t& l, int nghost = 1) { initialize(*mesh_p_, l, nghost); }
+    // field = field of the same layout (ORB keeps a copy of rho: OrthogonalRecursiveBisection.hpp:10-12)
+    void copyFrom(const Field& o) {
+        if (o.cells_ != cells_) throw IpplException("Field::copyFrom", "layouts differ");
+        b200::cuda_check(cudaMemcpy(data_, o.data_, sizeof(double) * cells_ * ncomp, cudaMemcpyDeviceToDevice), "Field::copyFrom");
     }
     // field = scalar (BareField.hpp:182-185)
     Field& operator=(double v) {
@@ -544,7 +562,23 @@ public:
         }
         count_ = need;
     }
-    void setCount(std::size_t n) override { count_ = n; }
+    void setCount(std::size_t n) override {
+        reserve(n);
+        count_ = n;
+    }
+    // capacity for at least n particles, contents kept
+    void reserve(std::size_t n) {
+        if (n <= capacity_) return;
+        for (int c = 0; c < ncomp; ++c) {
+            double* p = b200::device_alloc<double>(n);
+            if (d_[c]) {
+                b200::cuda_check(cudaMemcpy(p, d_[c], sizeof(double) * count_, cudaMemcpyDeviceToDevice), "ParticleAttrib::reserve");
+                cudaFree(d_[c]);
+            }
+            d_[c] = p;
+        }
+        capacity_ = n;
+    }
     std::size_t size() const { return capacity_; }
     std::size_t getParticleCount() const { return count_; }
     double* component(int c) const { return d_[c]; }
@@ -661,6 +695,19 @@ public:
             b200::check(ipplb_ctx_set_layout(b200::ctx(), fl.handle(), o, h), "ParticleSpatialLayout");
         }
     }
+    // ParticleSpatialLayout::updateLayout(fl, mesh), ParticleSpatialLayout.hpp:100-113: new regions for the ownership test
+    void updateLayout(FieldLayout<Dim>& fl, Mesh& mesh) {
+        fl_   = &fl;
+        mesh_ = &mesh;
+        if (Comm->size() > 1) {
+            double o[3], h[3];
+            for (int d = 0; d < 3; ++d) {
+                o[d] = mesh.getOrigin()[d];
+                h[d] = mesh.getMeshSpacing()[d];
+            }
+            b200::check(ipplb_ctx_set_layout(b200::ctx(), fl.handle(), o, h), "ParticleSpatialLayout::updateLayout");
+        }
+    }
     void setParticleBC(BC bc) { bc_ = bc; }
     // update(): applyBC (ParticleLayout.hpp:34-74, PeriodicBC ParticleBC.h:73-76), early return on one rank
     // (ParticleSpatialLayout.hpp:128), else ownership + exchange + compaction (ipplb_update)
@@ -713,6 +760,7 @@ public:
         localNum_ = n;
         for (auto* a : attributes_) a->setCount(n);
     }
+    PLayout& getLayout() { return *layout_; }
     void update() { layout_->update(*this); }
     // multi-rank exchange of R and the attributes a derived container exposes through migration_bundle()
     virtual void migrate() { throw IpplException("ParticleBase::migrate", "container does not expose a migration bundle"); }
@@ -763,6 +811,12 @@ namespace random {
             }
         }
         const ipplb_dist& handle() const { return d_; }
+        // rho(cell) = getFullPdf((global index + 0.5) * hr + origin) on the interior: the weights of the first
+        // repartition (LandauDampingManager.h:188-199)
+        template <class FieldT>
+        void fillFullPdf(FieldT& rho) const {
+            b200::check(ipplb_field_fill_pdf(b200::ctx(), &rho.b200_mesh(), &d_, rho.data()), "Distribution::getFullPdf");
+        }
 
     private:
         ipplb_dist d_{};
@@ -824,6 +878,50 @@ namespace random {
                     "random::randn");
     }
 }  // namespace random
+
+// ---- OrthogonalRecursiveBisection (src/Decomposition/OrthogonalRecursiveBisection.h / .hpp) ---------------------------------------------
+template <class FieldT, class Tp = double>
+class OrthogonalRecursiveBisection {
+    static constexpr unsigned Dim = 3;
+    using mesh_type               = typename FieldT::Mesh_t;
+
+public:
+    FieldT bf_m;  // the weights: a copy of rho on the first repartition, scatterR(R) afterwards
+
+    // initialize(fl, mesh, rho), .hpp:8-12
+    void initialize(FieldLayout<Dim>& fl, mesh_type& mesh, const FieldT& rho) {
+        bf_m.initialize(mesh, fl);
+        bf_m.copyFrom(rho);
+    }
+    // binaryRepartition(R, fl, isFirstRepartition), .hpp:14-105: plane sums on the device, reduced over ranks; the cuts
+    // (findCutAxis / findMedian / cutDomain) on the host; false when a box would get an axis of length 1
+    template <typename Attrib>
+    bool binaryRepartition(const Attrib& R, FieldLayout<Dim>& fl, const bool& isFirstRepartition) {
+        if (!isFirstRepartition) scatterR(R);
+        const int nr = Comm->size();
+        std::vector<int> boxes(6 * (std::size_t)nr);
+        int ok = 0;
+        b200::check(ipplb_orb_repartition(b200::ctx(), &bf_m.b200_mesh(), nr, bf_m.data(), boxes.data(), &ok),
+                    "OrthogonalRecursiveBisection::binaryRepartition");
+        if (!ok) return false;
+        std::vector<NDIndex<Dim>> domains(nr);
+        for (int r = 0; r < nr; ++r)
+            domains[r] = NDIndex<Dim>(Index(boxes[6 * r], boxes[6 * r + 3]), Index(boxes[6 * r + 1], boxes[6 * r + 4]),
+                                      Index(boxes[6 * r + 2], boxes[6 * r + 5]));
+        fl.updateLayout(domains);
+        bf_m.updateLayout(fl);
+        return true;
+    }
+    // scatterR, .hpp:234-300: CIC deposit of weight 1 per particle, then accumulateHalo
+    template <typename Attrib>
+    void scatterR(const Attrib& r) {
+        bf_m = 0.0;
+        b200::check(ipplb_scatter_cic(b200::ctx(), &bf_m.b200_mesh(), 0, (long)r.getParticleCount(), r.component(0), r.component(1),
+                                      r.component(2), nullptr, 1.0, nullptr, bf_m.data()),
+                    "OrthogonalRecursiveBisection::scatterR");
+        bf_m.accumulateHalo();
+    }
+};
 
 // ---- FFTPeriodicPoissonSolver (src/PoissonSolvers/FFTPeriodicPoissonSolver.h; non-owned stage, cuFFT) ------------------------------------
 template <class FieldLHS, class FieldRHS>

@@ -102,6 +102,14 @@ def test_facade_drivers_on_several_gpus(tmp_path, ranks):
     assert np.max(np.abs(got[:, 1:] - golden[:, 1:])) <= 0.4
     assert np.max(np.abs(fused[:, 1:] - got[:, 1:]) / np.abs(got[:, 1:])) <= 1e-9
     assert got[-1, 1] < 0.7 * got[0, 1]
+    # LoadBalancer / ORB in the drivers (demos/alpine/LoadBalancer.hpp): lbthres = 0.01 triggers the first repartition on
+    # the analytic density; --lb-every 5 forces binaryRepartition + updateLayout + pc->update() every 5 steps on both
+    # paths.  The physics must not notice.
+    for tag, extra in (("lb", ("--lb-every", "5")), ("lb_fused", ("--lb-every", "5", "--fused"))):
+        lb, log = _run(tmp_path, "landau_mr_" + tag, csv=csv, ranks=ranks, extra=extra)
+        assert "ORB repartitions during the run: 5" in log, log[-1500:]
+        assert "Could not repartition" not in log
+        assert np.max(np.abs(lb[:, 1:] - got[:, 1:]) / np.abs(got[:, 1:])) <= 1e-8
     kw = dict(app="PenningTrap", csv=f"ParticleField_{ranks}_manager.csv", grid=32, np_=2000000, nt=6, ranks=ranks)
     pt, _ = _run(tmp_path, "pt_mr", **kw)
     ptf, _ = _run(tmp_path, "pt_mr_fused", extra=("--fused",), **kw)
