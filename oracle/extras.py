@@ -224,3 +224,107 @@ def energy_stats(E_int):
 def kinetic(P):
     """sum_i dot(P_i, P_i), PenningTrapManager.h:354-362"""
     return float(np.sum((P[0] * P[0] + P[1] * P[1]) + P[2] * P[2]))
+
+
+# ---- the other two alpine mini-apps as single-rank CPU loops ------------------------------------------------------
+def _alpine_base():
+    import oracle as _o
+    return _o
+
+
+class AlpineOracle:
+    """PenningTrap / BumponTailInstability loops on the oracle kernels, same structure as oracle.LandauOracle
+    (AlpineManager.h:157-245 for scatter + getDensity; the managers' pre_run / LeapFrogStep / dump).  Initial particles
+    are INPUTS.  kind = "bumpontail": leapfrog push, dump = (Ez energy, Ez max norm)
+    (BumponTailInstabilityManager.h:315-369, 448-500); kind = "penning": Kick1 / drift / Kick2 in the external fields,
+    dump = (potential energy 0.5 h^3 sum dot(E,E), kinetic 0.5 sum dot(P,P), |Ex|, |Ey|, |Ez|)
+    (PenningTrapManager.h:242-336, 346-389)."""
+
+    def __init__(self, kind, nr, R, P, parallel=True):
+        o = _alpine_base()
+        self.o, self.kind, self.nr = o, kind, tuple(nr)
+        if kind == "bumpontail":
+            kw = 0.21
+            self.rmax = 2 * math.pi / kw
+            self.Q = -1.0 * self.rmax * self.rmax * self.rmax
+            self.hr = [self.rmax / n for n in nr]
+            self.dt = min(0.05, 0.5 * min(self.hr))
+        elif kind == "penning":
+            self.rmax = 20.0
+            self.Q = -1562.5
+            self.hr = [self.rmax / n for n in nr]
+            self.dt = 0.5 * (self.rmax / 2048)
+            self.pp = o.penning_params((0.0, 0.0, 0.0), (self.rmax,) * 3, self.dt, 5.0)
+        else:
+            raise ValueError(kind)
+        self.origin = [0.0, 0.0, 0.0]
+        self.mesh = o.Mesh.make(nr, self.origin, self.hr)
+        self.R = [np.ascontiguousarray(r, dtype=np.float64).copy() for r in R]
+        self.P = [np.ascontiguousarray(p, dtype=np.float64).copy() for p in P]
+        self.n = len(self.R[0])
+        self.q = self.Q / self.n
+        self.E = [np.zeros(self.n) for _ in range(3)]
+        self.rho = o.field_zeros(self.mesh)
+        self.Ef = o.field_zeros(self.mesh, 3)
+        self.time, self.par, self.history = 0.0, parallel, []
+
+    def scatter(self):
+        o = self.o
+        self.rho[:] = 0.0
+        o.scatter_cic(self.mesh, *self.R, self.q, self.rho, parallel=self.par)
+        o.halo_periodic(self.rho, self.mesh.ext, 1, 1, (1, 1, 1), "accumulate")
+        self.rel_err = abs((self.Q - o.field_sum(self.rho, self.mesh.ext)) / self.Q)
+        cell = self.hr[0] * self.hr[1] * self.hr[2]
+        size = 1.0
+        for _ in range(3):
+            size *= self.rmax - 0.0
+        o.density(self.rho, self.mesh.ext, 1, cell, self.Q / size)
+
+    def solve(self):
+        o = self.o
+        E = o.poisson_grad(o.interior(self.rho, self.mesh), self.origin, self.hr)
+        o.interior(self.Ef, self.mesh, 3)[...] = E
+
+    def gather(self):
+        o = self.o
+        o.halo_periodic(self.Ef, self.mesh.ext, 3, 1, (1, 1, 1), "fill")
+        o.gather_cic(self.mesh, *self.R, self.Ef, self.E, parallel=self.par)
+
+    def dump(self):
+        Ei = self.o.interior(self.Ef, self.mesh, 3)
+        cell = self.hr[0] * self.hr[1] * self.hr[2]
+        if self.kind == "bumpontail":
+            ez = Ei[..., 2]
+            self.history.append((self.time, float(np.sum(ez ** 2)) * cell, float(np.max(np.abs(ez)))))
+        else:
+            s2, _, dot = energy_stats(Ei)
+            self.history.append((self.time, 0.5 * cell * dot, 0.5 * kinetic(self.P), math.sqrt(s2[0]), math.sqrt(s2[1]),
+                                 math.sqrt(s2[2])))
+
+    def pre_run(self):
+        self.scatter()
+        self.solve()
+        self.gather()
+        self.dump()
+
+    def step(self):
+        o, dt = self.o, self.dt
+        if self.kind == "penning":
+            o.penning_kick(1, self.pp, self.R, self.P, self.E)
+        else:
+            for d in range(3):
+                o.kick(self.P[d], self.E[d], 0.5 * dt, self.par)
+        for d in range(3):
+            o.drift(self.R[d], self.P[d], dt, self.par)
+        for d in range(3):
+            o.periodic_bc(self.R[d], 0.0 * self.hr[d] + 0.0, self.nr[d] * self.hr[d] + 0.0, self.par)
+        self.scatter()
+        self.solve()
+        self.gather()
+        if self.kind == "penning":
+            o.penning_kick(2, self.pp, self.R, self.P, self.E)
+        else:
+            for d in range(3):
+                o.kick(self.P[d], self.E[d], 0.5 * dt, self.par)
+        self.time += dt
+        self.dump()
