@@ -14,6 +14,11 @@ PARITY STATUS
     unit_tests/PIC/ORB.cpp (every rank keeps a box, boxes tile the domain, particle counts conserved) -- the
     reference holds no golden cut positions.
   * dumps: PenningTrapManager.h:346-389, LandauDampingManager.h:339-366, BumponTailInstabilityManager.h:448-480.
+  * AlpineOracle (PenningTrap / BumponTail loops): built from the kernels of ippl_oracle.cpp, which ARE pinned against
+    the reference's headers; the loops themselves restate the managers line by line.  The reference holds no known-answer
+    file for these two apps (only FieldLandau_valid_result.csv exists): "parity unpinned" at app level beyond the
+    invariants in tests/test_extras_cpu.py (charge conservation at the reference's 1e-10 abort threshold, the imposed
+    perturbation's field energy from linear theory, the B-field rotation conserving |P| when E = 0).
 """
 import math
 

@@ -126,3 +126,53 @@ def test_orb_find_median_edge_cases():
         boxes, ok = orb.finish()
         m = ox.orb_find_median([float(x) for x in w])
         assert boxes[0][3] == m and boxes[1][0] == m + 1
+
+
+def test_alpine_oracle_loops_invariants():
+    """oracle.extras.AlpineOracle (the PenningTrap / BumponTail managers restated on the CPU): the invariants the
+    reference itself enforces or implies -- charge conservation below AlpineManager's 1e-10 abort threshold at every
+    scatter, the imposed BumponTail perturbation's E_z energy from linear theory at t = 0, particle count fixed."""
+    nr, n = (16, 16, 16), 2_000_000      # shot noise of the fundamental mode: sqrt(2 / n) = 0.001 against delta = 0.01
+    kb = 0.21
+    L = 2 * math.pi / kb
+    d = ox.Dist([0, 0, 1], [0.01, kb] * 3)
+    R, _ = ox.sample_positions(d, [0.0, 0.0, d.cdf(0.0, 2)], [L, L, d.cdf(L, 2)], 42, 0, n)
+    R = [np.clip(r, 1e-12, L) for r in R]
+    P = ox.sample_normal([0.0] * 3, [1 / math.sqrt(2)] * 3, 42, 0, n)
+    s = ox.AlpineOracle("bumpontail", nr, R, P, parallel=False)
+    s.pre_run()
+    assert s.rel_err < 1e-10
+    # the imposed mode: rho = rho0 (1 + delta cos(k z)), rho0 = Q / V = -1  ->  E_z = -(delta / k) sin(k z); project the
+    # computed field on sin(k z) (the total E_z energy is dominated by shot noise at 49 particles per cell)
+    ez = oracle.interior(s.Ef, s.mesh, 3)[..., 2]
+    zc = (np.arange(nr[2]) + 0.5) * s.hr[2]
+    amp = 2.0 * float(np.mean(ez * np.sin(kb * zc)[:, None, None]))
+    assert abs(amp / (-(0.01 / kb)) - 1.0) < 0.35, amp
+    assert s.history[0][1] > 0.5 * (0.5 * (0.01 / kb) ** 2 * L ** 3)
+    for _ in range(2):
+        s.step()
+        assert s.rel_err < 1e-10 and len(s.R[0]) == n
+        assert all((r >= 0).all() and (r <= L).all() for r in s.R)
+    # PenningTrap: blob stays inside the box; Kick1 + Kick2 with E = 0 rotate P about z without changing |P_xy| beyond
+    # the quadrupole's work, so compare against the closed form of one rotation step on a particle at the trap centre
+    d = ox.Dist([2, 2, 2], [10.0, 3.0, 10.0, 1.0, 10.0, 4.0])
+    ub = [d.cdf(0.0, k) for k in range(3)] + [d.cdf(20.0, k) for k in range(3)]
+    n = 200_000
+    R, _ = ox.sample_positions(d, ub[:3], ub[3:], 7, 0, n)
+    R = [np.clip(r, 1e-12, 20.0) for r in R]
+    P = ox.sample_normal([0.0] * 3, [1.0] * 3, 7, 0, n)
+    s = ox.AlpineOracle("penning", nr, R, P, parallel=False)
+    s.pre_run()
+    assert s.rel_err < 1e-10 and s.history[0][1] > 0 and abs(s.history[0][2] / (1.5 * n) - 1) < 0.02
+    s.step()
+    assert s.rel_err < 1e-10
+    pp = s.pp
+    Rc = [np.array([10.0]), np.array([10.0]), np.array([10.0])]      # trap centre: E_ext = 0
+    Pc = [np.array([1.0]), np.array([0.0]), np.array([0.5])]
+    E0 = [np.zeros(1) for _ in range(3)]
+    oracle.penning_kick(1, pp, Rc, Pc, E0)
+    oracle.penning_kick(2, pp, Rc, Pc, E0)
+    # Boris-like rotation: |P_xy| is conserved to O((alpha B)^3) per step (alpha B = 0.012), P_z untouched
+    assert abs(math.hypot(Pc[0][0], Pc[1][0]) - 1.0) < 1e-5 and Pc[2][0] == 0.5
+    ang = math.atan2(Pc[1][0], Pc[0][0])
+    assert abs(ang - 2 * math.atan(-pp.alpha * pp.Bext)) < 1e-6    # rotation by 2 atan(|alpha| B) ~ omega_c dt per step
