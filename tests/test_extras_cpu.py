@@ -175,4 +175,4 @@ def test_alpine_oracle_loops_invariants():
     # Boris-like rotation: |P_xy| is conserved to O((alpha B)^3) per step (alpha B = 0.012), P_z untouched
     assert abs(math.hypot(Pc[0][0], Pc[1][0]) - 1.0) < 1e-5 and Pc[2][0] == 0.5
     ang = math.atan2(Pc[1][0], Pc[0][0])
-    assert abs(ang - 2 * math.atan(-pp.alpha * pp.Bext)) < 1e-6    # rotation by 2 atan(|alpha| B) ~ omega_c dt per step
+    assert abs(ang - 2 * math.atan(-pp.alpha * pp.Bext)) < 1e-5    # rotation by 2 atan(|alpha| B) + O((alpha B)^3) per step
