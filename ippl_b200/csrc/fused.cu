@@ -645,11 +645,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArg
 //   * the deposit no longer issues reductions per (chunk, cell).  Every window cell has a fixed owner thread; the
 //     owner adds the chunk's 8 weight moments of its cell to accumulators that live in TENSOR MEMORY
 //     (tcgen05.ld / tcgen05.st, 32x32b.x16: 16 columns = 8 doubles per lane, private to the warp, no shared-memory
-//     or LSU traffic).  After the tile's last chunk the owners turn the moments into the 8 node sums of their cell
-//     and add them, node offset by node offset (8 rounds: inside a round all cells hit distinct nodes, so plain
-//     read-modify-write), into a 9x9x9 node lattice in shared memory, which is then flushed with ONE RED.F64 per
-//     touched node: ~0.2 reductions per particle instead of 1.6.
-constexpr int LAT = WIN + 1;  // nodes per axis of the window
+//     or LSU traffic).  After the tile's last chunk every owner turns its cell's moments into the 8 node sums and
+//     adds them to rho with one RED.F64 per node: ~0.5 reductions per particle instead of 1.6, and the end of a
+//     tile needs no barrier and no staging (an earlier variant summed the cells into a 9x9x9 node lattice in shared
+//     memory first -- 0.2 reductions per particle, but 9 CTA barriers per tile and 5.8 KB of shared memory, which is
+//     what now pays for the 15th consumer warp).
 
 template <int NT, int K>
 struct Step3Smem {
@@ -658,7 +658,6 @@ struct Step3Smem {
         double dat[6][CAP];  // as loaded: SoA planes; after the scan: CAP 48-byte records in sorted order
     } st[2];
     double2 ep[2][EP_N];
-    double lat[LAT * LAT * LAT];
     ChunkDesc desc[2];
     unsigned long long full[2], empty[2];
     int hist[WIN_CELLS];
@@ -789,7 +788,6 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
         s.tsof[id]    = (unsigned char)ts;
         s.hist[c]     = 0;
     }
-    for (int i = t; i < LAT * LAT * LAT; i += NT + 32) s.lat[i] = 0.0;
     __syncthreads();
 
     if (warp == NW) {
@@ -1039,57 +1037,35 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
         if (lane == 0) mbar_arrive(&s.empty[st]);
 
         if (D.pad[0]) {
-            // ---- last chunk of the tile: moments -> node sums -> node lattice (8 conflict-free rounds) -> global.
-            //      The moments are read from tensor memory once and the accumulators re-zeroed at once; the rounds work
-            //      from registers.
-            double am[NSL][8];
+            // ---- last chunk of the tile: every owner turns its cell's moments into the 8 node sums and adds them to
+            //      rho with one RED.F64 per node -- no barrier, no staging: the warps run on into the next tile
             const double z8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int sl = 0; sl < NSL; ++sl) {
                 if (sl * NT + warp * 32 < WIN_CELLS) {
-                    tmem_ld8(tm0 + sl * 16, am[sl]);
+                    double a[8];
+                    tmem_ld8(tm0 + sl * 16, a);
                     tmem_st8(tm0 + sl * 16, z8);
-                } else {
+                    if (a[0] != 0.0) {
+                        const double s1 = a[1], s2 = a[2], s3 = a[3], s12 = a[4], s13 = a[5], s23 = a[6], s123 = a[7];
+                        double nd[8];  // node n: bit d set -> lower node along d (weight 1 - w_d)
+                        nd[0] = s123;
+                        nd[1] = s23 - s123;
+                        nd[2] = s13 - s123;
+                        nd[3] = (s3 - s13) - (s23 - s123);
+                        nd[4] = s12 - s123;
+                        nd[5] = (s2 - s12) - (s23 - s123);
+                        nd[6] = (s1 - s12) - (s13 - s123);
+                        nd[7] = ((a[0] - s1) - (s2 - s12)) - ((s3 - s13) - (s23 - s123));
+                        const unsigned xyz = s.cellxyz[sl * NT + t];
+                        // ghosted index of the cell's upper node = window coordinate + window origin + nghost
+                        const long gx = (long)(xyz & 15) + wox + A.m.nghost, gy = (long)((xyz >> 4) & 15) + woy + A.m.nghost,
+                                   gz = (long)(xyz >> 8) + woz + A.m.nghost;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) am[sl][i] = 0.0;
-                }
-            }
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-#pragma unroll
-                for (int sl = 0; sl < NSL; ++sl) {
-                    if (sl * NT + warp * 32 < WIN_CELLS) {
-                        const double* a = am[sl];
-                        if (a[0] != 0.0) {
-                            const double s1 = a[1], s2 = a[2], s3 = a[3], s12 = a[4], s13 = a[5], s23 = a[6], s123 = a[7];
-                            double nd;  // node n: bit d set -> lower node along d (weight 1 - w_d)
-                            if (n == 0) nd = s123;
-                            else if (n == 1) nd = s23 - s123;
-                            else if (n == 2) nd = s13 - s123;
-                            else if (n == 3) nd = (s3 - s13) - (s23 - s123);
-                            else if (n == 4) nd = s12 - s123;
-                            else if (n == 5) nd = (s2 - s12) - (s23 - s123);
-                            else if (n == 6) nd = (s1 - s12) - (s13 - s123);
-                            else nd = ((a[0] - s1) - (s2 - s12)) - ((s3 - s13) - (s23 - s123));
-                            const unsigned xyz = s.cellxyz[sl * NT + t];
-                            // lattice coordinate of the cell's upper node = window coordinate + 1
-                            const int lx = (int)(xyz & 15) + 1 - (n & 1), ly = (int)((xyz >> 4) & 15) + 1 - ((n >> 1) & 1),
-                                      lz = (int)(xyz >> 8) + 1 - ((n >> 2) & 1);
-                            s.lat[(lz * LAT + ly) * LAT + lx] += nd;
-                        }
+                        for (int n = 0; n < 8; ++n)
+                            atomicAdd(&A.rho[(gx - (n & 1)) + (long)A.m.ex * ((gy - ((n >> 1) & 1)) + (long)A.m.ey * (gz - ((n >> 2) & 1)))],
+                                      A.q * nd[n]);
                     }
-                }
-                consumer_sync<NT>();
-            }
-            for (int i = t; i < LAT * LAT * LAT; i += NT) {
-                const double v = s.lat[i];
-                if (v != 0.0) {
-                    s.lat[i]     = 0.0;
-                    const int lx = i % LAT, ly = (i / LAT) % LAT, lz = i / (LAT * LAT);
-                    // lattice coordinate l <-> ghosted node index l + window origin + nghost - 1
-                    const long gi = (long)(lx + wox + A.m.nghost - 1) +
-                                    (long)A.m.ex * ((ly + woy + A.m.nghost - 1) + (long)A.m.ey * (lz + woz + A.m.nghost - 1));
-                    atomicAdd(&A.rho[gi], A.q * v);
                 }
             }
         }
@@ -1208,7 +1184,8 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         case 15: rc = launch_fused3<320, 2, 2>(ctx, A); break;
         case 17: rc = launch_fused3<416, 2, 2>(ctx, A); break;
         case 5: rc = launch_fused<384, 2, 2>(ctx, A); break;  // generation 2
-        default: rc = launch_fused3<448, 2, 2>(ctx, A); break;  // generation 3, 14 consumer warps (measured best)
+        case 16: rc = launch_fused3<448, 2, 2>(ctx, A); break;
+        default: rc = launch_fused3<480, 2, 2>(ctx, A); break;  // generation 3, 15 consumer warps (measured best)
     }
     if (rc) return rc;
     rc = bins_plan(ctx, b, o, A.seg_cap);
