@@ -3,12 +3,14 @@ recursive bisection and the dump reductions.  TEST INFRASTRUCTURE ONLY (same rul
 __graft_entry__.smoke() and bench.py's CPU legs may import it; the product never does).
 
 PARITY STATUS
-  * sampling: the reference draws from Kokkos::Random_XorShift64_Pool, whose stream assignment is per thread / per
-    lock and backend dependent, so no reference run pins a sample stream: "parity unpinned" for the
-    STREAM.  What is restated line by line and checked is everything around it: the rank counts
-    (InverseTransformSampling.h:106-131), the map u -> x (fill_random :199-215 + NewtonRaphson, Utility.h:52-59) and
-    the distribution functions of the three mini-apps; the uniform stream itself is the published Philox4x32-10,
-    implemented here independently of the product and pinned by the Random123 known-answer vectors.
+  * sampling: PINNED against the reference's own headers for everything but the random stream -- Random/Distribution.h,
+    NormalDistribution.h, Utility.h (NewtonRaphson), InverseTransformSampling.h (constructor = rank counts + CDF bounds,
+    generate / fill_random) and Randn.h are compiled in place from /root/reference with replayed random numbers
+    (oracle/ref_shim/refshim_random.cpp -> oracle/_ref/libippl_refshim_random.so) and compared live and through the
+    committed fixture tests/golden/ref_random.npz (tests/test_oracle_random_pinned.py).  The STREAM itself is "parity
+    unpinned" by nature: the reference draws from Kokkos::Random_XorShift64_Pool, whose stream assignment is per thread /
+    per lock and backend dependent; ours is the published Philox4x32-10, implemented here independently of
+    the product and pinned by the Random123 known-answer vectors.
   * ORB: findCutAxis / findMedian / cutDomain / binaryRepartition restated from
     src/Decomposition/OrthogonalRecursiveBisection.hpp:14-232; pinned by the invariants of the reference's own test
     unit_tests/PIC/ORB.cpp (every rank keeps a box, boxes tile the domain, particle counts conserved) -- the

@@ -83,3 +83,73 @@ def neighbors(ng, nranks, my, nghost=1, periodic=True, parallel=(1, 1, 1)):
 
 def matching_index(i):
     return lib().ref_matching_index(int(i))
+
+
+# ---- sampling path of the reference (oracle/_ref/libippl_refshim_random.so, ref_shim/refshim_random.cpp) ----------------
+_RLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_random.so")
+_rlib = None
+
+
+def random_available(try_build=True):
+    if os.path.exists(_RLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_RLIB_PATH)
+    return False
+
+
+def rlib():
+    global _rlib
+    if _rlib is None:
+        if not random_available():
+            raise RuntimeError("reference sampling shim not built (needs /root/reference)")
+        _rlib = C.CDLL(_RLIB_PATH)
+        _rlib.refrand_eval.restype = C.c_double
+        _rlib.refrand_full_pdf.restype = C.c_double
+        _rlib.refrand_newton.restype = C.c_double
+    return _rlib
+
+
+def _par(par):
+    return (C.c_double * 6)(*[float(p) for p in par])
+
+
+def rand_eval(kind, par, which, d, x, aux=0.0):
+    """kind 1 cosine functors / 2 NormalDistribution; which 0 cdf, 1 pdf, 2 estimate, 3 objective(x, u=aux), 4 its derivative"""
+    return rlib().refrand_eval(kind, _par(par), which, d, C.c_double(x), C.c_double(aux))
+
+
+def rand_full_pdf(kind, par, x):
+    return rlib().refrand_full_pdf(kind, _par(par), _d3(x))
+
+
+def rand_newton(kind, par, d, x0, u):
+    return rlib().refrand_newton(kind, _par(par), d, C.c_double(x0), C.c_double(u))
+
+
+def rand_sampling(kind, par, rmin, rmax, regions, ntotal, gen_rank=-1, u01=None):
+    """The reference's InverseTransformSampling constructor for every rank -> (nlocal[nranks], ubounds[nranks][6]) and,
+    for gen_rank >= 0, generate() with the uniforms u01[3][nlocal] replayed -> x[3][nlocal]."""
+    reg = np.ascontiguousarray(regions, dtype=np.float64)
+    nr = reg.shape[0]
+    nloc = (C.c_long * nr)()
+    ub = np.zeros((nr, 6))
+    out = None
+    if gen_rank >= 0:
+        u01 = np.ascontiguousarray(u01, dtype=np.float64)
+        out = np.zeros_like(u01)
+    rlib().refrand_sampling(kind, _par(par), _d3(rmin), _d3(rmax), _p(reg), nr, C.c_long(ntotal), nloc, _p(ub), gen_rank,
+                            _p(u01) if out is not None else None, _p(out) if out is not None else None)
+    return list(nloc), ub, out
+
+
+def rand_randn(mu, sd, g):
+    """randn::operator() with the standard normals g[n][3] replayed -> v[n][3]"""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    out = np.zeros_like(g)
+    rlib().refrand_randn(_d3(mu), _d3(sd), C.c_long(g.shape[0]), _p(g), _p(out))
+    return out
