@@ -12,9 +12,11 @@ PARITY STATUS
     per lock and backend dependent; ours is the published Philox4x32-10, implemented here independently of
     the product and pinned by the Random123 known-answer vectors.
   * ORB: findCutAxis / findMedian / cutDomain / binaryRepartition restated from
-    src/Decomposition/OrthogonalRecursiveBisection.hpp:14-232; pinned by the invariants of the reference's own test
-    unit_tests/PIC/ORB.cpp (every rank keeps a box, boxes tile the domain, particle counts conserved) -- the
-    reference holds no golden cut positions.
+    src/Decomposition/OrthogonalRecursiveBisection.hpp:14-232 and PINNED against that very code: the reference's
+    OrthogonalRecursiveBisection.h/.hpp (+ FieldLayout::updateLayout) are compiled in place on serial stand-ins
+    (oracle/ref_shim/refshim_orb.cpp -> oracle/_ref/libippl_refshim_orb.so) and compared live and through the committed
+    tests/golden/ref_orb.npz (tests/test_oracle_orb_pinned.py: 63 weight fields x rank counts, exact boxes); plus the
+    invariants of the reference's own test unit_tests/PIC/ORB.cpp (every rank keeps a box, boxes tile the domain).
   * dumps: PenningTrapManager.h:346-389, LandauDampingManager.h:339-366, BumponTailInstabilityManager.h:448-480.
   * AlpineOracle (PenningTrap / BumponTail loops): built from the kernels of ippl_oracle.cpp, which ARE pinned against
     the reference's headers; the loops themselves restate the managers line by line.  The reference holds no known-answer

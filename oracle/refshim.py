@@ -153,3 +153,42 @@ def rand_randn(mu, sd, g):
     out = np.zeros_like(g)
     rlib().refrand_randn(_d3(mu), _d3(sd), C.c_long(g.shape[0]), _p(g), _p(out))
     return out
+
+
+# ---- the reference's OrthogonalRecursiveBisection (oracle/_ref/libippl_refshim_orb.so, ref_shim/refshim_orb.cpp) --------
+_OLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_orb.so")
+_olib = None
+
+
+def orb_available(try_build=True):
+    if os.path.exists(_OLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_OLIB_PATH)
+    return False
+
+
+def olib():
+    global _olib
+    if _olib is None:
+        if not orb_available():
+            raise RuntimeError("reference ORB shim not built (needs /root/reference)")
+        _olib = C.CDLL(_OLIB_PATH)
+    return _olib
+
+
+def orb_find_median(w):
+    a = np.ascontiguousarray(w, dtype=np.float64)
+    return int(olib().reforb_find_median(_p(a), len(a)))
+
+
+def orb_repartition(ng, nranks, weight):
+    """binaryRepartition of the reference on the global interior weights weight[z][y][x] -> (boxes[nranks][6], ok)"""
+    w = np.ascontiguousarray(weight, dtype=np.float64)
+    boxes = np.zeros((nranks, 6), dtype=np.int32)
+    ok = olib().reforb_repartition(_i3(ng), nranks, _p(w), _p(boxes))
+    return boxes, bool(ok)
