@@ -106,7 +106,7 @@ namespace {
         }
         ippl::NDIndex<3> getOwned() const { return owned; }
         int getNghost() const { return nghost; }
-        View3 getView() const { return View3{const_cast<double*>(data.data()), owned[0].length() + 2, owned[1].length() + 2}; }
+        View3 getView() const { return View3{const_cast<double*>(data.data()), (long)owned[0].length() + 2, (long)owned[1].length() + 2}; }
         const FakeMesh& get_mesh() const { return *mesh; }
         const ippl::FieldLayout<3>& getLayout() const { return *fl; }
         void updateLayout(ippl::FieldLayout<3>&) {}  // the weights are consumed before the layout changes

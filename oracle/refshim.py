@@ -192,3 +192,32 @@ def orb_repartition(ng, nranks, weight):
     boxes = np.zeros((nranks, 6), dtype=np.int32)
     ok = olib().reforb_repartition(_i3(ng), nranks, _p(w), _p(boxes))
     return boxes, bool(ok)
+
+
+# ---- the reference's in-rank periodic halo (oracle/_ref/libippl_refshim_halo.so, ref_shim/refshim_halo.cpp) -------------
+_HLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_halo.so")
+_hlib = None
+
+
+def halo_available(try_build=True):
+    if os.path.exists(_HLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_HLIB_PATH)
+    return False
+
+
+def halo_periodic(field, ng, mode, nghost=1):
+    """HaloCells::applyPeriodicSerialDim<assign | rhs_plus_assign> of the reference, in place, on a ghosted scalar field
+    (x fastest) of a single-rank all-periodic layout; mode "fill" or "accumulate"."""
+    global _hlib
+    if _hlib is None:
+        if not halo_available():
+            raise RuntimeError("reference halo shim not built (needs /root/reference)")
+        _hlib = C.CDLL(_HLIB_PATH)
+    _hlib.refhalo_periodic(_i3(ng), nghost, 0 if mode == "fill" else 1, _p(field))
+    return field

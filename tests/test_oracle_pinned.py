@@ -102,3 +102,26 @@ def test_landau_known_answer_csv():
     assert np.max(np.abs(hist[:, 2] - ref[:, 2])) < 4e-1
     # far tighter than the reference asks: the damping curve itself
     assert np.max(np.abs(hist[:, 1] - ref[:, 1]) / ref[:, 1]) < 0.05
+
+
+def test_periodic_halo_vs_reference_code():
+    """The in-rank periodic wrap of fillHalo / accumulateHalo (HaloCells::applyPeriodicSerialDim + HaloPeriodicFunctor,
+    src/Field/HaloCells.hpp:59-87, 297-336, with the reference's own assign / rhs_plus_assign operators) executed by the
+    reference's code -- live through oracle/_ref/libippl_refshim_halo.so where /root/reference exists, and through the
+    committed tests/golden/ref_halo.npz -- against the restatement, bit for bit, including the x -> y -> z cascade that
+    makes edges and corners come out right.  (tests/test_gpu_parity.py holds the CUDA kernels to the restatement.)"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_halo import SHAPES
+    from oracle import refshim
+    gold = np.load(os.path.join(root, "tests", "golden", "ref_halo.npz"))
+    for i, ng in enumerate(SHAPES):
+        ext = tuple(n + 2 for n in ng)
+        for mode in ("fill", "accumulate"):
+            got = gold[f"in_{i}"].copy()
+            oracle.halo_periodic(got, ext, 1, 1, (1, 1, 1), mode)
+            assert np.array_equal(got, gold[f"{mode}_{i}"]), (ng, mode)
+            if refshim.halo_available():
+                assert np.array_equal(refshim.halo_periodic(gold[f"in_{i}"].copy(), ng, mode), gold[f"{mode}_{i}"])
