@@ -221,3 +221,34 @@ def halo_periodic(field, ng, mode, nghost=1):
         _hlib = C.CDLL(_HLIB_PATH)
     _hlib.refhalo_periodic(_i3(ng), nghost, 0 if mode == "fill" else 1, _p(field))
     return field
+
+
+# ---- the reference's RegionLayout (oracle/_ref/libippl_refshim_region.so, ref_shim/refshim_region.cpp) -------------------
+_GLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_region.so")
+_glib = None
+
+
+def region_available(try_build=True):
+    if os.path.exists(_GLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_GLIB_PATH)
+    return False
+
+
+def regions(ng, nranks, origin, h, boxes=None):
+    """detail::RegionLayout(FieldLayout, UniformCartesian) of the reference -> regions[nranks][6] = min[3], max[3]; with
+    `boxes` ([nranks][6] lo, hi inclusive) after FieldLayout::updateLayout(boxes)"""
+    global _glib
+    if _glib is None:
+        if not region_available():
+            raise RuntimeError("reference region shim not built (needs /root/reference)")
+        _glib = C.CDLL(_GLIB_PATH)
+    out = np.zeros((nranks, 6))
+    b = None if boxes is None else np.ascontiguousarray(boxes, dtype=np.int32)
+    _glib.refregion_regions(_i3(ng), nranks, _p(b) if b is not None else None, _d3(origin), _d3(h), _p(out))
+    return out

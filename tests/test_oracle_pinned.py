@@ -125,3 +125,37 @@ def test_periodic_halo_vs_reference_code():
             assert np.array_equal(got, gold[f"{mode}_{i}"]), (ng, mode)
             if refshim.halo_available():
                 assert np.array_equal(refshim.halo_periodic(gold[f"in_{i}"].copy(), ng, mode), gold[f"{mode}_{i}"])
+
+
+def test_rank_regions_vs_reference_code():
+    """The physical region of every rank -- the doubles positionInRegion compares particle positions with, so ownership
+    is bit-exact only if they are -- from the reference's real detail::RegionLayout + UniformCartesian::getVertexPosition
+    (Region/RegionLayout.hpp:68-98, Meshes/UniformCartesian.h:45-53; oracle/ref_shim/refshim_region.cpp), live and through
+    tests/golden/ref_region.npz, against the restatement AND the product's ipplb_layout_regions: exact."""
+    import math
+    import os
+    import sys
+    import ippl_b200 as ib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_region import GRIDS, RANKS, meshes
+    from oracle import refshim
+    gold = np.load(os.path.join(root, "tests", "golden", "ref_region.npz"))
+    for gi, ng in enumerate(GRIDS):
+        for nr in RANKS:
+            boxes = oracle.partition(ng, nr)
+            L = ib.Layout(ng, nr)
+            for mi, (origin, h) in enumerate(meshes(ng)):
+                want = gold[f"reg_{gi}_{nr}_{mi}"]
+                assert np.array_equal(oracle.regions(ng, boxes, origin, h), want), (ng, nr, mi)
+                assert np.array_equal(L.regions(origin, h), want), (ng, nr, mi)
+                if refshim.region_available() and gi < 4:
+                    assert np.array_equal(refshim.regions(ng, nr, origin, h), want)
+            L.close()
+    ng, origin, h = (24, 16, 16), (0.0, 0.0, 0.0), (4 * math.pi / 16,) * 3
+    boxes, want = gold["orb_boxes"], gold["orb_regions"]
+    assert np.array_equal(oracle.regions(ng, boxes, origin, h), want)
+    L = ib.Layout(ng, 2)
+    L.set_boxes(boxes)
+    assert np.array_equal(L.regions(origin, h), want)
+    L.close()
