@@ -112,15 +112,17 @@ namespace {
         void updateLayout(ippl::FieldLayout<3>&) {}  // the weights are consumed before the layout changes
         void accumulateHalo() {}
     };
-    struct NoParticles {  // binaryRepartition is run with isFirstRepartition = true: scatterR is compiled, not executed
+    struct Positions {  // what scatterR asks of a particle attribute
         using memory_space = Kokkos::HostSpace;
         struct V {
             ippl::Vector<double, 3>* p;
             ippl::Vector<double, 3>& operator()(std::size_t i) const { return p[i]; }
         };
-        V getView() const { return V{nullptr}; }
-        std::size_t getParticleCount() const { return 0; }
+        std::vector<ippl::Vector<double, 3>> r;
+        V getView() const { return V{const_cast<ippl::Vector<double, 3>*>(r.data())}; }
+        std::size_t getParticleCount() const { return r.size(); }
     };
+    using NoParticles = Positions;  // binaryRepartition below runs with isFirstRepartition = true: scatterR is not executed
 }  // namespace
 
 #include "Decomposition/OrthogonalRecursiveBisection.h"
@@ -161,6 +163,29 @@ int reforb_repartition(const int ng[3], int nranks, const double* w, int* boxes_
         }
     refshim::g_size = 1;
     return ok ? 1 : 0;
+}
+
+// scatterR(R), OrthogonalRecursiveBisection.hpp:234-300: the reference's own particle loop -- l = (R - origin) * invdx +
+// 0.5, index = (int) l, whi = l - index, wlo = 1 - whi, args = index - lDom.first() + nghost, scatterToField with weight
+// 1 -- on a single-rank layout of ng cells; field_out is the ghosted (ng + 2)^3 array, x fastest, BEFORE any halo
+// accumulation.  The same loop body as ParticleAttrib::scatter (ParticleAttrib.hpp:167-184).
+void reforb_scatterR(const int ng[3], const double origin[3], const double h[3], long n, const double* x, const double* y,
+                     const double* z, double* field_out) {
+    refshim::g_rank = 0;
+    refshim::g_size = 1;
+    ippl::Index ix(ng[0]), iy(ng[1]), iz(ng[2]);
+    ippl::NDIndex<3> domain(ix, iy, iz);
+    std::array<bool, 3> par = {true, true, true};
+    ippl::FieldLayout<3> fl(ippl::mpi::Communicator(), domain, par, true, 1);
+    FakeMesh mesh;
+    for (int d = 0; d < 3; ++d) { mesh.hx[d] = h[d]; mesh.origin[d] = origin[d]; }
+    ippl::OrthogonalRecursiveBisection<FakeField, double> orb;
+    orb.bf_m.initialize(mesh, fl);
+    Positions R;
+    R.r.resize((std::size_t)n);
+    for (long i = 0; i < n; ++i) { R.r[i][0] = x[i]; R.r[i][1] = y[i]; R.r[i][2] = z[i]; }
+    orb.scatterR(R);
+    for (std::size_t i = 0; i < orb.bf_m.data.size(); ++i) field_out[i] = orb.bf_m.data[i];
 }
 
 }  // extern "C"

@@ -252,3 +252,12 @@ def regions(ng, nranks, origin, h, boxes=None):
     b = None if boxes is None else np.ascontiguousarray(boxes, dtype=np.int32)
     _glib.refregion_regions(_i3(ng), nranks, _p(b) if b is not None else None, _d3(origin), _d3(h), _p(out))
     return out
+
+
+def orb_scatter_r(ng, origin, h, x, y, z):
+    """OrthogonalRecursiveBisection::scatterR of the reference (the same particle loop as ParticleAttrib::scatter, weight
+    1) on a single-rank layout -> ghosted (ng + 2)^3 field, x fastest, before any halo accumulation"""
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    out = np.zeros((ng[0] + 2) * (ng[1] + 2) * (ng[2] + 2))
+    olib().reforb_scatterR(_i3(ng), _d3(origin), _d3(h), C.c_long(len(x)), _p(x), _p(y), _p(z), _p(out))
+    return out

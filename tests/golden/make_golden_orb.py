@@ -40,6 +40,15 @@ def main():
     for i, w in enumerate(MEDIANS):
         out[f"median_w_{i}"] = np.asarray(w, dtype=np.float64)
         out[f"median_{i}"] = np.array([refshim.orb_find_median(w)])
+    # scatterR: the reference's own particle loop (index truncation, weights, scatterToField), weight 1
+    rng = np.random.default_rng(20261020)
+    ng, origin, h, n = (12, 10, 8), (0.25, -1.0, 3.0), (0.5, 0.125, 1.5), 4000
+    R = [origin[d] + rng.uniform(0, ng[d] * h[d], n) for d in range(3)]
+    for d in range(3):   # on the lower / upper corner of the box, on a cell face, on a cell centre
+        R[d][0], R[d][1] = origin[d], origin[d] + ng[d] * h[d]
+        R[d][2], R[d][3] = origin[d] + 3.0 * h[d], origin[d] + 2.5 * h[d]
+    out.update(sr_ng=np.array(ng), sr_origin=np.array(origin), sr_h=np.array(h), sr_x=R[0], sr_y=R[1], sr_z=R[2],
+               sr_field=refshim.orb_scatter_r(ng, origin, h, *R))
     path = os.path.join(os.path.dirname(__file__), "ref_orb.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays", os.path.getsize(path), "bytes")

@@ -65,3 +65,20 @@ def test_find_median_vs_reference(gold):
             orb.cut(np.asarray(w, dtype=np.float64))
             boxes, _ = orb.finish()
             assert boxes[0][3] == want and boxes[1][0] == want + 1
+
+
+def test_scatter_loop_vs_reference(gold):
+    """scatterR executed by the reference's code: l = (R - origin) * invdx + 0.5, index = (int) l, whi = l - index,
+    wlo = 1 - whi, args = index - lDom.first() + nghost, scatterToField -- the particle loop ParticleAttrib::scatter
+    shares (ParticleAttrib.hpp:167-184).  The serial restatement visits particles and stencil points in the same order:
+    bit-exact, corner / face / centre particles included."""
+    import oracle
+    ng, origin, h = tuple(int(v) for v in gold["sr_ng"]), tuple(gold["sr_origin"]), tuple(gold["sr_h"])
+    R = [gold["sr_x"], gold["sr_y"], gold["sr_z"]]
+    m = oracle.Mesh.make(ng, origin, h)
+    got = oracle.field_zeros(m)
+    oracle.scatter_cic(m, *R, 1.0, got)
+    assert np.array_equal(got, gold["sr_field"])
+    assert abs(got.sum() - len(R[0])) < 1e-9
+    if refshim.orb_available():
+        assert np.array_equal(refshim.orb_scatter_r(ng, origin, h, *R), gold["sr_field"])
