@@ -169,5 +169,42 @@ int ref_neighbors(const int* ng, const int* is_parallel, int nranks, int periodi
     return cnt;
 }
 
+// the same tables after FieldLayout::updateLayout(domains) with caller-supplied rank boxes ([nranks][6] lo, hi inclusive):
+// what an ORB repartition leaves behind (FieldLayout.hpp:59-73 -> findNeighbors)
+int ref_neighbors_boxes(const int* ng, int nranks, int periodic, int nghost, int my, const int* boxes, int* out,
+                        int max_entries) {
+    refshim::g_rank = my;
+    refshim::g_size = nranks;
+    ippl::Index i0(ng[0]), i1(ng[1]), i2(ng[2]);
+    ippl::NDIndex<3> domain(i0, i1, i2);
+    std::array<bool, 3> par = {true, true, true};
+    ippl::FieldLayout<3> fl(ippl::mpi::Communicator(), domain, par, periodic != 0, nghost);
+    std::vector<ippl::NDIndex<3>> doms(nranks);
+    for (int r = 0; r < nranks; ++r)
+        doms[r] = ippl::NDIndex<3>(ippl::Index(boxes[6 * r], boxes[6 * r + 3]), ippl::Index(boxes[6 * r + 1], boxes[6 * r + 4]),
+                                   ippl::Index(boxes[6 * r + 2], boxes[6 * r + 5]));
+    fl.updateLayout(doms);
+    int cnt = 0;
+    const auto& nb = fl.getNeighbors();
+    const auto& sr = fl.getNeighborsSendRange();
+    const auto& rr = fl.getNeighborsRecvRange();
+    for (size_t comp = 0; comp < nb.size(); ++comp)
+        for (size_t i = 0; i < nb[comp].size(); ++i) {
+            if (cnt < max_entries) {
+                int* o = out + cnt * 14;
+                o[0]   = (int)comp;
+                o[1]   = nb[comp][i];
+                for (int d = 0; d < 3; ++d) {
+                    o[2 + d]  = (int)sr[comp][i].lo[d];
+                    o[5 + d]  = (int)sr[comp][i].hi[d];
+                    o[8 + d]  = (int)rr[comp][i].lo[d];
+                    o[11 + d] = (int)rr[comp][i].hi[d];
+                }
+            }
+            ++cnt;
+        }
+    return cnt;
+}
+
 int ref_matching_index(int i) { return ippl::FieldLayout<3>::getMatchingIndex(i); }
 }

@@ -81,6 +81,15 @@ def neighbors(ng, nranks, my, nghost=1, periodic=True, parallel=(1, 1, 1)):
     return boxes, out[:n].copy()
 
 
+def neighbors_boxes(ng, boxes, my, nghost=1, periodic=True):
+    """neighbour tables of rank `my` after FieldLayout::updateLayout(boxes) (an ORB layout)"""
+    b = np.ascontiguousarray(boxes, dtype=np.int32)
+    out = np.zeros((512, 14), dtype=np.int32)
+    n = lib().ref_neighbors_boxes(_i3(ng), b.shape[0], int(periodic), nghost, my, _p(b), _p(out), 512)
+    assert 0 <= n <= 512
+    return out[:n].copy()
+
+
 def matching_index(i):
     return lib().ref_matching_index(int(i))
 

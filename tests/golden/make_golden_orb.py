@@ -40,6 +40,15 @@ def main():
     for i, w in enumerate(MEDIANS):
         out[f"median_w_{i}"] = np.asarray(w, dtype=np.float64)
         out[f"median_{i}"] = np.array([refshim.orb_find_median(w)])
+    # neighbour tables of the ORB layouts: FieldLayout::updateLayout(domains) -> findNeighbors of the reference
+    for gi, ng in enumerate(GRIDS):
+        for kind in ("blob", "random"):
+            for nr in (2, 3, 4, 5, 8):
+                boxes = out[f"boxes_{gi}_{kind}_{nr}"]
+                if not out[f"ok_{gi}_{kind}_{nr}"][0] or (boxes[:, 3:] - boxes[:, :3] + 1).min() < 2:
+                    continue
+                for my in range(nr):
+                    out[f"nb_{gi}_{kind}_{nr}_{my}"] = refshim.neighbors_boxes(ng, boxes, my)
     # scatterR: the reference's own particle loop (index truncation, weights, scatterToField), weight 1
     rng = np.random.default_rng(20261020)
     ng, origin, h, n = (12, 10, 8), (0.25, -1.0, 3.0), (0.5, 0.125, 1.5), 4000

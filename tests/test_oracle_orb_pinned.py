@@ -82,3 +82,28 @@ def test_scatter_loop_vs_reference(gold):
     assert abs(got.sum() - len(R[0])) < 1e-9
     if refshim.orb_available():
         assert np.array_equal(refshim.orb_scatter_r(ng, origin, h, *R), gold["sr_field"])
+
+
+def test_neighbour_tables_of_orb_layouts_vs_reference(gold):
+    """After an ORB repartition the reference rebuilds its halo tables with FieldLayout::updateLayout -> findNeighbors
+    (FieldLayout.hpp:59-73, 203-341) on boxes of unequal size.  The restatement and the product's ipplb_layout_set_boxes
+    + ipplb_layout_neighbors reproduce components, peers and send / receive ranges exactly."""
+    import oracle
+    n = 0
+    for gi, ng in enumerate(GRIDS):
+        for kind in ("blob", "random"):
+            for nr in (2, 3, 4, 5, 8):
+                if f"nb_{gi}_{kind}_{nr}_0" not in gold:
+                    continue
+                boxes = gold[f"boxes_{gi}_{kind}_{nr}"]
+                L = ib.Layout(ng, nr)
+                L.set_boxes(boxes)
+                for my in range(nr):
+                    want = gold[f"nb_{gi}_{kind}_{nr}_{my}"]
+                    assert np.array_equal(oracle.neighbors(ng, boxes, my), want), (ng, kind, nr, my)
+                    assert np.array_equal(L.neighbors(my), want), (ng, kind, nr, my)
+                    if refshim.available():
+                        assert np.array_equal(refshim.neighbors_boxes(ng, boxes, my), want)
+                    n += 1
+                L.close()
+    assert n >= 100
