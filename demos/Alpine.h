@@ -384,7 +384,13 @@ protected:
 // the reference's main() of the three drivers (demos/alpine/LandauDamping.cpp:38-95): same positional arguments
 template <class Manager>
 int alpine_main(int argc, char* argv[]) {
-    ippl::initialize(argc, argv);
+    try {
+        ippl::initialize(argc, argv);
+    } catch (const std::exception& ex) {
+        // no CUDA device / driver: the library has no CPU fallback, and neither has the driver
+        std::cerr << TestName << ": cannot start: " << ex.what() << " (a CUDA device is required; there is no CPU fallback)" << std::endl;
+        return 2;
+    }
     int exit_code = 0;
     {
         try {

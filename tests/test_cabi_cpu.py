@@ -59,3 +59,21 @@ def test_layout_matches_oracle(nr):
 def test_layout_rejects_too_many_ranks():
     with pytest.raises(ib.IpplbError):
         ib.Layout((2, 1, 1), 4)  # FieldLayout::initialize throws (FieldLayout.hpp:111-117)
+
+
+def test_facade_drivers_build_and_refuse_to_run_without_a_gpu(tmp_path):
+    """The C++ facade (include/ippl/Ippl.h) and the three drivers compile with the host compiler alone, and a driver
+    started without a CUDA device stops with an error instead of computing anything on the CPU."""
+    import os
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "demos"), "-s"])
+    for app in ("LandauDamping", "PenningTrap", "BumponTailInstability"):
+        assert os.path.exists(os.path.join(root, "demos", app))
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([os.path.join(root, "demos", "LandauDamping"), "8", "8", "8", "1000", "1", "FFT", "1.0", "LeapFrog"],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 2 and "no CPU fallback" in out.stderr
+    assert not (tmp_path / "data").exists()
