@@ -1193,7 +1193,6 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         case 17: rc = launch_fused3<416, 2, 2>(ctx, A); break;
         case 5: rc = launch_fused<384, 2, 2>(ctx, A); break;  // generation 2
         case 16: rc = launch_fused3<448, 2, 2>(ctx, A); break;
-        case 17: rc = launch_fused3<416, 2, 2>(ctx, A); break;  // 5 x 820 fills 832 slots: next round's sweep
         default: rc = launch_fused3<480, 2, 2>(ctx, A); break;  // generation 3, 15 consumer warps (measured best)
     }
     if (rc) return rc;
