@@ -5,7 +5,8 @@ __graft_entry__.smoke() and bench.py's CPU legs may import it; the product never
 PARITY STATUS
   * sampling: PINNED against the reference's own headers for everything but the random stream -- Random/Distribution.h,
     NormalDistribution.h, Utility.h (NewtonRaphson), InverseTransformSampling.h (constructor = rank counts + CDF bounds,
-    generate / fill_random) and Randn.h are compiled in place from /root/reference with replayed random numbers
+    generate / fill_random), Randn.h and the managers' own CustomDistributionFunctions structs (cut out of
+    demos/alpine/*Manager.h at build time) are compiled in place from /root/reference with replayed random numbers
     (oracle/ref_shim/refshim_random.cpp -> oracle/_ref/libippl_refshim_random.so) and compared live and through the
     committed fixture tests/golden/ref_random.npz (tests/test_oracle_random_pinned.py).  The STREAM itself is "parity
     unpinned" by nature: the reference draws from Kokkos::Random_XorShift64_Pool, whose stream assignment is per thread /

@@ -1,0 +1,48 @@
+"""TEST INFRASTRUCTURE.  Cuts small pieces of source out of the reference's alpine manager headers -- which cannot be
+included, they pull in the whole framework -- so that the shims can compile the reference's OWN text in place:
+  * the bodies of the Kokkos lambdas "Kick1" / "Kick2" of demos/alpine/PenningTrapManager.h
+      -> penning_kick{1,2}.inc            (oracle/ref_shim/refshim_penning.cpp)
+  * struct CustomDistributionFunctions of LandauDampingManager.h and BumponTailInstabilityManager.h
+      -> landau_dist.inc, bumpontail_dist.inc   (oracle/ref_shim/refshim_random.cpp)
+The outputs are build products under oracle/_ref (git-ignored), never committed.
+usage: python gen_penning.py <reference root> <output dir>"""
+import os
+import sys
+
+
+def lambda_body(lines, name):
+    start = next(i for i, l in enumerate(lines) if f'"{name}"' in l and "KOKKOS_LAMBDA" in l)
+    body = []
+    for l in lines[start + 1:]:
+        if l.strip() == "});":
+            return body
+        body.append(l)
+    raise RuntimeError(f"end of lambda {name} not found")
+
+
+def struct_text(lines, name):
+    start = next(i for i, l in enumerate(lines) if l.startswith(f"struct {name} {{"))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i] == "};")
+    return lines[start:end + 1]
+
+
+def main():
+    ref, out = sys.argv[1], sys.argv[2]
+    os.makedirs(out, exist_ok=True)
+    for app, inc in (("LandauDampingManager.h", "landau_dist.inc"), ("BumponTailInstabilityManager.h", "bumpontail_dist.inc")):
+        src = open(os.path.join(ref, "demos", "alpine", app)).read().splitlines()
+        text = struct_text(src, "CustomDistributionFunctions")
+        assert 15 <= len(text) <= 45 and any("struct CDF" in l for l in text), (app, len(text))
+        with open(os.path.join(out, inc), "w") as f:
+            f.write("\n".join(text) + "\n")
+    lines = open(os.path.join(ref, "demos", "alpine", "PenningTrapManager.h")).read().splitlines()
+    os.makedirs(out, exist_ok=True)
+    for k in (1, 2):
+        body = lambda_body(lines, f"Kick{k}")
+        assert 10 <= len(body) <= 30 and any("Bext" in l for l in body), (k, len(body))
+        with open(os.path.join(out, f"penning_kick{k}.inc"), "w") as f:
+            f.write("\n".join(body) + "\n")
+
+
+if __name__ == "__main__":
+    main()

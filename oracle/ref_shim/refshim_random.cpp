@@ -9,9 +9,9 @@
 //   Random/Randn.h                randn::operator()
 // The uniform / normal draws are REPLAYED from caller-supplied arrays (Kokkos_Random.hpp stand-in): what is compared
 // with the restatement is the reference's arithmetic on identical random numbers.  The alpine managers' custom
-// distribution functors live in demos/alpine/*Manager.h, which cannot be included (they pull in the whole framework);
-// `CosineFunctions` below repeats those three one-line functors (LandauDampingManager.h:21-44) so that the reference's
-// Distribution / NewtonRaphson / fill_random machinery is exercised with them.
+// distribution functors live in demos/alpine/*Manager.h, which cannot be included (they pull in the whole framework):
+// struct CustomDistributionFunctions of LandauDampingManager.h (:21-44) and of BumponTailInstabilityManager.h (:23-52)
+// are cut out of those files at build time and compiled here unchanged.
 #include <Kokkos_Core.hpp>
 #include <Kokkos_Random.hpp>
 
@@ -50,24 +50,18 @@ namespace ippl {
 #include "Random/Randn.h"
 #include "Random/UniformDistribution.h"
 
+// the managers' own functor structs, cut out of the reference files at build time (gen_penning.py -> oracle/_ref/*.inc)
+namespace ref_landau {
+#include "landau_dist.inc"
+}
+namespace ref_bumpontail {
+constexpr unsigned Dim = 3;   // the driver-level constant the struct refers to (demos/alpine/BumponTailInstability.cpp)
+#include "bumpontail_dist.inc"
+}
+
 namespace {
-    struct CosineFunctions {   // == CustomDistributionFunctions of demos/alpine/LandauDampingManager.h:21-44
-        struct CDF {
-            KOKKOS_INLINE_FUNCTION double operator()(double x, unsigned int d, const double* params_p) const {
-                return x + (params_p[d * 2 + 0] / params_p[d * 2 + 1]) * Kokkos::sin(params_p[d * 2 + 1] * x);
-            }
-        };
-        struct PDF {
-            KOKKOS_INLINE_FUNCTION double operator()(double x, unsigned int d, double const* params_p) const {
-                return 1.0 + params_p[d * 2 + 0] * Kokkos::cos(params_p[d * 2 + 1] * x);
-            }
-        };
-        struct Estimate {
-            KOKKOS_INLINE_FUNCTION double operator()(double u, unsigned int d, double const* params_p) const {
-                return u + params_p[d] * 0.;
-            }
-        };
-    };
+    using CosineFunctions = ref_landau::CustomDistributionFunctions;
+    using BumpDist        = ippl::random::Distribution<double, 3, 6, ref_bumpontail::CustomDistributionFunctions>;
     using CosDist  = ippl::random::Distribution<double, 3, 6, CosineFunctions>;
     using NormDist = ippl::random::NormalDistribution<double, 3>;
 
@@ -134,8 +128,13 @@ namespace {
 
 extern "C" {
 
-// kind 1: cosine functors, kind 2: NormalDistribution.  which: 0 cdf, 1 pdf, 2 estimate, 3 objective(x, u = aux), 4 d objective
+// kind 1: LandauDamping's functors, 2: NormalDistribution (PenningTrap), 3: BumponTail's functors.  which: 0 cdf, 1 pdf, 2 estimate, 3 objective(x, u = aux), 4 d objective
 double refrand_eval(int kind, const double* par, int which, int d, double x, double aux) {
+    if (kind == 3) {
+        BumpDist D(par);
+        switch (which) { case 0: return D.getCdf(x, d); case 1: return D.getPdf(x, d); case 2: return D.getEstimate(x, d);
+                         case 3: return D.getObjFunc(x, d, aux); default: return D.getDerObjFunc(x, d); }
+    }
     if (kind == 2) {
         NormDist D(par);
         switch (which) { case 0: return D.getCdf(x, d); case 1: return D.getPdf(x, d); case 2: return D.getEstimate(x, d);
@@ -150,6 +149,7 @@ double refrand_full_pdf(int kind, const double* par, const double x[3]) {
     ippl::Vector<double, 3> v;
     for (int d = 0; d < 3; ++d) v[d] = x[d];
     if (kind == 2) { NormDist D(par); return D.getFullPdf(v); }
+    if (kind == 3) { BumpDist D(par); return D.getFullPdf(v); }
     CosDist D(par);
     return D.getFullPdf(v);
 }
@@ -158,6 +158,7 @@ double refrand_full_pdf(int kind, const double* par, const double x[3]) {
 double refrand_newton(int kind, const double* par, int d, double x0, double u) {
     double x = x0;
     if (kind == 2) { NormDist D(par); ippl::random::detail::NewtonRaphson<double, NormDist> s(D); s.solve(d, x, u); return x; }
+    if (kind == 3) { BumpDist D(par); ippl::random::detail::NewtonRaphson<double, BumpDist> s(D); s.solve(d, x, u); return x; }
     CosDist D(par);
     ippl::random::detail::NewtonRaphson<double, CosDist> s(D);
     s.solve(d, x, u);
@@ -169,6 +170,7 @@ double refrand_newton(int kind, const double* par, int d, double x0, double u) {
 void refrand_sampling(int kind, const double* par, const double* rmin, const double* rmax, const double* regions, int nranks,
                       long ntotal, long* nlocal_out, double* ubounds_out, int gen_rank, const double* u01, double* out) {
     if (kind == 2) { NormDist D(par); run_sampling(D, rmin, rmax, regions, nranks, ntotal, nlocal_out, ubounds_out, gen_rank, u01, out); return; }
+    if (kind == 3) { BumpDist D(par); run_sampling(D, rmin, rmax, regions, nranks, ntotal, nlocal_out, ubounds_out, gen_rank, u01, out); return; }
     CosDist D(par);
     run_sampling(D, rmin, rmax, regions, nranks, ntotal, nlocal_out, ubounds_out, gen_rank, u01, out);
 }

@@ -270,3 +270,34 @@ def orb_scatter_r(ng, origin, h, x, y, z):
     out = np.zeros((ng[0] + 2) * (ng[1] + 2) * (ng[2] + 2))
     olib().reforb_scatterR(_i3(ng), _d3(origin), _d3(h), C.c_long(len(x)), _p(x), _p(y), _p(z), _p(out))
     return out
+
+
+# ---- the reference's PenningTrap kicks (oracle/_ref/libippl_refshim_penning.so, ref_shim/refshim_penning.cpp) ------------
+_PLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_penning.so")
+_plib = None
+
+
+def penning_available(try_build=True):
+    if os.path.exists(_PLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_PLIB_PATH)
+    return False
+
+
+def penning_kick(which, R, P, E, origin, length, V0, alpha, Bext, DrInv):
+    """the "Kick1" / "Kick2" lambda bodies of demos/alpine/PenningTrapManager.h over n particles; R, P, E lists of three
+    arrays; returns the new P as three arrays"""
+    global _plib
+    if _plib is None:
+        if not penning_available():
+            raise RuntimeError("reference Penning shim not built (needs /root/reference)")
+        _plib = C.CDLL(_PLIB_PATH)
+    Ra, Pa, Ea = (np.ascontiguousarray(np.stack(a, axis=1), dtype=np.float64) for a in (R, P, E))
+    _plib.refpenning_kick(int(which), C.c_long(Ra.shape[0]), _p(Ra), _p(Pa), _p(Ea), _d3(origin), _d3(length), C.c_double(V0),
+                          C.c_double(alpha), C.c_double(Bext), C.c_double(DrInv))
+    return [np.ascontiguousarray(Pa[:, d]) for d in range(3)]

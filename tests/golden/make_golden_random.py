@@ -1,5 +1,6 @@
 """Generates tests/golden/ref_random.npz from the REAL reference headers of the sampling path (Random/Distribution.h,
-NormalDistribution.h, Utility.h NewtonRaphson, InverseTransformSampling.h, Randn.h) through oracle/_ref/
+NormalDistribution.h, Utility.h NewtonRaphson, InverseTransformSampling.h, Randn.h, and the managers' own
+CustomDistributionFunctions structs cut out of demos/alpine/*Manager.h at build time) through oracle/_ref/
 libippl_refshim_random.so, with the random numbers REPLAYED from the arrays stored next to the results.  Run here (the
 container that has /root/reference):
     python tests/golden/make_golden_random.py
@@ -18,6 +19,7 @@ CASES = {
     # name: (kind of the shim, kinds of the restatement, par, rmin, rmax)
     "landau": (1, [1, 1, 1], [0.05, 0.5] * 3, [0.0] * 3, [4 * math.pi] * 3),
     "penning": (2, [2, 2, 2], [10.0, 3.0, 10.0, 1.0, 10.0, 4.0], [0.0] * 3, [20.0] * 3),
+    "bumpontail": (3, [0, 0, 1], [0.01, 0.21] * 3, [0.0] * 3, [2 * math.pi / 0.21] * 3),
 }
 
 

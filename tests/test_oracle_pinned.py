@@ -159,3 +159,25 @@ def test_rank_regions_vs_reference_code():
     L.set_boxes(boxes)
     assert np.array_equal(L.regions(origin, h), want)
     L.close()
+
+
+def test_penning_kicks_vs_reference_expressions():
+    """PenningTrap Kick1 / Kick2 (demos/alpine/PenningTrapManager.h:256-272, 313-333): the lambda bodies are cut out of the
+    reference file at build time and compiled unchanged (oracle/ref_shim/gen_penning.py, refshim_penning.cpp); the
+    restatement gives the same momenta bit for bit -- live and through tests/golden/ref_penning.npz.  (The CUDA kicks are
+    held bit-exact to the restatement by tests/test_gpu_parity.py.)"""
+    import os
+    from oracle import refshim
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "ref_penning.npz"))
+    L, dt = float(g["L"][0]), float(g["dt"][0])
+    pp = oracle.penning_params((0.0, 0.0, 0.0), (L, L, L), dt, 5.0)
+    R, E = [a.copy() for a in g["R"]], [a.copy() for a in g["E"]]
+    for which in (1, 2):
+        P = [a.copy() for a in g["P"]]
+        oracle.penning_kick(which, pp, R, P, E)
+        assert np.array_equal(np.stack(P), g[f"kick{which}"]), which
+        if refshim.penning_available():
+            live = refshim.penning_kick(which, R, [a.copy() for a in g["P"]], E, (0, 0, 0), (L, L, L), pp.V0, pp.alpha,
+                                        pp.Bext, pp.DrInv)
+            assert np.array_equal(np.stack(live), g[f"kick{which}"])

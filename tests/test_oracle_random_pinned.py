@@ -2,7 +2,8 @@
 headers of the sampling path: live through oracle/_ref/libippl_refshim_random.so where /root/reference exists, and
 everywhere against tests/golden/ref_random.npz (the committed outputs of those headers, tests/golden/
 make_golden_random.py).  Random numbers are replayed, so what is compared is the reference's arithmetic: distribution
-functions, getFullPdf, NewtonRaphson::solve, the InverseTransformSampling constructor (rank counts + CDF bounds),
+functions (the managers' own CustomDistributionFunctions structs, cut out of demos/alpine/*Manager.h at build time, and
+NormalDistribution), getFullPdf, NewtonRaphson::solve, the InverseTransformSampling constructor (rank counts + CDF bounds),
 generate() / fill_random, randn."""
 import math
 import os
@@ -16,8 +17,8 @@ from oracle import extras as ox
 from oracle import refshim
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = ("landau", "penning")
-SHIM_KIND = {"landau": 1, "penning": 2}
+NAMES = ("landau", "penning", "bumpontail")
+SHIM_KIND = {"landau": 1, "penning": 2, "bumpontail": 3}
 NG = (32, 32, 32)
 
 
@@ -52,7 +53,8 @@ def test_distribution_functions_vs_reference(gold, name):
 def test_rank_counts_and_bounds_vs_reference(gold, name, nranks):
     """InverseTransformSampling's constructor: the restatement AND the product's ipplb_sample_counts, exactly"""
     od, bd, par = _dist(gold, name)
-    rmin, rmax = ([0.0] * 3, [4 * math.pi] * 3) if name == "landau" else ([0.0] * 3, [20.0] * 3)
+    rmin = [0.0] * 3
+    rmax = {"landau": [4 * math.pi] * 3, "penning": [20.0] * 3, "bumpontail": [2 * math.pi / 0.21] * 3}[name]
     h = [(rmax[d] - rmin[d]) / NG[d] for d in range(3)]
     regs = oracle.regions(NG, oracle.partition(NG, nranks), rmin, h)
     for ntotal in (1 << 20, 10_000_000, 12345):
