@@ -258,10 +258,10 @@ def update(ng, boxes, origin, h, parts):
 # the stand-in for heFFTe/FFTW here.  rho_int: (nz, ny, nx) interior array (x fastest).
 # Returns E interior as (nz, ny, nx, 3).
 # ----------------------------------------------------------------------------------------------
-def poisson_grad(rho_int, origin, h):
-    nz, ny, nx = rho_int.shape
-    N = (nx, ny, nz)
-    rhat = np.fft.fftn(rho_int) / (nx * ny * nz)
+def poisson_kspace_multipliers(N, origin, h):
+    """The three k-space multipliers -(i k_gd / |k|^2) of FFTPeriodicPoissonSolver::solve, GRAD output
+    (src/PoissonSolvers/FFTPeriodicPoissonSolver.hpp:115-150: shift, Nyquist ("notMid") rule, k = 0 guard), arrays
+    [nz][ny][nx] for N = (nx, ny, nz)."""
     k = []
     for d in range(3):
         rmax = origin[d] + N[d] * h[d]
@@ -276,9 +276,15 @@ def poisson_grad(rho_int, origin, h):
     Dr = KX * KX + KY * KY + KZ * KZ
     nz_ = Dr != 0.0
     factor = nz_ * (1.0 / (Dr + (~nz_) * 1.0))
+    return [-(1j * K * factor) for K in (KX, KY, KZ)]
+
+
+def poisson_grad(rho_int, origin, h):
+    nz, ny, nx = rho_int.shape
+    rhat = np.fft.fftn(rho_int) / (nx * ny * nz)
     E = np.empty((nz, ny, nx, 3))
-    for gd, K in enumerate((KX, KY, KZ)):
-        tmp = rhat * (-(1j * K * factor))
+    for gd, M in enumerate(poisson_kspace_multipliers((nx, ny, nz), origin, h)):
+        tmp = rhat * M
         E[..., gd] = np.real(np.fft.ifftn(tmp)) * (nx * ny * nz)
     return E
 

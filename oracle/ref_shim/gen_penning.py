@@ -4,6 +4,8 @@ included, they pull in the whole framework -- so that the shims can compile the 
       -> penning_kick{1,2}.inc            (oracle/ref_shim/refshim_penning.cpp)
   * struct CustomDistributionFunctions of LandauDampingManager.h and BumponTailInstabilityManager.h
       -> landau_dist.inc, bumpontail_dist.inc   (oracle/ref_shim/refshim_random.cpp)
+  * the body of the k-space lambda "Gradient FFTPeriodicPoissonSolver" of src/PoissonSolvers/
+    FFTPeriodicPoissonSolver.hpp (the solver header needs heFFTe) -> poisson_grad_lambda.inc (refshim_poisson.cpp)
 The outputs are build products under oracle/_ref (git-ignored), never committed.
 usage: python gen_penning.py <reference root> <output dir>"""
 import os
@@ -29,6 +31,17 @@ def struct_text(lines, name):
 def main():
     ref, out = sys.argv[1], sys.argv[2]
     os.makedirs(out, exist_ok=True)
+    hpp = open(os.path.join(ref, "src", "PoissonSolvers", "FFTPeriodicPoissonSolver.hpp")).read().splitlines()
+    start = next(i for i, l in enumerate(hpp) if '"Gradient FFTPeriodicPoissonSolver"' in l)
+    assert "KOKKOS_LAMBDA" in hpp[start + 1]
+    body = []
+    for l in hpp[start + 2:]:
+        if l.strip() == "});":
+            break
+        body.append(l)
+    assert 20 <= len(body) <= 45 and any("notMid" in l for l in body), len(body)
+    with open(os.path.join(out, "poisson_grad_lambda.inc"), "w") as f:
+        f.write("\n".join(body) + "\n")
     for app, inc in (("LandauDampingManager.h", "landau_dist.inc"), ("BumponTailInstabilityManager.h", "bumpontail_dist.inc")):
         src = open(os.path.join(ref, "demos", "alpine", app)).read().splitlines()
         text = struct_text(src, "CustomDistributionFunctions")

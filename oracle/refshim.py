@@ -301,3 +301,34 @@ def penning_kick(which, R, P, E, origin, length, V0, alpha, Bext, DrInv):
     _plib.refpenning_kick(int(which), C.c_long(Ra.shape[0]), _p(Ra), _p(Pa), _p(Ea), _d3(origin), _d3(length), C.c_double(V0),
                           C.c_double(alpha), C.c_double(Bext), C.c_double(DrInv))
     return [np.ascontiguousarray(Pa[:, d]) for d in range(3)]
+
+
+# ---- the reference's k-space gradient step (oracle/_ref/libippl_refshim_poisson.so, ref_shim/refshim_poisson.cpp) --------
+_KLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_poisson.so")
+_klib = None
+
+
+def poisson_available(try_build=True):
+    if os.path.exists(_KLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_KLIB_PATH)
+    return False
+
+
+def poisson_grad_kspace(spec, origin, h, gd):
+    """the lambda "Gradient FFTPeriodicPoissonSolver" applied to every index of the complex array spec[nz][ny][nx]"""
+    global _klib
+    if _klib is None:
+        if not poisson_available():
+            raise RuntimeError("reference Poisson shim not built (needs /root/reference)")
+        _klib = C.CDLL(_KLIB_PATH)
+    spec = np.ascontiguousarray(spec, dtype=np.complex128)
+    nz, ny, nx = spec.shape
+    out = np.zeros_like(spec)
+    _klib.refpoisson_grad_kspace(_i3((nx, ny, nz)), _d3(origin), _d3(h), int(gd), _p(spec), _p(out))
+    return out

@@ -181,3 +181,26 @@ def test_penning_kicks_vs_reference_expressions():
             live = refshim.penning_kick(which, R, [a.copy() for a in g["P"]], E, (0, 0, 0), (L, L, L), pp.V0, pp.alpha,
                                         pp.Bext, pp.DrInv)
             assert np.array_equal(np.stack(live), g[f"kick{which}"])
+
+
+def test_poisson_kspace_step_vs_reference_lambda():
+    """The k-space step of the periodic Poisson solve with gradient output -- wave numbers with the shift and the Nyquist
+    rule, 1/|k|^2 with the k = 0 guard, multiplication by -(i k_gd factor) -- executed by the reference's own lambda
+    (FFTPeriodicPoissonSolver.hpp:115-150, cut out at build time: oracle/ref_shim/refshim_poisson.cpp) against the
+    multipliers the oracle's poisson_grad uses: bit for bit, even and odd extents.  (The FFTs around it are numpy's here,
+    heFFTe's in the reference, cuFFT's in the product: that part is checked numerically, not pinned.)"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_poisson import CASES
+    from oracle import refshim
+    g = np.load(os.path.join(root, "tests", "golden", "ref_poisson.npz"))
+    for i, (ng, origin, h) in enumerate(CASES):
+        spec = g[f"spec_{i}"]
+        for gd, M in enumerate(oracle.poisson_kspace_multipliers(ng, origin, h)):
+            got = spec * M
+            assert np.array_equal(got.view(np.float64), g[f"grad_{i}_{gd}"].view(np.float64)), (ng, gd)
+            if refshim.poisson_available():
+                live = refshim.poisson_grad_kspace(spec, origin, h, gd)
+                assert np.array_equal(live.view(np.float64), g[f"grad_{i}_{gd}"].view(np.float64))
