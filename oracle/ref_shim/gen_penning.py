@@ -4,6 +4,8 @@ included, they pull in the whole framework -- so that the shims can compile the 
       -> penning_kick{1,2}.inc            (oracle/ref_shim/refshim_penning.cpp)
   * struct CustomDistributionFunctions of LandauDampingManager.h and BumponTailInstabilityManager.h
       -> landau_dist.inc, bumpontail_dist.inc   (oracle/ref_shim/refshim_random.cpp)
+  * the bodies of the lambdas "ParticleAttrib::scatter" and "ParticleAttrib::gather" of src/Particle/ParticleAttrib.hpp
+    (the header needs the whole particle framework) -> attrib_scatter.inc, attrib_gather.inc (refshim_attrib.cpp)
   * the body of the k-space lambda "Gradient FFTPeriodicPoissonSolver" of src/PoissonSolvers/
     FFTPeriodicPoissonSolver.hpp (the solver header needs heFFTe) -> poisson_grad_lambda.inc (refshim_poisson.cpp)
 The outputs are build products under oracle/_ref (git-ignored), never committed.
@@ -31,6 +33,19 @@ def struct_text(lines, name):
 def main():
     ref, out = sys.argv[1], sys.argv[2]
     os.makedirs(out, exist_ok=True)
+    pa = open(os.path.join(ref, "src", "Particle", "ParticleAttrib.hpp")).read().splitlines()
+    for name, inc in (("ParticleAttrib::scatter", "attrib_scatter.inc"), ("ParticleAttrib::gather", "attrib_gather.inc")):
+        start = next(i for i, l in enumerate(pa) if f'"{name}"' in l)
+        while "KOKKOS_LAMBDA" not in pa[start]:
+            start += 1
+        body = []
+        for l in pa[start + 1:]:
+            if l.strip() == "});":
+                break
+            body.append(l)
+        assert 8 <= len(body) <= 25 and any("invdx" in l for l in body), (name, len(body))
+        with open(os.path.join(out, inc), "w") as f:
+            f.write("\n".join(body) + "\n")
     hpp = open(os.path.join(ref, "src", "PoissonSolvers", "FFTPeriodicPoissonSolver.hpp")).read().splitlines()
     start = next(i for i, l in enumerate(hpp) if '"Gradient FFTPeriodicPoissonSolver"' in l)
     assert "KOKKOS_LAMBDA" in hpp[start + 1]

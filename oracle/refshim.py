@@ -332,3 +332,50 @@ def poisson_grad_kspace(spec, origin, h, gd):
     out = np.zeros_like(spec)
     _klib.refpoisson_grad_kspace(_i3((nx, ny, nz)), _d3(origin), _d3(h), int(gd), _p(spec), _p(out))
     return out
+
+
+# ---- ParticleAttrib::scatter / ::gather lambda bodies (oracle/_ref/libippl_refshim_attrib.so, ref_shim/refshim_attrib.cpp)
+_ALIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_attrib.so")
+_alib = None
+
+
+def attrib_available(try_build=True):
+    if os.path.exists(_ALIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_ALIB_PATH)
+    return False
+
+
+def _alib_get():
+    global _alib
+    if _alib is None:
+        if not attrib_available():
+            raise RuntimeError("reference attribute shim not built (needs /root/reference)")
+        _alib = C.CDLL(_ALIB_PATH)
+    return _alib
+
+
+def attrib_scatter(mesh, x, y, z, q, rho, begin=0, end=None, hash=None):
+    """the body of the "ParticleAttrib::scatter" lambda over particles [begin, end), optional hash remap; rho += in place"""
+    R = np.ascontiguousarray(np.stack([x, y, z], axis=1), dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    end = len(x) if end is None else end
+    hv = None if hash is None else np.ascontiguousarray(hash, dtype=np.int32)
+    _alib_get().refattrib_scatter(C.c_long(begin), C.c_long(end), _p(R), _p(q), _p(hv) if hv is not None else None,
+                                  C.c_long(0 if hv is None else len(hv)), _d3(mesh.origin), _d3(mesh.h), _i3(mesh.first),
+                                  mesh.nghost, _i3(mesh.ext), _p(rho))
+    return rho
+
+
+def attrib_gather(mesh, x, y, z, efield, E, add=False):
+    """the body of the "ParticleAttrib::gather" lambda for a Vector<double,3> field; E = list of three arrays (in / out)"""
+    R = np.ascontiguousarray(np.stack([x, y, z], axis=1), dtype=np.float64)
+    Ea = np.ascontiguousarray(np.stack(E, axis=1), dtype=np.float64)
+    _alib_get().refattrib_gather(C.c_long(len(x)), _p(R), _d3(mesh.origin), _d3(mesh.h), _i3(mesh.first), mesh.nghost,
+                                 _i3(mesh.ext), _p(np.ascontiguousarray(efield, dtype=np.float64)), int(add), _p(Ea))
+    return [np.ascontiguousarray(Ea[:, d]) for d in range(3)]

@@ -204,3 +204,35 @@ def test_poisson_kspace_step_vs_reference_lambda():
             if refshim.poisson_available():
                 live = refshim.poisson_grad_kspace(spec, origin, h, gd)
                 assert np.array_equal(live.view(np.float64), g[f"grad_{i}_{gd}"].view(np.float64))
+
+
+def test_scatter_gather_kernels_vs_reference_lambdas():
+    """ParticleAttrib::scatter / ::gather executed by the reference's own lambda bodies (ParticleAttrib.hpp:167-184,
+    229-244, cut out at build time, on the reference's Interpolation/CIC.h: oracle/ref_shim/refshim_attrib.cpp): scatter of
+    a per-particle charge, plain and through a hash remap over a sub-range; gather of a Vector<double,3> field, replace
+    and add; full box and sub-box with offset; particles on box corners, cell faces and cell centres.  The serial
+    restatement visits particles and stencil points in the same order: bit for bit."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_attrib import BOXES, H, NG, ORIGIN
+    from oracle import refshim
+    g = np.load(os.path.join(root, "tests", "golden", "ref_attrib.npz"))
+    for bi, (first, nl) in enumerate(BOXES):
+        m = oracle.Mesh.make(NG, ORIGIN, H, first=first, nl=nl)
+        R, q, hashv, ef = [a.copy() for a in g[f"R_{bi}"]], g[f"q_{bi}"].copy(), g[f"hash_{bi}"].copy(), g[f"ef_{bi}"].copy()
+        rho = oracle.field_zeros(m)
+        oracle.scatter_cic(m, *R, q, rho)
+        assert np.array_equal(rho, g[f"scatter_{bi}"])
+        rho = oracle.field_zeros(m)
+        oracle.scatter_cic(m, *R, q, rho, begin=100, end=1700, hash=hashv)
+        assert np.array_equal(rho, g[f"scatter_hash_{bi}"])
+        for add, key in ((False, "gather"), (True, "gather_add")):
+            E = [a.copy() for a in g[f"E0_{bi}"]]
+            oracle.gather_cic(m, *R, ef, E, add=add)
+            assert np.array_equal(np.stack(E), g[f"{key}_{bi}"]), (bi, key)
+        if refshim.attrib_available():
+            assert np.array_equal(refshim.attrib_scatter(m, *R, q, oracle.field_zeros(m)), g[f"scatter_{bi}"])
+            live = refshim.attrib_gather(m, *R, ef, [a.copy() for a in g[f"E0_{bi}"]], add=True)
+            assert np.array_equal(np.stack(live), g[f"gather_add_{bi}"])
