@@ -4,6 +4,9 @@ included, they pull in the whole framework -- so that the shims can compile the 
       -> penning_kick{1,2}.inc            (oracle/ref_shim/refshim_penning.cpp)
   * struct CustomDistributionFunctions of LandauDampingManager.h and BumponTailInstabilityManager.h
       -> landau_dist.inc, bumpontail_dist.inc   (oracle/ref_shim/refshim_random.cpp)
+  * from src/Particle/ParticleSpatialLayout.hpp: the return statements of positionInRegion / positionInRegionInclusive
+    and the body of the destRankOf lambda of locateParticlesPacked -> psl_in_region.inc, psl_in_region_inclusive.inc,
+    psl_dest_rank.inc (refshim_locate.cpp)
   * the bodies of the lambdas "ParticleAttrib::scatter" and "ParticleAttrib::gather" of src/Particle/ParticleAttrib.hpp
     (the header needs the whole particle framework) -> attrib_scatter.inc, attrib_gather.inc (refshim_attrib.cpp)
   * the body of the k-space lambda "Gradient FFTPeriodicPoissonSolver" of src/PoissonSolvers/
@@ -33,6 +36,23 @@ def struct_text(lines, name):
 def main():
     ref, out = sys.argv[1], sys.argv[2]
     os.makedirs(out, exist_ok=True)
+    psl = open(os.path.join(ref, "src", "Particle", "ParticleSpatialLayout.hpp")).read().splitlines()
+    for fn, inc in (("positionInRegionInclusive(", "psl_in_region_inclusive.inc"), ("positionInRegion(", "psl_in_region.inc")):
+        # the out-of-class definition: "ParticleSpatialLayout<...>::<fn>" followed by its single return statement
+        start = next(i for i, l in enumerate(psl) if l.strip().startswith("ParticleSpatialLayout<") and l.strip().endswith("::" + fn))
+        ret = next(i for i in range(start, start + 6) if psl[i].strip().startswith("return "))
+        assert psl[ret].strip().endswith(";"), psl[ret]
+        with open(os.path.join(out, inc), "w") as f:
+            f.write(psl[ret] + "\n")
+    start = next(i for i, l in enumerate(psl) if "auto destRankOf = KOKKOS_LAMBDA" in l)
+    body = []
+    for l in psl[start + 1:]:
+        if l.rstrip() == "        };":
+            break
+        body.append(l)
+    assert 15 <= len(body) <= 35 and any("positionInRegionInclusive" in l for l in body), len(body)
+    with open(os.path.join(out, "psl_dest_rank.inc"), "w") as f:
+        f.write("\n".join(body) + "\n")
     pa = open(os.path.join(ref, "src", "Particle", "ParticleAttrib.hpp")).read().splitlines()
     for name, inc in (("ParticleAttrib::scatter", "attrib_scatter.inc"), ("ParticleAttrib::gather", "attrib_gather.inc")):
         start = next(i for i, l in enumerate(pa) if f'"{name}"' in l)

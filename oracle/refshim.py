@@ -379,3 +379,37 @@ def attrib_gather(mesh, x, y, z, efield, E, add=False):
     _alib_get().refattrib_gather(C.c_long(len(x)), _p(R), _d3(mesh.origin), _d3(mesh.h), _i3(mesh.first), mesh.nghost,
                                  _i3(mesh.ext), _p(np.ascontiguousarray(efield, dtype=np.float64)), int(add), _p(Ea))
     return [np.ascontiguousarray(Ea[:, d]) for d in range(3)]
+
+
+# ---- particle ownership (oracle/_ref/libippl_refshim_locate.so, ref_shim/refshim_locate.cpp) ------------------------------
+_LLIB_PATH = os.path.join(_HERE, "_ref", "libippl_refshim_locate.so")
+_llib = None
+
+
+def locate_available(try_build=True):
+    if os.path.exists(_LLIB_PATH):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        except Exception:
+            return False
+        return os.path.exists(_LLIB_PATH)
+    return False
+
+
+def dest_rank(regions, my, x, y, z, neighbours=None):
+    """the destRankOf lambda of ParticleSpatialLayout::locateParticlesPacked for rank `my`: regions[nranks][6]; neighbours =
+    the cached neighbour ranks searched before the global scan (default: every other rank)"""
+    global _llib
+    if _llib is None:
+        if not locate_available():
+            raise RuntimeError("reference ownership shim not built (needs /root/reference)")
+        _llib = C.CDLL(_LLIB_PATH)
+    reg = np.ascontiguousarray(regions, dtype=np.float64)
+    nr = reg.shape[0]
+    nb = np.ascontiguousarray([r for r in range(nr) if r != my] if neighbours is None else neighbours, dtype=np.int32)
+    R = np.ascontiguousarray(np.stack([x, y, z], axis=1), dtype=np.float64)
+    out = np.zeros(R.shape[0], dtype=np.int32)
+    _llib.reflocate_dest_rank(nr, _p(reg), int(my), _p(nb), len(nb), C.c_long(R.shape[0]), _p(R), _p(out))
+    return out

@@ -236,3 +236,28 @@ def test_scatter_gather_kernels_vs_reference_lambdas():
             assert np.array_equal(refshim.attrib_scatter(m, *R, q, oracle.field_zeros(m)), g[f"scatter_{bi}"])
             live = refshim.attrib_gather(m, *R, ef, [a.copy() for a in g[f"E0_{bi}"]], add=True)
             assert np.array_equal(np.stack(live), g[f"gather_add_{bi}"])
+
+
+def test_particle_ownership_vs_reference_lambda():
+    """Which rank owns a particle: the destRankOf lambda of ParticleSpatialLayout::locateParticlesPacked with
+    positionInRegion / positionInRegionInclusive (ParticleSpatialLayout.hpp:316-330, 372-395), cut out of the reference at
+    build time (oracle/ref_shim/refshim_locate.cpp), against the restatement: identical destination for every particle,
+    including particles exactly on region faces, one ulp to either side, on the domain's lower corner (inclusive
+    fallback) and outside every region.  (The CUDA locate / fused-step ownership is held to the restatement, bit-exact,
+    by tests/test_gpu_parity.py and tests/mgpu_check.py.)"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_locate import CASES, H, ORIGIN
+    from oracle import refshim
+    g = np.load(os.path.join(root, "tests", "golden", "ref_locate.npz"))
+    for ci, (ng, nr) in enumerate(CASES):
+        regs = oracle.regions(ng, oracle.partition(ng, nr), ORIGIN, H)
+        R = [a.copy() for a in g[f"R_{ci}"]]
+        for my in range(nr):
+            want = g[f"dest_{ci}_{my}"]
+            assert np.array_equal(oracle.locate(regs, my, *R), want), (ng, nr, my)
+            if refshim.locate_available():
+                # the neighbour list only changes the search order: regions are disjoint, the answer is the same
+                assert np.array_equal(refshim.dest_rank(regs, my, *R, neighbours=[r for r in range(nr) if r != my][::-1]), want)
