@@ -11,8 +11,9 @@ included, they pull in the whole framework -- so that the shims can compile the 
     (the header needs the whole particle framework) -> attrib_scatter.inc, attrib_gather.inc (refshim_attrib.cpp)
   * the body of the k-space lambda "Gradient FFTPeriodicPoissonSolver" of src/PoissonSolvers/
     FFTPeriodicPoissonSolver.hpp (the solver header needs heFFTe) -> poisson_grad_lambda.inc (refshim_poisson.cpp)
-The outputs are build products under oracle/_ref (git-ignored), never committed.
-usage: python gen_penning.py <reference root> <output dir>"""
+The outputs go to the directory given on the command line -- the Makefile passes a temporary directory and removes it
+after the compile: no reference text is left in the tree.
+usage: python gen_snippets.py <reference root> <output dir>"""
 import os
 import sys
 

@@ -1,7 +1,7 @@
 // refshim_attrib.cpp -- TEST INFRASTRUCTURE.  ParticleAttrib::scatter and ::gather as the reference writes them: the
 // bodies of the two Kokkos lambdas (src/Particle/ParticleAttrib.hpp:167-184 and :229-244 -- optional hash remap, position
 // -> l -> index truncation -> whi / wlo -> args, then detail::scatterToField / gatherFromField, replace or add) are cut
-// out of the reference file at build time (gen_penning.py -> oracle/_ref/attrib_{scatter,gather}.inc) and compiled here
+// out of the reference file at build time (gen_snippets.py -> attrib_{scatter,gather}.inc in a temporary include directory) and compiled here
 // unchanged inside a plain loop; the interpolation itself is the reference's Interpolation/CIC.h, included in place.
 // The ParticleAttrib header cannot be included (it needs the whole particle framework).
 #include <Kokkos_Core.hpp>

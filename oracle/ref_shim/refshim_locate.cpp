@@ -1,8 +1,8 @@
 // refshim_locate.cpp -- TEST INFRASTRUCTURE.  Particle ownership as the reference decides it: the destRankOf lambda of
 // ParticleSpatialLayout::locateParticlesPacked (src/Particle/ParticleSpatialLayout.hpp:372-395: own region, cached
 // neighbours, every rank, then the inclusive fallback) and the return statements of positionInRegion /
-// positionInRegionInclusive (:316-330) are cut out of the reference file at build time (gen_penning.py ->
-// oracle/_ref/psl_*.inc) and compiled here unchanged; regions are the reference's NDRegion / PRegion (Region/*.h, included
+// positionInRegionInclusive (:316-330) are cut out of the reference file at build time (gen_snippets.py -> psl_*.inc in a
+// temporary include directory) and compiled here unchanged; regions are the reference's NDRegion / PRegion (Region/*.h, included
 // in place).  The layout header itself cannot be included (it needs the whole particle framework).
 #include <Kokkos_Core.hpp>
 

@@ -1,6 +1,6 @@
 // refshim_penning.cpp -- TEST INFRASTRUCTURE.  The PenningTrap kicks as the reference writes them: the bodies of the
 // "Kick1" / "Kick2" lambdas of demos/alpine/PenningTrapManager.h (:256-272, :313-333) are cut out of the reference file
-// at build time (gen_penning.py -> oracle/_ref/penning_kick{1,2}.inc, git-ignored build products) and compiled here,
+// at build time (gen_snippets.py -> penning_kick{1,2}.inc in a temporary include directory) and compiled here,
 // unchanged, inside a plain loop over the particles.  Views are AoS Vector<double,3>-like: view(j)[d].
 #include <Kokkos_Core.hpp>
 

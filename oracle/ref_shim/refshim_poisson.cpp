@@ -1,7 +1,7 @@
 // refshim_poisson.cpp -- TEST INFRASTRUCTURE.  The k-space step of the reference's periodic Poisson solve with gradient
 // output: the body of the lambda "Gradient FFTPeriodicPoissonSolver" (src/PoissonSolvers/FFTPeriodicPoissonSolver.hpp:
 // 115-150: wave numbers with the shift and the Nyquist ("notMid") rule, 1/|k|^2 with the k = 0 guard, multiplication by
-// -(i k_gd factor)) is cut out of the reference file at build time (gen_penning.py -> oracle/_ref/
+// -(i k_gd factor)) is cut out of the reference file at build time (gen_snippets.py -> oracle/_ref/
 // poisson_grad_lambda.inc) and compiled here unchanged, applied to every index of a complex array.  The solver header
 // itself needs heFFTe and cannot be included; the transforms around this step are not the reference's here.
 #include <Kokkos_Core.hpp>

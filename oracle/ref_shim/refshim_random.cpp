@@ -50,7 +50,7 @@ namespace ippl {
 #include "Random/Randn.h"
 #include "Random/UniformDistribution.h"
 
-// the managers' own functor structs, cut out of the reference files at build time (gen_penning.py -> oracle/_ref/*.inc)
+// the managers' own functor structs, cut out of the reference files at build time (gen_snippets.py -> a temporary include directory)
 namespace ref_landau {
 #include "landau_dist.inc"
 }

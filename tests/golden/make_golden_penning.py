@@ -1,6 +1,6 @@
 """Generates tests/golden/ref_penning.npz: momenta after the reference's own "Kick1" / "Kick2" expressions
 (demos/alpine/PenningTrapManager.h:256-272, 313-333, cut out at build time and compiled in place:
-oracle/ref_shim/gen_penning.py + refshim_penning.cpp).  Run here (the container that has /root/reference):
+oracle/ref_shim/gen_snippets.py + refshim_penning.cpp).  Run here (the container that has /root/reference):
     python tests/golden/make_golden_penning.py"""
 import os
 import sys

@@ -163,7 +163,7 @@ def test_rank_regions_vs_reference_code():
 
 def test_penning_kicks_vs_reference_expressions():
     """PenningTrap Kick1 / Kick2 (demos/alpine/PenningTrapManager.h:256-272, 313-333): the lambda bodies are cut out of the
-    reference file at build time and compiled unchanged (oracle/ref_shim/gen_penning.py, refshim_penning.cpp); the
+    reference file at build time and compiled unchanged (oracle/ref_shim/gen_snippets.py, refshim_penning.cpp); the
     restatement gives the same momenta bit for bit -- live and through tests/golden/ref_penning.npz.  (The CUDA kicks are
     held bit-exact to the restatement by tests/test_gpu_parity.py.)"""
     import os
