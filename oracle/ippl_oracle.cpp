@@ -13,9 +13,9 @@
 // /root/reference).  It is pinned three ways (see tests/test_oracle_*.py):
 //   (1) against the reference's OWN headers for the pure-arithmetic pieces
 //       (CIC.hpp weights/fold order, ParticleBC.h PeriodicBC, Index/NDIndex/
-//       Partitioner/FieldLayout neighbour tables, HaloCells.hpp's in-rank
-//       periodic wrap, RegionLayout's rank regions, the PenningTrap kick
-//       lambdas), compiled from /root/reference with a minimal Kokkos
+//       Partitioner/FieldLayout neighbour tables, HaloCells.hpp's periodic wrap
+//       and multi-rank exchange, RegionLayout's rank regions, ownership, the
+//       scatter / gather and PenningTrap kick lambdas), compiled from /root/reference with a minimal Kokkos
 //       stand-in into oracle/_ref (oracle/ref_shim/, Makefile target `ref`);
 //   (2) against every invariant the reference's unit tests hold for the
 //       path;

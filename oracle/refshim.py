@@ -220,6 +220,23 @@ def halo_available(try_build=True):
     return False
 
 
+def halo_exchange(ng, boxes, fields, ncomp, mode, nghost=1, use_boxes=False):
+    """BareField::fillHalo / accumulateHalo of the reference for EVERY rank at once: HaloCells::exchangeBoundaries (pack,
+    isend / recv over an in-process mailbox, unpack) on one thread per rank, then applyPeriodicSerialDim.  fields[r]:
+    rank r's ghosted array (ncomp doubles per cell), modified in place.  use_boxes: apply `boxes` with
+    FieldLayout::updateLayout (an ORB layout) instead of the default partition."""
+    global _hlib
+    if _hlib is None:
+        if not halo_available():
+            raise RuntimeError("reference halo shim not built (needs /root/reference)")
+        _hlib = C.CDLL(_HLIB_PATH)
+    nr = len(fields)
+    arr = (C.c_void_p * nr)(*[f.ctypes.data for f in fields])
+    b = np.ascontiguousarray(boxes, dtype=np.int32) if use_boxes else None
+    _hlib.refhalo_exchange(_i3(ng), nr, _p(b) if b is not None else None, nghost, ncomp, 0 if mode == "fill" else 1, arr)
+    return fields
+
+
 def halo_periodic(field, ng, mode, nghost=1):
     """HaloCells::applyPeriodicSerialDim<assign | rhs_plus_assign> of the reference, in place, on a ghosted scalar field
     (x fastest) of a single-rank all-periodic layout; mode "fill" or "accumulate"."""

@@ -261,3 +261,33 @@ def test_particle_ownership_vs_reference_lambda():
             if refshim.locate_available():
                 # the neighbour list only changes the search order: regions are disjoint, the answer is the same
                 assert np.array_equal(refshim.dest_rank(regs, my, *R, neighbours=[r for r in range(nr) if r != my][::-1]), want)
+
+
+def test_multi_rank_halo_exchange_vs_reference_code():
+    """BareField::fillHalo / accumulateHalo over several ranks: HaloCells::exchangeBoundaries with pack / unpack
+    (src/Field/HaloCells.hpp:109-285) and then applyPeriodicSerialDim, executed by the reference's own code -- one thread
+    per rank over an in-process mailbox (oracle/ref_shim/refshim_halo.cpp) -- against the restatement's all-ranks
+    simulation (oracle.halo_full): every rank's ghosted field bit for bit, fill and accumulate (cells that receive
+    several contributions are summed in the reference's component order), scalar and Vector<double,3> fields, default
+    partitions on 2 / 3 / 4 / 8 ranks and ORB layouts with unequal boxes.  (The CUDA / NCCL halo is held to the
+    restatement by tests/mgpu_check.py on real GPUs.)"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_halo_exchange import CASES, boxes_of
+    from oracle import refshim
+    g = np.load(os.path.join(root, "tests", "golden", "ref_halo_exchange.npz"))
+    for ci, case in enumerate(CASES):
+        ng, nr, b = case
+        boxes = boxes_of(case)
+        for ncomp in (1, 3):
+            for mode in ("fill", "accumulate"):
+                fields = [g[f"in_{ci}_{ncomp}_{r}"].copy() for r in range(nr)]
+                oracle.halo_full(ng, boxes, fields, ncomp, mode)
+                for r in range(nr):
+                    assert np.array_equal(fields[r], g[f"{mode}_{ci}_{ncomp}_{r}"]), (ng, nr, ncomp, mode, r)
+        if refshim.halo_available():
+            live = refshim.halo_exchange(ng, boxes, [g[f"in_{ci}_1_{r}"].copy() for r in range(nr)], 1, "accumulate",
+                                         use_boxes=b is not None)
+            assert all(np.array_equal(live[r], g[f"accumulate_{ci}_1_{r}"]) for r in range(nr))
