@@ -207,7 +207,7 @@ def main():
     # ---- self-consistent E from one solve (single GPU); synthetic smooth E on N > 1 (solver is non-owned)
     solve_ms = None
     if world == 1:
-        ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho)
+        ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho, end=n_mine)  # only the sampled slots
         ctx.halo_accumulate_periodic(mesh, rho)
         cell = h[0] * h[1] * h[2]
         ctx.field_density(mesh, rho, cell, q * n_total / (Lg[0] * Lg[1] * Lg[2]))
@@ -235,11 +235,14 @@ def main():
     region = list(reg) if world > 1 else None
 
     def step(first=False):
-        fill_e_halo()
         push = ib.leapfrog_push(dt, kick2=0 if first else 1)
         if bins is not None and world == 1:
+            # one rank owns the whole periodic domain: the fused kernel aliases ghost nodes itself, which replaces the
+            # fillHalo(E) / accumulateHalo(rho) passes (HaloCells::applyPeriodicSerialDim)
             ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=2, bins=bins)
-        elif bins is not None:
+            return
+        fill_e_halo()
+        if bins is not None:
             # fused step with ownership test -> NCCL migration (arrivals appended + deposited) -> accumulateHalo
             ctx.field_fill(rho, 0.0)
             bins.step(push, parts, scratch, ef, rho, exit_buf=exit_buf, region=region)

@@ -252,6 +252,10 @@ int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* in
  * Particles that left the rank's region (multi-GPU: reference ownership test, ParticleSpatialLayout.hpp:
  * 316-330) are not deposited: each is appended as one record (x,y,z,px,py,pz) to its destination rank's segment of
  * exit_buf[nranks][exit_cap / nranks][6] (16-byte aligned; one rank: exit_buf[exit_cap][6]).
+ * One rank that owns the WHOLE periodic domain (nl == ng in every dimension, no region test, periodic BC in the push): the
+ * step aliases ghost nodes to the opposite interior layer itself -- what HaloCells::applyPeriodicSerialDim does in two
+ * extra passes (src/Field/HaloCells.hpp:297-336).  efield's ghost layers are then not read (no fillHalo needed) and rho's
+ * ghost layers receive nothing (a chained accumulateHalo adds zeros).
  * Replaces, for one step: ParticleAttrib::operator= x3 (ParticleAttrib.hpp:118-130), applyBC
  * (ParticleLayout.hpp:34-74), gather (:193-246) and scatter (:132-184). */
 int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_push* push, const ipplb_particles* cur,
@@ -357,8 +361,8 @@ int ipplb_orb_repartition(ipplb_ctx* ctx, const ipplb_mesh* mesh, int nranks, co
 /* One PIC step of the metric (scatter + push + gather) on resident particles, single rank:
  *   do_sort 0: gather_push -> rho = 0 -> atomic scatter -> periodic accumulate
  *   do_sort 1: gather_push -> counting sort -> rho = 0 -> sorted scatter -> periodic accumulate
- *   do_sort 2: rho = 0 -> ipplb_bins_step (p must be bucketed by `bins`) -> periodic accumulate;
- *              p and scratch swap.
+ *   do_sort 2: rho = 0 -> ipplb_bins_step with periodic aliasing (p must be bucketed by `bins`; the mesh must be the
+ *              whole periodic domain; efield's halo is not read, rho's ghost layers stay zero); p and scratch swap.
  * The field solve is NOT included (non-owned). */
 int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
                    ipplb_particles* scratch, int* cell_offsets, ipplb_bins* bins, const double* efield,

@@ -20,7 +20,7 @@ struct PlanArgs {
     const int* cap_o;
     int *count_o, *state_o, *start_i, *cap_i, *count_i, *state_i, *misc;
     long long* scratch;  // [PLAN_CTAS][4] partial sums, then [4] barrier words (as long long)
-    const int* exit_cnt;  // leavers per destination rank
+    int* exit_cnt;  // [2][MAX_RANKS]: live counters of the step, snapshot of the last step (for the migration)
     int exit_ranks, seg_cap;
     int capacity, slack_div, slack_sqrt, slack_const, tail_reserve;
 };
@@ -147,14 +147,21 @@ __global__ void __launch_bounds__(PLAN_NT) bins_plan_kernel(const PlanArgs a) {
         a.misc[BM_ST_TOTAL]      = (int)(tot[2] + tc);
         a.misc[BM_ST_BUCKETED]   = (int)tot[2];
         a.misc[BM_ST_TAIL]       = tc;
+        // leavers per destination rank: snapshot for ipplb_bins_migrate, live counters re-armed for the next step
         int nexit = 0;
         for (int r = 0; r < a.exit_ranks; ++r) {
-            nexit += a.exit_cnt[r];
-            if (a.exit_cnt[r] > a.seg_cap) flags |= IPPLB_FLAG_EXIT_OVERFLOW;
+            const int c = a.exit_cnt[r];
+            nexit += c;
+            if (c > a.seg_cap) flags |= IPPLB_FLAG_EXIT_OVERFLOW;
+            a.exit_cnt[MAX_RANKS + r] = c;
+            a.exit_cnt[r]             = 0;
         }
         a.misc[BM_ST_EXIT]       = nexit;
         a.misc[BM_ST_TAIL_START] = a.state_o[BS_TAIL_START];
-        a.misc[BM_ST_FLAGS]      = a.misc[BM_FLAGS] | flags;
+        // error bits are sticky until the next ipplb_bins_build: a status read after K steps sees a drop in any of them
+        a.misc[BM_ST_FLAGS]      = (a.misc[BM_ST_FLAGS] & 7) | a.misc[BM_FLAGS] | flags;
+        // the step's scratch words (work counter, flags) are re-armed here: no memset in front of the next step
+        a.misc[BM_WORK] = 0; a.misc[BM_EXIT] = 0; a.misc[BM_FLAGS] = 0; a.misc[BM_SPARE] = 0;
     }
     // the last CTA to get here resets the barrier words for the next launch
     if (t == 0) {
@@ -309,8 +316,8 @@ int ipplb_bins_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, long capacity, ipp
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cell, sizeof(int) * (size_t)(b->ncells + 1));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_plan, sizeof(long long) * (PLAN_CTAS * 4 + 4));
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_plan, 0, sizeof(long long) * (PLAN_CTAS * 4 + 4), ctx->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_exit_cnt, sizeof(int) * MAX_RANKS);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_exit_cnt, 0, sizeof(int) * MAX_RANKS, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_exit_cnt, sizeof(int) * 2 * MAX_RANKS);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_exit_cnt, 0, sizeof(int) * 2 * MAX_RANKS, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_status, sizeof(int) * (BM_WORDS + MAX_RANKS));
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_tab, 0, sizeof(int) * b->tab_words(), ctx->stream);
     if (e != cudaSuccess) {

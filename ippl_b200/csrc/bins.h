@@ -26,7 +26,7 @@ struct ipplb_bins {
     int* d_tab    = nullptr;  // start[2][nt] cap[2][nt] count[2][nt] state[2][BS_WORDS] misc[BM_WORDS]
     int* d_cell   = nullptr;  // build scratch: per-cell offsets [ncells + 1]
     long long* d_plan = nullptr;  // planning kernel scratch (partial sums + grid barrier words)
-    int* d_exit_cnt = nullptr;    // [MAX_RANKS] leavers per destination rank of the last step
+    int* d_exit_cnt = nullptr;    // [2][MAX_RANKS] leavers per destination rank: live counters, snapshot of the last step
     int exit_ranks  = 1;          // how many of them the last step used
     int* h_status = nullptr;  // pinned [BM_WORDS]
     // slack = total / slack_div + slack_sqrt * sqrt(total) + slack_const  (elements per bucket)

@@ -52,6 +52,18 @@ __device__ __forceinline__ long cic_node(const MeshDev& m, const int a[3], int p
     return i + (long)m.ex * (j + (long)m.ey * k);
 }
 
+// A rank that owns a whole periodic axis: ghost layer g aliases the opposite interior layer (what
+// HaloCells::applyPeriodicSerialDim copies / adds, src/Field/HaloCells.hpp:297-336)
+__device__ __forceinline__ int wrap_axis(int g, int nl, int nghost) {
+    return g < nghost ? g + nl : (g >= nl + nghost ? g - nl : g);
+}
+__device__ __forceinline__ long cic_node_wrapped(const MeshDev& m, const int a[3], int p) {
+    const long i = wrap_axis(a[0] - (p & 1), m.nl[0], m.nghost);
+    const long j = wrap_axis(a[1] - ((p >> 1) & 1), m.nl[1], m.nghost);
+    const long k = wrap_axis(a[2] - ((p >> 2) & 1), m.nl[2], m.nghost);
+    return i + (long)m.ex * (j + (long)m.ey * k);
+}
+
 // Cell key used by the sort: c[d] = index[d] - first[d] in [0, nl[d]] (a particle sitting exactly on
 // the upper region boundary has index == first + nl).  Keys are TILE-MAJOR: the key space is cut into
 // 4x4x4-cell tiles, key = tile_id * 64 + cell_in_tile (x fastest inside the tile and across tiles), so
@@ -82,14 +94,26 @@ __device__ __forceinline__ void key_to_args(const MeshDev& m, int key, int a[3])
     a[2] = tz * TILE + (in >> 4) + m.nghost;
 }
 
-// PeriodicBC::operator(), src/Particle/ParticleBC.h:73-76
-__device__ __forceinline__ double periodic_wrap(double v, double extent, double middle) {
-    const double num = dmul(dsub(v, middle), 2.0);
-    // |num| < extent  =>  |num/extent| < 1 after correct rounding  =>  (int) = 0  =>  v - extent*0 == v:
-    // skip the fp64 division for particles that stay inside (bit-identical result)
-    if (fabs(num) < extent) return v;
-    const double t = __ddiv_rn(num, extent);
+// PeriodicBC::operator(), src/Particle/ParticleBC.h:73-76.  half_extent = extent * 0.5 (exact), formed on the host.
+// The wrap itself (an fp64 division) is out of line: ~1 % of the particles per step cross the domain boundary.
+#ifndef IPPLB_FAR_ATTR
+#define IPPLB_FAR_ATTR __forceinline__
+#endif
+static __device__ IPPLB_FAR_ATTR double periodic_wrap_far(double v, double extent, double off) {
+    const double num = dmul(off, 2.0);
+    const double t   = __ddiv_rn(num, extent);
     return dsub(v, dmul(extent, (double)__double2int_rz(t)));
+}
+__device__ __forceinline__ double periodic_wrap(double v, double extent, double middle, double half_extent) {
+    const double off = dsub(v, middle);
+    // num = off * 2 (exact).  |num| < extent  =>  |num/extent| < 1 after correct rounding  =>  (int) = 0  =>
+    // v - extent*0 == v: skip the fp64 division for particles that stay inside (bit-identical result); the test is
+    // made on off against extent / 2 (both scalings by 2 are exact), which saves a multiply on the fast path
+    if (fabs(off) < half_extent) return v;
+    return periodic_wrap_far(v, extent, off);
+}
+__device__ __forceinline__ double periodic_wrap(double v, double extent, double middle) {
+    return periodic_wrap(v, extent, middle, dmul(extent, 0.5));
 }
 
 }  // namespace ipplb

@@ -526,7 +526,7 @@ int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, cons
     if (nr >= 2) {
         IPPLB_REQUIRE(P && ctx->nccl && exit_buf, "bins_migrate: no layout/communicator/exit buffer bound");
         IPPLB_REQUIRE(b->exit_ranks == nr, "bins_migrate: the last step was not run with this layout");
-        IPPLB_NCCL(ncclAllGather(b->d_exit_cnt, P->d_matrix, nr, ncclInt, (ncclComm_t)ctx->nccl, ctx->stream));
+        IPPLB_NCCL(ncclAllGather(b->d_exit_cnt + MAX_RANKS, P->d_matrix, nr, ncclInt, (ncclComm_t)ctx->nccl, ctx->stream));
         ctx->launches++;
         IPPLB_CUDA(cudaMemcpyAsync(P->h_matrix, P->d_matrix, sizeof(int) * nr * nr, cudaMemcpyDeviceToHost, ctx->stream));
     }

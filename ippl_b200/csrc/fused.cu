@@ -3,18 +3,21 @@
 // Storage: per-tile buckets (tile = 4x4x4 key cells) with slack, double-buffered; device-resident tables
 // start/cap/count per tile, re-planned on the device after every step (bins.cu).
 //
-// Kernel (persistent, 2 CTAs per SM, dynamic tile scheduler):
-//   producer warp : walks (tile, chunk) work items, streams the chunk's six SoA runs into a 2-stage shared
-//                   memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx, i.e. TMA 1-D)
+// Kernel (persistent, 2 CTAs per SM, dynamic tile scheduler, 15 consumer warps + 1 producer warp):
+//   producer warp : walks (tile, chunk) work items two deep, streams the chunk's six SoA runs into a 2-stage
+//                   shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx, TMA 1-D)
 //                   and stages the tile's 5x5x5-node E window as x-pairs so the gather is 12 LDS.128.
 //   consumer warps: P1 gather E from shared memory, kick/kick/drift/BC in registers, bin by NEW cell with
-//                      integer shared-memory atomics on an 8x8x8-cell window (tile-major ids);
-//                   P2 scan of the window histogram, one global reservation per destination TILE (<= 27);
-//                   P3 sorted position -> arrival slot permutation;
-//                   P4 coalesced store of R,P into next step's buckets (overflow -> tail), CIC weights of
-//                      the new positions into the freed staging columns, in sorted order;
-//                   P5 charge deposit: 2 lanes per non-empty cell walk the cell's weights, register
-//                      accumulation of the 8 nodes, 4 RED.F64 per lane.
+//                      integer shared-memory atomics on an 8x8x8-cell window (tile-major ids); the pushed
+//                      particle is parked in TENSOR MEMORY (tcgen05.st) across the scan;
+//                   P2 scan of the window histogram (8 warps) while a ninth warp sums the histogram per
+//                      destination tile and issues the <= 27 bucket reservations (global atomics);
+//                   P3 every particle is written once, as a 48-byte record, at its sorted position;
+//                   P4 coalesced store of the records into next step's buckets (overflow -> tail); the CIC
+//                      weights of the new position replace the head of the record;
+//                   P5 deposit: every window cell has a fixed owner thread that adds the chunk's 8 weight
+//                      moments of its cell to accumulators in tensor memory; node sums go to rho once per
+//                      tile (one RED.F64 per node and cell).
 // HBM traffic: 48 B read + 48 B written per particle.  E never round-trips through HBM, rho is produced
 // without re-reading the particles, and there is no sort pass.  Positions and momenta are bit-identical to
 // the unfused path (same device functions, same operation order).
@@ -25,13 +28,29 @@
 #include "bins.h"
 #include "push.cuh"
 
+// A/B knob of the build (scripts/build_variants.sh): rare paths in line or out of line (out of line costs ~18 %: the
+// call ABI pins registers and the 64-register kernel spills)
+#ifndef IPPLB_SLOW_ATTR
+#define IPPLB_SLOW_ATTR __forceinline__
+#endif
+#ifdef IPPLB_NO_WRAP   // A/B: periodic aliasing compiled out
+#define IPPLB_WRAP(A) false
+#define IPPLB_WRAP_CT(S) false
+#else
+#define IPPLB_WRAP(A) ((A).wrap != 0)
+#ifdef IPPLB_WRAP_RUNTIME   // A/B: runtime flag only
+#define IPPLB_WRAP_CT(S) false
+#else
+#define IPPLB_WRAP_CT(S) (S)
+#endif
+#endif
+
 namespace ipplb {
 
 constexpr int WH        = 2;              // window halo (cells) around the home tile
 constexpr int WIN       = TILE + 2 * WH;  // 8
 constexpr int WIN_CELLS = WIN * WIN * WIN;
 constexpr int NSLOT     = 27;             // destination tiles touched by the window
-constexpr unsigned short NOSLOT = 0xFFFFu;
 constexpr int EP_N = 3 * 5 * 5 * 4;       // E x-pairs per tile window
 
 enum { CH_TILE = 0, CH_TAIL = 1, CH_STOP = 2 };
@@ -63,30 +82,10 @@ struct StepArgs {
     int capacity;
     int ntx, nty, ntz, ntiles;
     int check_owner;
-    int balance_chunks;  // equal chunks per tile instead of full chunks + a remainder (IPPLB_FUSED_CFG = 2xx: off)
+    int balance_chunks;  // equal chunks per tile instead of full chunks + a remainder
+    int wrap;  // the rank owns the whole periodic domain: E reads and rho adds alias ghost nodes to the opposite interior layer
+               // (no fillHalo(E) needed before the step, no accumulateHalo(rho) after it; rho's ghost layers stay untouched)
     double rmin[3], rmax[3];
-};
-
-template <int NT, int K>
-struct StepSmem {
-    static constexpr int CAP = NT * K;
-    struct Stage {
-        double dat[6][CAP];
-    } st[2];
-    double2 ep[2][EP_N];  // E window of the current / next tile (x-pairs), indexed by ChunkDesc::epi
-    ChunkDesc desc[2];
-    unsigned long long full[2], empty[2];
-    int hist[WIN_CELLS];
-    int prefix[WIN_CELLS + 1];
-    unsigned short local[CAP], rank[CAP], perm[CAP];
-    unsigned short list[WIN_CELLS];
-    unsigned short cellxyz[WIN_CELLS];  // window id -> packed window coords
-    unsigned short winid[WIN_CELLS];    // window coords (wz*64 + wy*8 + wx) -> tile-major window id
-    unsigned char tsof[WIN_CELLS];      // window id -> destination tile slot
-    int tsbase[NSLOT + 1];
-    int adj[NSLOT], lim[NSLOT], tadj[NSLOT];
-    int warp_sums[32];
-    int nne, total;
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA 1-D) -----------------------------------------------
@@ -112,6 +111,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
         "DONE_%=:\n"
         "}" ::"r"(smem_u32(b)),
         "r"(parity)
+        : "memory");
+}
+// the same wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes instead of
+// re-issuing the test every ~40 ns (a spinning producer warp otherwise takes issue slots from its scheduler's consumers)
+__device__ __forceinline__ void mbar_wait_hint(unsigned long long* b, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(b)),
+        "r"(parity), "r"(ns)
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
@@ -140,17 +154,20 @@ __device__ __forceinline__ void win_seg(int w, int& s, int& l, int& wd) {
 // region, then the inclusive fallback, else stay -- ParticleSpatialLayout.hpp:372-395; the own strict test has
 // already failed), appended to that rank's segment of the exit buffer.  Lanes of a warp that leave for the same
 // rank share one atomic.
-__device__ __forceinline__ void place_exit(const StepArgs& A, const double r[3], const double p[3]) {
+// The two functions below are rare paths: they are kept OUT OF LINE (the kernel's parameter block is __grid_constant__,
+// so its address can be passed) to keep the hot loop short -- the whole kernel has to stay resident in the instruction
+// cache while two CTAs per SM run different phases of it.
+static __device__ IPPLB_SLOW_ATTR void place_exit(const StepArgs& A, double x, double y, double z, double px, double py, double pz) {
     int d = 0;
     if (A.regions) {
         d = -1;
         for (int k = 0; d < 0 && k < A.nranks; ++k) {
             const double* R = A.regions + 6 * k;
-            if (r[0] > R[0] && r[1] > R[1] && r[2] > R[2] && r[0] <= R[3] && r[1] <= R[4] && r[2] <= R[5]) d = k;
+            if (x > R[0] && y > R[1] && z > R[2] && x <= R[3] && y <= R[4] && z <= R[5]) d = k;
         }
         for (int k = 0; d < 0 && k < A.nranks; ++k) {
             const double* R = A.regions + 6 * k;
-            if (r[0] >= R[0] && r[1] >= R[1] && r[2] >= R[2] && r[0] <= R[3] && r[1] <= R[4] && r[2] <= R[5]) d = k;
+            if (x >= R[0] && y >= R[1] && z >= R[2] && x <= R[3] && y <= R[4] && z <= R[5]) d = k;
         }
         if (d < 0) d = A.me;
     }
@@ -164,16 +181,16 @@ __device__ __forceinline__ void place_exit(const StepArgs& A, const double r[3],
     if (e < A.seg_cap) {
         // one 48-byte record per leaver: a destination's segment is one contiguous message
         double2* rec = reinterpret_cast<double2*>(A.exit_buf + ((size_t)d * A.seg_cap + e) * 6);
-        rec[0]       = make_double2(r[0], r[1]);
-        rec[1]       = make_double2(r[2], p[0]);
-        rec[2]       = make_double2(p[1], p[2]);
+        rec[0]       = make_double2(x, y);
+        rec[1]       = make_double2(z, px);
+        rec[2]       = make_double2(py, pz);
     }
 }
 
 // a particle whose destination is outside the chunk's window (or that sits in the unsorted tail): claim one
 // slot of the destination bucket, scattered write, 8 reductions
-__device__ __forceinline__ void place_direct(const StepArgs& A, const double r[3], const double p[3],
-                                             const int c[3], const double whi[3]) {
+static __device__ IPPLB_SLOW_ATTR void place_direct(const StepArgs& A, const double r[3], const double p[3], const int c[3],
+                                                    const double whi[3]) {
     const int tile = (c[0] >> 2) + A.ntx * ((c[1] >> 2) + A.nty * (c[2] >> 2));
     int slot       = atomicAdd(&A.cursor_out[tile], 1);
     long g;
@@ -195,7 +212,8 @@ __device__ __forceinline__ void place_direct(const StepArgs& A, const double r[3
     }
     const int a[3] = {c[0] + A.m.nghost, c[1] + A.m.nghost, c[2] + A.m.nghost};
 #pragma unroll
-    for (int n = 0; n < 8; ++n) atomicAdd(&A.rho[cic_node(A.m, a, n)], dmul(A.q, cic_weight(whi, n)));
+    for (int n = 0; n < 8; ++n)
+        atomicAdd(&A.rho[IPPLB_WRAP(A) ? cic_node_wrapped(A.m, a, n) : cic_node(A.m, a, n)], dmul(A.q, cic_weight(whi, n)));
 }
 
 __device__ __forceinline__ bool owned_by_me(const StepArgs& A, const double r[3], const int c[3]) {
@@ -233,14 +251,18 @@ __device__ __forceinline__ void gather_pairs(const double2* __restrict__ ep, int
 }
 
 // ---- producer warp: shared by both kernel generations ---------------------------------------------------
-template <typename S>
+template <typename S, bool HINT, bool WRAP_CT>
 __device__ __forceinline__ void producer_loop(const StepArgs& A, S& s, const int lane) {
     constexpr int CAP = S::CAP;
     const int tail_start = A.state_in[BS_TAIL_START];
     const int tail_count = A.state_in[BS_TAIL_COUNT];
-    int rem = 0, kind = CH_STOP, hx = 0, hy = 0, hz = 0, epi = 1, chunk = CAP;
-    bool fresh = false;  // first chunk of a tile: its E window has to be staged
+    int rem = 0, kind = CH_STOP, hx = 0, hy = 0, hz = 0, chunk = CAP;
+    bool fresh = false;  // first chunk of a tile
     long pbeg = 0;
+    // E windows: tile number k (counting the non-empty tiles this CTA works on) uses buffer k & 1 and signals it through
+    // eready[k & 1].  The window of the NEXT tile is staged one tile ahead, behind the second chunk of the current tile
+    // (when the previous tile's window is dead), so that a tile never starts by waiting for ~20 dependent loads per lane.
+    int tile_seq = 0, buf_cur = 0, cur_tile = -1, staged_for = -1;
     // work items are fetched two deep so that neither the scheduler atomic nor the table loads sit on the
     // critical path: C = atomic issued (result pending in lane 0), B = item known, count/start loads in flight
     int c_it = 0, b_it = 0, b_rem = 0, b_start = 0;
@@ -254,12 +276,39 @@ __device__ __forceinline__ void producer_loop(const StepArgs& A, S& s, const int
             b_start = A.start_in[b_it];
         }
     };
+    // E window of a tile as x-pairs: ep[c][kz][jy][ix] = (E_c(node ix), E_c(node ix+1)); node (0,0,0) is the lower node
+    // of the tile's first cell, ghosted index = 4*h + nghost - 1
+    auto stage_window = [&](int tile, int buf) {
+        const int tx = tile % A.ntx, ty = (tile / A.ntx) % A.nty, tz = tile / (A.ntx * A.nty);
+        const int gx0 = 4 * tx + A.m.nghost - 1, gy0 = 4 * ty + A.m.nghost - 1, gz0 = 4 * tz + A.m.nghost - 1;
+        for (int e = lane; e < EP_N; e += 32) {
+            const int ix = e & 3, jy = (e >> 2) % 5, kz = ((e >> 2) / 5) % 5, c = (e >> 2) / 25;
+            int gx = gx0 + ix, gx1 = gx + 1, gy = gy0 + jy, gz = gz0 + kz;
+            double2 v = make_double2(0.0, 0.0);
+            if (gy < A.m.ey && gz < A.m.ez) {
+                const bool okx = gx < A.m.ex, okx1 = gx1 < A.m.ex;
+                if (IPPLB_WRAP_CT(WRAP_CT) || IPPLB_WRAP(A)) {
+                    gx  = wrap_axis(gx, A.m.nl[0], A.m.nghost);
+                    gx1 = wrap_axis(gx1, A.m.nl[0], A.m.nghost);
+                    gy  = wrap_axis(gy, A.m.nl[1], A.m.nghost);
+                    gz  = wrap_axis(gz, A.m.nl[2], A.m.nghost);
+                }
+                const long row = (long)A.m.ex * (gy + (long)A.m.ey * gz);
+                if (okx) v.x = __ldg(&A.ef[(gx + row) * 3 + c]);
+                if (okx1) v.y = __ldg(&A.ef[(gx1 + row) * 3 + c]);
+            }
+            s.ep[buf][e] = v;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.eready[buf]);
+    };
     issue_c();
     load_b();
     issue_c();
     for (unsigned seq = 0;; ++seq) {
         const int st = seq & 1;
-        mbar_wait(&s.empty[st], ((seq >> 1) & 1) ^ 1);
+        if (HINT) mbar_wait_hint(&s.empty[st], ((seq >> 1) & 1) ^ 1, 20000);
+        else mbar_wait(&s.empty[st], ((seq >> 1) & 1) ^ 1);
         while (rem == 0) {
             const int it = b_it;
             if (it < A.ntiles) {
@@ -271,7 +320,8 @@ __device__ __forceinline__ void producer_loop(const StepArgs& A, S& s, const int
                     const int nch = (rem + CAP - 1) / CAP;
                     chunk         = min(CAP, (((rem + nch - 1) / nch) + 1) & ~1);
                 }
-                fresh = rem > 0;
+                fresh    = rem > 0;
+                cur_tile = it;
                 hx   = it % A.ntx;
                 hy   = (it / A.ntx) % A.nty;
                 hz   = it / (A.ntx * A.nty);
@@ -296,49 +346,46 @@ __device__ __forceinline__ void producer_loop(const StepArgs& A, S& s, const int
             }
             break;
         }
-        const int cnt = min(rem, chunk);
+        const int cnt    = min(rem, chunk);
+        const bool first = kind == CH_TILE && fresh;
+        int first_word = 0;  // first chunk of a tile: 1 | parity of the window barrier << 1 (the consumers keep no state for it)
+        if (first) {
+            buf_cur    = tile_seq & 1;
+            first_word = 1 | (((tile_seq >> 1) & 1) << 1);
+            ++tile_seq;
+            fresh = false;
+        }
         if (lane == 0) {
             ChunkDesc d;
             d.kind = kind; d.cnt = cnt; d.hx = hx; d.hy = hy; d.hz = hz;
-            d.epi  = epi ^ (fresh ? 1 : 0);
-            d.pad[0] = (kind == CH_TILE && rem == cnt) ? 1 : 0;
-            d.pad[1] = 0;
+            d.epi  = buf_cur;
+            d.pad[0] = (kind == CH_TILE && rem == cnt) ? 1 : 0;  // last chunk of its tile
+            d.pad[1] = first_word;                               // first chunk: the consumers wait for the tile's E window
             s.desc[st] = d;
             const uint32_t bytes = (uint32_t)(((cnt + 1) & ~1) * 8);
             mbar_expect_tx(&s.full[st], 6 * bytes);
 #pragma unroll
             for (int a = 0; a < 6; ++a) bulk_g2s(&s.st[st].dat[a][0], A.in[a] + pbeg, bytes, &s.full[st]);
+            mbar_arrive(&s.full[st]);
         }
-        if (kind == CH_TILE && fresh) {
-            // (safe to overwrite: the window of two tiles ago is dead once the stage of chunk seq - 2 was released)
-            epi ^= 1;
-            fresh = false;
-            // E window of the tile as x-pairs: ep[c][kz][jy][ix] = (E_c(node ix), E_c(node ix+1)); node (0,0,0)
-            // is the lower node of the tile's first cell, ghosted index = 4*h + nghost - 1
-            const int gx0 = 4 * hx + A.m.nghost - 1, gy0 = 4 * hy + A.m.nghost - 1,
-                      gz0 = 4 * hz + A.m.nghost - 1;
-            for (int e = lane; e < EP_N; e += 32) {
-                const int ix = e & 3, jy = (e >> 2) % 5, kz = ((e >> 2) / 5) % 5, c = (e >> 2) / 25;
-                const int gx = gx0 + ix, gy = gy0 + jy, gz = gz0 + kz;
-                double2 v = make_double2(0.0, 0.0);
-                if (gy < A.m.ey && gz < A.m.ez) {
-                    const long base = ((long)gx + (long)A.m.ex * (gy + (long)A.m.ey * gz)) * 3 + c;
-                    if (gx < A.m.ex) v.x = __ldg(&A.ef[base]);
-                    if (gx + 1 < A.m.ex) v.y = __ldg(&A.ef[base + 3]);
-                }
-                s.ep[epi][e] = v;
-            }
+        if (first) {
+            // not staged ahead (first tile of the CTA, a one-chunk predecessor, an empty tile in between): stage it now.
+            // Safe to overwrite: the window of two tiles ago is dead once the stage of chunk seq - 2 was released.
+            if (staged_for != cur_tile) stage_window(cur_tile, buf_cur);
+        } else if (kind == CH_TILE && b_it < A.ntiles && b_rem > 0 && staged_for != b_it) {
+            // second or later chunk of a tile: the previous tile's window (buffer tile_seq & 1) is dead -- its last chunk
+            // was released before this chunk's stage became free -- so the NEXT tile's window can be staged now
+            stage_window(b_it, tile_seq & 1);
+            staged_for = b_it;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.full[st]);
         rem -= cnt;
         pbeg += cnt;
     }
 }
 
-// unsorted particles (overflow of the previous step, migration arrivals): global gather, direct placement
+// unsorted particles (overflow of the previous step, migration arrivals): global gather, direct placement (out of line)
 template <int NT, int K>
-__device__ __forceinline__ void tail_chunk(const StepArgs& A, const double (*dat)[NT * K], const int cnt, const int t) {
+__device__ IPPLB_SLOW_ATTR void tail_chunk(const StepArgs& A, const double (*dat)[NT * K], const int cnt, const int t) {
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const int slot = k * NT + t;
@@ -348,301 +395,17 @@ __device__ __forceinline__ void tail_chunk(const StepArgs& A, const double (*dat
             Cic c;
             cic_setup(A.m, r[0], r[1], r[2], c);
             double E[3];
-            gather_point<3>(A.m, c, A.ef, E);
+            if (IPPLB_WRAP(A)) gather_point_at<3>(c.whi, [&](int n) { return cic_node_wrapped(A.m, c.a, n); }, A.ef, E);
+            else gather_point<3>(A.m, c, A.ef, E);
             push_particle(A.P, r, p, E);
             Cic cn;
             cic_setup(A.m, r[0], r[1], r[2], cn);
             const int cc[3] = {cn.a[0] - A.m.nghost, cn.a[1] - A.m.nghost, cn.a[2] - A.m.nghost};
             if (owned_by_me(A, r, cc)) place_direct(A, r, p, cc, cn.whi);
-            else place_exit(A, r, p);
+            else place_exit(A, r[0], r[1], r[2], p[0], p[1], p[2]);
         }
     }
 }
-
-// ---- the kernel --------------------------------------------------------------------------------------------
-template <int NT, int K, int MINB>
-__global__ void __launch_bounds__(NT + 32, MINB) fused_step_kernel(const StepArgs A) {
-    using S           = StepSmem<NT, K>;
-    constexpr int CAP = S::CAP;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    S& s           = *reinterpret_cast<S*>(smem_raw);
-    const int t    = threadIdx.x;
-    const int lane = t & 31, warp = t >> 5;
-
-    // ---- one-time tables ---------------------------------------------------------------------------------
-    if (t == 0) {
-        int run = 0;
-        for (int ts = 0; ts < NSLOT; ++ts) {
-            s.tsbase[ts] = run;
-            const int wx = (ts % 3 == 1) ? 4 : 2, wy = ((ts / 3) % 3 == 1) ? 4 : 2, wz = (ts / 9 == 1) ? 4 : 2;
-            run += wx * wy * wz;
-        }
-        s.tsbase[NSLOT] = run;
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s.full[i], 1);
-            mbar_init(&s.empty[i], NT / 32);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    for (int c = t; c < WIN_CELLS; c += NT + 32) {
-        const int wx = c & 7, wy = (c >> 3) & 7, wz = c >> 6;
-        int sx, lx, dx, sy, ly, dy, sz, lz, dz;
-        win_seg(wx, sx, lx, dx);
-        win_seg(wy, sy, ly, dy);
-        win_seg(wz, sz, lz, dz);
-        const int ts = sx + 3 * (sy + 3 * sz);
-        const int id = s.tsbase[ts] + (lz * dy + ly) * dx + lx;
-        s.cellxyz[id] = (unsigned short)(wx | (wy << 4) | (wz << 8));
-        s.winid[c]    = (unsigned short)id;
-        s.tsof[id]    = (unsigned char)ts;
-        s.hist[c]     = 0;
-    }
-    __syncthreads();
-
-    if (warp == NT / 32) {
-        producer_loop<S>(A, s, lane);
-        return;
-    }
-
-    // ======================================= consumer warps =================================================
-    for (unsigned seq = 0;; ++seq) {
-        const int st = seq & 1;
-        mbar_wait(&s.full[st], (seq >> 1) & 1);
-        const ChunkDesc D = s.desc[st];
-        if (D.kind == CH_STOP) break;
-        typename S::Stage& G = s.st[st];
-        const int cnt        = D.cnt;
-
-        if (D.kind == CH_TAIL) {
-            tail_chunk<NT, K>(A, G.dat, cnt, t);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.empty[st]);
-            continue;
-        }
-
-        const int wox = D.hx * TILE - WH, woy = D.hy * TILE - WH, woz = D.hz * TILE - WH;
-        // ---- P1: gather, push, bin by new cell ------------------------------------------------------------
-        {
-            const double2* ep = s.ep[D.epi];
-#pragma unroll 1
-            for (int k = 0; k < K; ++k) {
-                const int slot = k * NT + t;
-                unsigned short loc = NOSLOT, rk = 0;
-                if (slot < cnt) {
-                    double r[3] = {G.dat[0][slot], G.dat[1][slot], G.dat[2][slot]};
-                    double p[3] = {G.dat[3][slot], G.dat[4][slot], G.dat[5][slot]};
-                    Cic c;
-                    cic_setup(A.m, r[0], r[1], r[2], c);
-                    double E[3];
-                    gather_pairs(ep, c.a[0] - A.m.nghost - D.hx * TILE, c.a[1] - A.m.nghost - D.hy * TILE,
-                                 c.a[2] - A.m.nghost - D.hz * TILE, c.whi, E);
-                    push_particle(A.P, r, p, E);
-                    Cic cn;
-                    cic_setup(A.m, r[0], r[1], r[2], cn);
-                    const int cc[3] = {cn.a[0] - A.m.nghost, cn.a[1] - A.m.nghost, cn.a[2] - A.m.nghost};
-                    if (!owned_by_me(A, r, cc)) {
-                        place_exit(A, r, p);
-                    } else {
-                        const int wx = cc[0] - wox, wy = cc[1] - woy, wz = cc[2] - woz;
-                        if ((unsigned)wx < (unsigned)WIN && (unsigned)wy < (unsigned)WIN &&
-                            (unsigned)wz < (unsigned)WIN) {
-                            const int id = s.winid[(wz * WIN + wy) * WIN + wx];
-                            loc          = (unsigned short)id;
-                            rk           = (unsigned short)atomicAdd(&s.hist[id], 1);
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                G.dat[d][slot]     = r[d];
-                                G.dat[3 + d][slot] = p[d];
-                            }
-                        } else {
-                            place_direct(A, r, p, cc, cn.whi);
-                        }
-                    }
-                }
-                s.local[slot] = loc;
-                s.rank[slot]  = rk;
-            }
-        }
-        consumer_sync<NT>();
-        // ---- P2: exclusive scan of the window histogram (tile-major ids), 2 cells per thread ---------------
-        static_assert(NT >= WIN_CELLS / 2, "the scan uses WIN_CELLS / 2 threads");
-        // value = count | (count > 0) << 16: one scan yields the particle prefix and the ordered list of non-empty cells
-        int v0 = 0, v1 = 0, inc = 0;
-        if (t < WIN_CELLS / 2) {
-            v0 = s.hist[2 * t];
-            v1 = s.hist[2 * t + 1];
-            v0 |= (v0 > 0) << 16;
-            v1 |= (v1 > 0) << 16;
-            inc = v0 + v1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += y;
-            }
-            if (lane == 31) s.warp_sums[warp] = inc;
-        }
-        consumer_sync<NT>();
-        if (t < WIN_CELLS / 2) {
-            int run = inc - v0 - v1;
-#pragma unroll
-            for (int w = 0; w < WIN_CELLS / 64 - 1; ++w)
-                if (w < warp) run += s.warp_sums[w];
-            s.prefix[2 * t]     = run & 0xFFFF;
-            s.prefix[2 * t + 1] = (run + v0) & 0xFFFF;
-            if (v0 >> 16) {
-                s.list[run >> 16] = (unsigned short)(2 * t);
-                s.hist[2 * t]     = 0;  // ready for the next chunk
-            }
-            if (v1 >> 16) {
-                s.list[(run + v0) >> 16] = (unsigned short)(2 * t + 1);
-                s.hist[2 * t + 1]        = 0;
-            }
-            if (t == WIN_CELLS / 2 - 1) {
-                s.prefix[WIN_CELLS] = (run + v0 + v1) & 0xFFFF;
-                s.nne               = (run + v0 + v1) >> 16;
-            }
-        }
-        consumer_sync<NT>();
-        // ---- reserve one block per destination tile (global atomics, consumed only after the next barrier so
-        //      their latency hides behind P3 and the P4 loads); P3: sorted position -> arrival slot -----------
-        int rs_b0 = 0, rs_n = 0, rs_base = 0, rs_cap = 0, rs_start = 0;
-        bool rs_bad = false;
-        if (t < NSLOT) {
-            rs_b0 = s.prefix[s.tsbase[t]];
-            rs_n  = s.prefix[s.tsbase[t + 1]] - rs_b0;
-            if (rs_n > 0) {
-                const int tx = D.hx + (t % 3) - 1, ty = D.hy + ((t / 3) % 3) - 1, tz = D.hz + (t / 9) - 1;
-                rs_bad = tx < 0 || tx >= A.ntx || ty < 0 || ty >= A.nty || tz < 0 || tz >= A.ntz;
-                if (!rs_bad) {
-                    const int tile = tx + A.ntx * (ty + A.nty * tz);
-                    rs_base        = atomicAdd(&A.cursor_out[tile], rs_n);
-                    rs_cap         = A.cap_out[tile];
-                    rs_start       = A.start_out[tile];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int slot           = k * NT + t;
-            const unsigned short loc = s.local[slot];
-            if (loc != NOSLOT) s.perm[s.prefix[loc] + s.rank[slot]] = (unsigned short)slot;
-        }
-        consumer_sync<NT>();
-        // ---- P4: sorted order -> registers (random shared-memory reads) ----------------------------------------
-        const int ntot = s.prefix[WIN_CELLS];
-        double pr[K][6];
-        int pts[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int p = k * NT + t;
-            pts[k]      = -1;
-            if (p < ntot) {
-                const int slot = s.perm[p];
-                pts[k]         = s.tsof[s.local[slot]];
-#pragma unroll
-                for (int a = 0; a < 6; ++a) pr[k][a] = G.dat[a][slot];
-            }
-        }
-        if (t < NSLOT) {
-            int adj = 0, lim = 0, tadj = 0;
-            if (rs_n > 0) {
-                if (rs_bad) {
-                    atomicOr(&A.misc[BM_FLAGS], IPPLB_FLAG_INTERNAL);
-                    tadj = INT_MIN;  // lim = 0: everything of this block is dropped
-                } else {
-                    const int abs0 = rs_start + rs_base;
-                    adj            = abs0 - rs_b0;
-                    lim            = rs_start + rs_cap;
-                    const int g0   = max(lim, abs0);  // first absolute slot that does not fit
-                    const int over = abs0 + rs_n - g0;
-                    if (over > 0) {
-                        const int tb = A.state_out[BS_TAIL_START] + atomicAdd(&A.state_out[BS_TAIL_COUNT], over);
-                        tadj         = tb - g0;
-                        if ((long)tb + over > A.capacity) {
-                            atomicOr(&A.misc[BM_FLAGS], IPPLB_FLAG_CAPACITY);
-                            tadj = INT_MIN;
-                        }
-                    }
-                }
-            }
-            s.adj[t]  = adj;
-            s.lim[t]  = lim;
-            s.tadj[t] = tadj;
-        }
-        consumer_sync<NT>();
-        // ---- coalesced store into next step's buckets; CIC weights of the new positions, sorted order --------
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int p = k * NT + t;
-            if (pts[k] >= 0) {
-                const int ts = pts[k];
-                int g        = s.adj[ts] + p;
-                if (g >= s.lim[ts]) {
-                    const int ta = s.tadj[ts];
-                    g            = ta == INT_MIN ? -1 : g + ta;
-                }
-                if (g >= 0) {  // negative: dropped (flag already raised)
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) A.out[a][g] = pr[k][a];
-                }
-                int idx;
-                double w0, w1, w2;
-                cic_axis(pr[k][0], A.m.origin[0], A.m.invdx[0], idx, w0);
-                cic_axis(pr[k][1], A.m.origin[1], A.m.invdx[1], idx, w1);
-                cic_axis(pr[k][2], A.m.origin[2], A.m.invdx[2], idx, w2);
-                G.dat[3][p] = w0;
-                G.dat[4][p] = w1;
-                G.dat[5][p] = w2;
-            }
-        }
-        consumer_sync<NT>();
-        // ---- P5: deposit, one lane per non-empty cell (list is in tile-major id order: the 64 home cells, which hold
-        //      most particles, are neighbours in the list, so the lanes of a warp run similar trip counts).  The eight
-        //      node sums follow from eight moments of the weights: 4 multiplies + 7 adds per particle.
-        {
-            const int nne = s.nne;
-            for (int j = t; j < nne; j += NT) {
-                const int id = s.list[j];
-                const int b = s.prefix[id], e = s.prefix[id + 1];
-                double s1 = 0.0, s2 = 0.0, s3 = 0.0, s12 = 0.0, s13 = 0.0, s23 = 0.0, s123 = 0.0;
-                for (int p = b; p < e; ++p) {
-                    const double w0 = G.dat[3][p], w1 = G.dat[4][p], w2 = G.dat[5][p];
-                    const double w01 = w0 * w1;
-                    s1 += w0;
-                    s2 += w1;
-                    s3 += w2;
-                    s12 += w01;
-                    s13 += w0 * w2;
-                    s23 += w1 * w2;
-                    s123 += w01 * w2;
-                }
-                const double cnt = (double)(e - b);
-                double nd[8];  // node n: bit d set -> lower node along d (weight 1 - w_d)
-                nd[0] = s123;
-                nd[1] = s23 - s123;
-                nd[2] = s13 - s123;
-                nd[3] = (s3 - s13) - (s23 - s123);
-                nd[4] = s12 - s123;
-                nd[5] = (s2 - s12) - (s23 - s123);
-                nd[6] = (s1 - s12) - (s13 - s123);
-                nd[7] = ((cnt - s1) - (s2 - s12)) - ((s3 - s13) - (s23 - s123));
-                const unsigned xyz = s.cellxyz[id];
-                const int a[3]     = {(int)(xyz & 15) + wox + A.m.nghost, (int)((xyz >> 4) & 15) + woy + A.m.nghost,
-                                      (int)(xyz >> 8) + woz + A.m.nghost};
-#pragma unroll
-                for (int n = 0; n < 8; ++n) atomicAdd(&A.rho[cic_node(A.m, a, n)], A.q * nd[n]);
-            }
-        }
-        // every consumer releases the stage on its own (no CTA barrier between chunks): the next chunk's P1 only
-        // touches the other stage, hist (already reset) and local / rank (dead since P4)
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[st]);
-    }
-}
-
 
 // ---- generation 3: sorted records + per-cell moment accumulators in tensor memory ----------------------------
 // Same producer, same P1 arithmetic.  What changes:
@@ -666,13 +429,12 @@ struct Step3Smem {
     } st[2];
     double2 ep[2][EP_N];
     ChunkDesc desc[2];
-    unsigned long long full[2], empty[2];
+    unsigned long long full[2], empty[2], eready[2];
     int hist[WIN_CELLS];
     int lpre[WIN_CELLS + 1];    // exclusive prefix inside the 64-cell scan segment
     int prefix[WIN_CELLS + 1];  // global particle prefix per window id (valid after barrier D)
     unsigned short cellxyz[WIN_CELLS];
     unsigned short winid[WIN_CELLS];
-    unsigned char tsof[WIN_CELLS];
     unsigned char tsp[CAP];  // sorted position -> destination tile slot
     int tsbase[NSLOT + 1];
     int adj[NSLOT], lim[NSLOT], tadj[NSLOT];
@@ -741,18 +503,37 @@ __device__ __forceinline__ void tmem_ld6(uint32_t addr, double v[6]) {
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 constexpr int tmem_cols_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int NT, int K, int MINB>
+// Kernel variants (template parameter VAR, bit mask; the default is chosen in ipplb_bins_step):
+//   V_OWNER_TAIL  the 64 cells of the home tile, which receive ~70 % of a chunk's particles and make their owners' P5
+//                 the longest, are owned by the LAST two consumer warps -- the warps whose second P1 / P4 round is empty
+//                 when the producer cuts a tile into equal chunks (5 x 820 of 960 slots at 64 particles per cell);
+//   V_HINT        mbarrier waits carry a suspend-time hint: a waiting warp sleeps in hardware instead of re-issuing the
+//                 test every ~40 ns (the producer's spin was 4 % of all issued instructions);
+//   V_LEAPFROG    the steady-state leapfrog push with every sub-step on (kick, kick, drift, periodic BC): no flag tests;
+//   V_PERIODIC1   one rank that owns the whole periodic domain: no ownership test on the fast path (a wrapped particle
+//                 is always inside; the test is kept on the out-of-window path) and the periodic aliasing of ghost
+//                 nodes (StepArgs::wrap) compiled in unconditionally;
+enum { V_OWNER_TAIL = 1, V_HINT = 2, V_LEAPFROG = 4, V_P5U2 = 8, V_PERIODIC1 = 16 };
+constexpr int HOME_ID0 = 224;  // first tile-major window id of the home tile (slot 13): sum of the sizes of slots 0..12
+
+template <int NT, int K, int MINB, int VAR>
 __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepArgs A) {
     using S            = Step3Smem<NT, K>;
-    constexpr int CAP  = S::CAP;
     constexpr int NW   = NT / 32;
     constexpr int NSEG = WIN_CELLS / 64;
     constexpr int NSL  = (WIN_CELLS + NT - 1) / NT;  // window cells owned per thread
     constexpr int WCOLS = NSL * 16 + K * 16;  // tensor-memory columns per warp: accumulators + parked particles
     constexpr int TCOLS = tmem_cols_pow2(((NW + 3) / 4) * WCOLS);
+    constexpr bool OWNER_TAIL = (VAR & V_OWNER_TAIL) != 0;
+    constexpr bool HINT       = (VAR & V_HINT) != 0;
+    constexpr bool P5U2       = (VAR & V_P5U2) != 0;
+    constexpr bool LEAPFROG   = (VAR & V_LEAPFROG) != 0;
+    constexpr bool PERIODIC1  = (VAR & V_PERIODIC1) != 0;
     static_assert(NT >= WIN_CELLS / 2, "the scan uses WIN_CELLS / 2 threads");
     static_assert(NSEG <= 16, "segment offsets live in one warp");
     static_assert(TCOLS * MINB <= 512, "tensor memory columns of the co-resident CTAs");
+    static_assert(!OWNER_TAIL || (NSL == 2 && NT >= HOME_ID0 + 64 + 32 && 2 * NT - WIN_CELLS >= 96),
+                  "owner remap: ids NT.. go to the third-last warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     S& s           = *reinterpret_cast<S*>(smem_raw);
     const int t    = threadIdx.x;
@@ -770,6 +551,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.full[i], 1);
             mbar_init(&s.empty[i], NW);
+            mbar_init(&s.eready[i], 1);
         }
         fence_mbar_init();
     }
@@ -791,14 +573,13 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
         const int ts = sx + 3 * (sy + 3 * sz);
         const int id = s.tsbase[ts] + (lz * dy + ly) * dx + lx;
         s.cellxyz[id] = (unsigned short)(wx | (wy << 4) | (wz << 8));
-        s.winid[c]    = (unsigned short)id;
-        s.tsof[id]    = (unsigned char)ts;
+        s.winid[c]    = (unsigned short)(id | (ts << 9));  // window id (9 bits) | destination tile slot
         s.hist[c]     = 0;
     }
     __syncthreads();
 
     if (warp == NW) {
-        producer_loop<S>(A, s, lane);
+        producer_loop<S, HINT, PERIODIC1>(A, s, lane);
         return;
     }
     // this warp's accumulator columns: lanes 32 * (warp % 4) of tensor memory, 16 columns per owned cell slot
@@ -809,10 +590,25 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
 #pragma unroll
         for (int sl = 0; sl < NSL; ++sl) tmem_st8(tm0 + sl * 16, z);
     }
+    // window cell this thread owns in slot sl of P5 (< 0: none; recomputed where needed instead of held in registers).
+    // Plain map: id = sl * NT + t.  V_OWNER_TAIL: the ids are rotated so that the home tile's 64 cells land on the last
+    // two warps, and the WIN_CELLS - NT ids of the second slot (far corner / edge cells, almost always empty) on the
+    // warp before them.
+    auto own = [&](int sl) -> int {
+        if (OWNER_TAIL) {
+            if (sl == 0) {
+                const int v = t + (64 + HOME_ID0);
+                return v >= NT ? v - NT : v;
+            }
+            return (t >= NT - 96 && t < NT - 96 + (WIN_CELLS - NT)) ? NT + (t - (NT - 96)) : -1;
+        }
+        return sl * NT + t < WIN_CELLS ? sl * NT + t : -1;
+    };
 
     for (unsigned seq = 0;; ++seq) {
         const int st = seq & 1;
-        mbar_wait(&s.full[st], (seq >> 1) & 1);
+        if (HINT) mbar_wait_hint(&s.full[st], (seq >> 1) & 1, 20000);
+        else mbar_wait(&s.full[st], (seq >> 1) & 1);
         const ChunkDesc D = s.desc[st];
         if (D.kind == CH_STOP) break;
         typename S::Stage& G = s.st[st];
@@ -826,9 +622,16 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
             continue;
         }
 
+        if (D.pad[1]) {  // first chunk of a tile: its E window (staged one tile ahead as a rule) has to be there
+            mbar_wait(&s.eready[D.epi], (unsigned)D.pad[1] >> 1);
+        }
         const int wox = D.hx * TILE - WH, woy = D.hy * TILE - WH, woz = D.hz * TILE - WH;
         // ---- P1: gather, push, bin by new cell; the pushed particle stays in registers ----------------------
-        int lr[K];  // window id | rank inside the cell << 16, or -1
+        int lr[K];  // window id (9 bits) | destination tile slot << 9 | rank inside the cell << 16, or -1
+        auto bin_particle = [&](int wx, int wy, int wz) {
+            const int idts = s.winid[(wz * WIN + wy) * WIN + wx];
+            return idts | (atomicAdd(&s.hist[idts & 0x1FF], 1) << 16);
+        };
         {
             const double2* ep = s.ep[D.epi];
 #pragma unroll
@@ -844,21 +647,29 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
                     double E[3];
                     gather_pairs(ep, c.a[0] - A.m.nghost - D.hx * TILE, c.a[1] - A.m.nghost - D.hy * TILE,
                                  c.a[2] - A.m.nghost - D.hz * TILE, c.whi, E);
-                    push_particle(A.P, r, p, E);
+                    if (LEAPFROG) push_leapfrog_full(A.P, r, p, E);
+                    else push_particle(A.P, r, p, E);
                     Cic cn;
                     cic_setup(A.m, r[0], r[1], r[2], cn);
                     const int cc[3] = {cn.a[0] - A.m.nghost, cn.a[1] - A.m.nghost, cn.a[2] - A.m.nghost};
-                    if (!owned_by_me(A, r, cc)) {
-                        place_exit(A, r, p);
-                    } else {
-                        const int wx = cc[0] - wox, wy = cc[1] - woy, wz = cc[2] - woz;
-                        if ((unsigned)wx < (unsigned)WIN && (unsigned)wy < (unsigned)WIN &&
-                            (unsigned)wz < (unsigned)WIN) {
-                            const int id = s.winid[(wz * WIN + wy) * WIN + wx];
-                            lr[k]        = id | (atomicAdd(&s.hist[id], 1) << 16);
-                        } else {
+                    const int wx = cc[0] - wox, wy = cc[1] - woy, wz = cc[2] - woz;
+                    const bool inwin = (unsigned)wx < (unsigned)WIN && (unsigned)wy < (unsigned)WIN &&
+                                       (unsigned)wz < (unsigned)WIN;
+                    if (PERIODIC1) {
+                        // every window cell a wrapped particle can reach lies inside the periodic domain
+                        if (inwin) {
+                            lr[k] = bin_particle(wx, wy, wz);
+                        } else if (owned_by_me(A, r, cc)) {
                             place_direct(A, r, p, cc, cn.whi);
+                        } else {
+                            place_exit(A, r[0], r[1], r[2], p[0], p[1], p[2]);
                         }
+                    } else if (!owned_by_me(A, r, cc)) {
+                        place_exit(A, r[0], r[1], r[2], p[0], p[1], p[2]);
+                    } else if (inwin) {
+                        lr[k] = bin_particle(wx, wy, wz);
+                    } else {
+                        place_direct(A, r, p, cc, cn.whi);
                     }
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
@@ -935,7 +746,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
         double2* rec = reinterpret_cast<double2*>(&G.dat[0][0]);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int id  = lr[k] < 0 ? 0 : (lr[k] & 0xFFFF);
+            const int id  = lr[k] < 0 ? 0 : (lr[k] & 0x1FF);
             const int pre = gpre(id);
             double pk[6];
             tmem_ld6(tmp + k * 16, pk);
@@ -944,10 +755,12 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
                 rec[3 * pos]     = make_double2(pk[0], pk[1]);
                 rec[3 * pos + 1] = make_double2(pk[2], pk[3]);
                 rec[3 * pos + 2] = make_double2(pk[4], pk[5]);
-                s.tsp[pos]       = s.tsof[id];
+                s.tsp[pos]       = (unsigned char)((lr[k] >> 9) & 31);
             }
         }
-        if (warp == 0 && lane < NSLOT) {
+        int t_now = t;  // opaque copy: keeps the compiler from hoisting this test out of the chunk loop into a spilled predicate
+        asm volatile("" : "+r"(t_now));
+        if (t_now < NSLOT) {
             int adj = 0, lim = 0, tadj = 0;
             if (rs_n > 0) {
                 if (rs_bad) {
@@ -1008,16 +821,16 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
             }
         }
         consumer_sync<NT>();  // ---- E: weights are in place
-        // ---- P5: every window cell has a fixed owner (window id = slot * NT + thread); the owner adds the chunk's
-        //      moments of its cell to the cell's accumulators in tensor memory
+        // ---- P5: every window cell has a fixed owner thread; the owner adds the chunk's moments of its cell to the
+        //      cell's accumulators in tensor memory
 #pragma unroll
         for (int sl = 0; sl < NSL; ++sl) {
-            if (sl * NT + warp * 32 < WIN_CELLS) {  // warp-uniform
-                const int id = sl * NT + t;
-                const int b = s.prefix[id], e = s.prefix[id + 1];
+            const int id = own(sl);
+            if (__any_sync(0xffffffffu, id >= 0)) {
+                const int b = id >= 0 ? s.prefix[id] : 0, e = id >= 0 ? s.prefix[id + 1] : 0;
                 if (__any_sync(0xffffffffu, e > b)) {
                     double m[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // 1 w0 w1 w2 w0w1 w0w2 w1w2 w0w1w2
-                    for (int p = b; p < e; ++p) {
+                    auto add_weights = [&](int p) {
                         const double2 w01 = rec[3 * p];
                         const double w2   = rec[3 * p + 1].x;
                         const double p01  = w01.x * w01.y;
@@ -1028,6 +841,12 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
                         m[5] += w01.x * w2;
                         m[6] += w01.y * w2;
                         m[7] += p01 * w2;
+                    };
+                    if (P5U2) {
+#pragma unroll 2
+                        for (int p = b; p < e; ++p) add_weights(p);
+                    } else {
+                        for (int p = b; p < e; ++p) add_weights(p);
                     }
                     m[0] = (double)(e - b);
                     double acc[8];
@@ -1049,11 +868,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
             const double z8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int sl = 0; sl < NSL; ++sl) {
-                if (sl * NT + warp * 32 < WIN_CELLS) {
+                if (__any_sync(0xffffffffu, own(sl) >= 0)) {
                     double a[8];
                     tmem_ld8(tm0 + sl * 16, a);
                     tmem_st8(tm0 + sl * 16, z8);
-                    if (a[0] != 0.0) {
+                    if (own(sl) >= 0 && a[0] != 0.0) {
                         const double s1 = a[1], s2 = a[2], s3 = a[3], s12 = a[4], s13 = a[5], s23 = a[6], s123 = a[7];
                         double nd[8];  // node n: bit d set -> lower node along d (weight 1 - w_d)
                         nd[0] = s123;
@@ -1064,13 +883,23 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
                         nd[5] = (s2 - s12) - (s23 - s123);
                         nd[6] = (s1 - s12) - (s13 - s123);
                         nd[7] = ((a[0] - s1) - (s2 - s12)) - ((s3 - s13) - (s23 - s123));
-                        const unsigned xyz = s.cellxyz[sl * NT + t];
+                        const unsigned xyz = s.cellxyz[own(sl)];
                         // ghosted index of the cell's upper node = window coordinate + window origin + nghost
                         const long gx = (long)(xyz & 15) + wox + A.m.nghost, gy = (long)((xyz >> 4) & 15) + woy + A.m.nghost,
                                    gz = (long)(xyz >> 8) + woz + A.m.nghost;
+                        // upper / lower node per axis (aliased to the opposite interior layer on a whole periodic domain)
+                        long xs[2] = {gx, gx - 1}, ys[2] = {gy, gy - 1}, zs[2] = {gz, gz - 1};
+                        if (IPPLB_WRAP_CT(PERIODIC1) || IPPLB_WRAP(A)) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                xs[i] = wrap_axis((int)xs[i], A.m.nl[0], A.m.nghost);
+                                ys[i] = wrap_axis((int)ys[i], A.m.nl[1], A.m.nghost);
+                                zs[i] = wrap_axis((int)zs[i], A.m.nl[2], A.m.nghost);
+                            }
+                        }
 #pragma unroll
                         for (int n = 0; n < 8; ++n)
-                            atomicAdd(&A.rho[(gx - (n & 1)) + (long)A.m.ex * ((gy - ((n >> 1) & 1)) + (long)A.m.ey * (gz - ((n >> 2) & 1)))],
+                            atomicAdd(&A.rho[xs[n & 1] + (long)A.m.ex * (ys[(n >> 1) & 1] + (long)A.m.ey * zs[(n >> 2) & 1])],
                                       A.q * nd[n]);
                     }
                 }
@@ -1083,42 +912,30 @@ __global__ void __launch_bounds__(NT + 32, MINB) fused_step3_kernel(const StepAr
     }
 }
 
-template <int NT, int K, int MINB>
-static int launch_fused(ipplb_ctx* ctx, const StepArgs& A) {
-    using S   = StepSmem<NT, K>;
-    auto kern = fused_step_kernel<NT, K, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IPPLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
-        attr_set = true;
-    }
-    kern<<<ctx->num_sms * MINB, NT + 32, sizeof(S), ctx->stream>>>(A);
-    IPPLB_CHECK_LAUNCH(ctx);
-    return IPPLB_OK;
-}
-
-template <int NT, int K, int MINB>
+template <int NT, int K, int MINB, int VAR>
 static int launch_fused3(ipplb_ctx* ctx, const StepArgs& A) {
     using S   = Step3Smem<NT, K>;
-    auto kern = fused_step3_kernel<NT, K, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    auto kern = fused_step3_kernel<NT, K, MINB, VAR>;
+    // the attribute is per device: one flag per device ordinal (a process may hold contexts on several GPUs)
+    static bool attr_set[64] = {};
+    const int dev = ctx->device & 63;
+    if (!attr_set[dev]) {
         IPPLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     kern<<<ctx->num_sms * MINB, NT + 32, sizeof(S), ctx->stream>>>(A);
     IPPLB_CHECK_LAUNCH(ctx);
     return IPPLB_OK;
 }
 
-// tuning knob (experiments only): IPPLB_FUSED_CFG selects the CTA shape; the default is the measured best
-static int fused_cfg() {
-    static int cfg = -1;
-    if (cfg < 0) {
-        const char* e = getenv("IPPLB_FUSED_CFG");
-        cfg           = e ? atoi(e) : 0;
+// tuning knob (experiments only): IPPLB_FUSED_VAR selects the kernel variant mask (V_*); the default is the measured best
+static int fused_var() {
+    int var = -1;
+    {
+        const char* e = getenv("IPPLB_FUSED_VAR");  // read on every call so that one process can A/B the variants
+        var           = e ? (atoi(e) & 31) : (V_OWNER_TAIL | V_HINT | V_P5U2 | V_LEAPFROG | V_PERIODIC1);
     }
-    return cfg;
+    return var;
 }
 
 }  // namespace ipplb
@@ -1171,29 +988,36 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
     A.capacity   = (int)b->capacity;
     A.ntx = b->ntx; A.nty = b->nty; A.ntz = b->ntz; A.ntiles = b->ntiles;
     A.check_owner = (region_min && region_max) ? 1 : 0;
-    A.balance_chunks = (fused_cfg() / 100) == 2 ? 0 : 1;  // on by default (4.25 -> 4.20 ms at C2); IPPLB_FUSED_CFG=2xx turns it off
+    A.balance_chunks = 1;  // equal chunks per tile (4.25 -> 4.20 ms at C2)
     for (int d = 0; d < 3; ++d) {
         A.rmin[d] = region_min ? region_min[d] : 0.0;
         A.rmax[d] = region_max ? region_max[d] : 0.0;
     }
-    IPPLB_CUDA(cudaMemsetAsync(b->misc(), 0, sizeof(int) * 4, ctx->stream));
-    IPPLB_CUDA(cudaMemsetAsync(b->d_exit_cnt, 0, sizeof(int) * nrk, ctx->stream));
+    // the step's scratch words and exit counters were re-armed by the last bins_plan (build or step)
+    // One rank that owns the whole periodic domain: ghost nodes are aliased to the opposite interior layer inside the
+    // kernel (E window reads, rho adds) -- what HaloCells::applyPeriodicSerialDim does in two extra passes over the
+    // fields (src/Field/HaloCells.hpp:297-336).  efield's ghost layers are then not read and rho's receive nothing.
+    const ipplb_mesh& M = b->mesh;
+    const bool whole = M.nl[0] == M.ng[0] && M.nl[1] == M.ng[1] && M.nl[2] == M.ng[2];
+    A.wrap = (nrk == 1 && !A.check_owner && whole && push->do_bc) ? 1 : 0;
+    // the variant follows the call: V_PERIODIC1 when the aliasing applies, V_LEAPFROG for the steady-state leapfrog step
+    const bool lf = push->kind == IPPLB_PUSH_LEAPFROG && push->do_kick2 && push->do_kick1 && push->do_drift && push->do_bc;
+    int var = fused_var();
+    if (!lf) var &= ~V_LEAPFROG;
+    if (!A.wrap) var &= ~V_PERIODIC1;
     int rc;
-    switch (fused_cfg() % 100) {
-        case 1: rc = launch_fused<256, 2, 3>(ctx, A); break;
-        case 2: rc = launch_fused<512, 2, 1>(ctx, A); break;
-        case 3: rc = launch_fused<768, 2, 1>(ctx, A); break;
-        case 4: rc = launch_fused<256, 2, 2>(ctx, A); break;
-        case 10: rc = launch_fused3<384, 2, 2>(ctx, A); break;
-        case 11: rc = launch_fused3<256, 2, 3>(ctx, A); break;
-        case 12: rc = launch_fused3<256, 3, 2>(ctx, A); break;
-        case 13: rc = launch_fused3<512, 2, 1>(ctx, A); break;
-        case 14: rc = launch_fused3<352, 2, 2>(ctx, A); break;
-        case 15: rc = launch_fused3<320, 2, 2>(ctx, A); break;
-        case 17: rc = launch_fused3<416, 2, 2>(ctx, A); break;
-        case 5: rc = launch_fused<384, 2, 2>(ctx, A); break;  // generation 2
-        case 16: rc = launch_fused3<448, 2, 2>(ctx, A); break;
-        default: rc = launch_fused3<480, 2, 2>(ctx, A); break;  // generation 3, 15 consumer warps (measured best)
+    // instantiated: the tuned set (V_OWNER_TAIL | V_HINT | V_P5U2) with every combination of the two call-dependent
+    // bits, and the plain kernel (0) as the A/B baseline; any other request runs the plain kernel
+    constexpr int T = V_OWNER_TAIL | V_HINT | V_P5U2;
+    switch (var) {
+#define IPPLB_VAR_CASE(v) case v: rc = launch_fused3<480, 2, 2, v>(ctx, A); break;
+        IPPLB_VAR_CASE(T)
+        IPPLB_VAR_CASE(T | V_LEAPFROG)
+        IPPLB_VAR_CASE(T | V_PERIODIC1)
+        IPPLB_VAR_CASE(T | V_LEAPFROG | V_PERIODIC1)
+        IPPLB_VAR_CASE(V_LEAPFROG | V_PERIODIC1)
+#undef IPPLB_VAR_CASE
+        default: rc = launch_fused3<480, 2, 2, 0>(ctx, A); break;
     }
     if (rc) return rc;
     rc = bins_plan(ctx, b, o, A.seg_cap);

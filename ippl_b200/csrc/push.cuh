@@ -9,15 +9,16 @@ namespace ipplb {
 // ------------------------------------------------------------------------------------------------
 // Gather (API-faithful): E_p = sum_p w_p * F(node_p), right fold like CIC.hpp:63-65.
 // ------------------------------------------------------------------------------------------------
-template <int NCOMP>
-__device__ __forceinline__ void gather_point(const MeshDev& m, const Cic& c,
-                                             const double* __restrict__ f, double out[NCOMP]) {
+// node(p) -> linear ghosted node index of stencil point p
+template <int NCOMP, typename NodeFn>
+__device__ __forceinline__ void gather_point_at(const double whi[3], NodeFn node, const double* __restrict__ f,
+                                                double out[NCOMP]) {
     double w[8];
     long id[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-        w[p]  = cic_weight(c.whi, p);
-        id[p] = cic_node(m, c.a, p) * NCOMP;
+        w[p]  = cic_weight(whi, p);
+        id[p] = node(p) * NCOMP;
     }
 #pragma unroll
     for (int d = 0; d < NCOMP; ++d) {
@@ -27,11 +28,16 @@ __device__ __forceinline__ void gather_point(const MeshDev& m, const Cic& c,
         out[d] = acc;
     }
 }
+template <int NCOMP>
+__device__ __forceinline__ void gather_point(const MeshDev& m, const Cic& c,
+                                             const double* __restrict__ f, double out[NCOMP]) {
+    gather_point_at<NCOMP>(c.whi, [&](int p) { return cic_node(m, c.a, p); }, f, out);
+}
 
 struct PushDev {
     int kind, do_kick2, do_kick1, do_drift, do_bc;
     double dt, c;          // c = 0.5*dt
-    double lo[3], ext[3], mid[3];  // periodic BC constants (ParticleBC.h:43-52)
+    double lo[3], ext[3], mid[3], hext[3];  // periodic BC constants (ParticleBC.h:43-52); hext = ext / 2
     double p_origin[3], p_half_len[3], cxy, cz, alpha, Bext, DrInv, aB;  // penning
 };
 
@@ -78,8 +84,21 @@ __device__ __forceinline__ void push_particle(const PushDev& P, double r[3], dou
     }
     if (P.do_bc) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) r[d] = periodic_wrap(r[d], P.ext[d], P.mid[d]);
+        for (int d = 0; d < 3; ++d) r[d] = periodic_wrap(r[d], P.ext[d], P.mid[d], P.hext[d]);
     }
+}
+
+// the steady-state leapfrog step with every sub-step on (kick2, kick1, drift, periodic BC): the same operations in the
+// same order as push_particle, without the flag tests
+__device__ __forceinline__ void push_leapfrog_full(const PushDev& P, double r[3], double p[3], const double E[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) p[d] = dsub(p[d], dmul(P.c, E[d]));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) p[d] = dsub(p[d], dmul(P.c, E[d]));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) r[d] = dadd(r[d], dmul(P.dt, p[d]));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) r[d] = periodic_wrap(r[d], P.ext[d], P.mid[d], P.hext[d]);
 }
 
 inline PushDev make_push_dev(const ipplb_mesh* mesh, const ipplb_push* push) {
@@ -99,6 +118,7 @@ inline PushDev make_push_dev(const ipplb_mesh* mesh, const ipplb_push* push) {
         P.lo[d]  = lo;
         P.ext[d] = hi - lo;
         P.mid[d] = (lo + hi) / 2;
+        P.hext[d] = P.ext[d] * 0.5;
     }
     if (push->kind == IPPLB_PUSH_PENNING) {
         const double l2 = std::pow(push->length[2], 2);

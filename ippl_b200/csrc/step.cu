@@ -29,12 +29,15 @@ int ipplb_pic_step(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* pus
         IPPLB_REQUIRE(bins && scratch, "pic_step: the fused step needs bins and a second particle bundle");
         if ((rc = ipplb_field_fill(ctx, rho, cells, 0.0))) return rc;
         const long n = p->n;
-        if ((rc = ipplb_bins_step(ctx, bins, push, p, scratch, efield, rho, nullptr, 0, nullptr, nullptr)))
-            return rc;
+        // without the BC on the whole periodic domain a leaver would be dropped silently (no exit buffer here)
+        IPPLB_REQUIRE(push->do_bc && mask == 7, "pic_step: the fused single-rank step needs the periodic BC on the whole domain");
+        // the rank owns the whole periodic domain: ipplb_bins_step aliases ghost nodes to the opposite interior layer
+        // itself, so E needs no fillHalo before the step and rho no accumulateHalo after it
+        if ((rc = ipplb_bins_step(ctx, bins, push, p, scratch, efield, rho, nullptr, 0, nullptr, nullptr))) return rc;
         swap_bundles(p, scratch);
         p->n       = n;  // single rank, periodic: nobody leaves (ipplb_bins_status reports the device truth)
         scratch->n = 0;
-        return ipplb_halo_accumulate_periodic(ctx, mesh, rho, 1, mask);
+        return IPPLB_OK;
     }
     if ((rc = ipplb_gather_push(ctx, mesh, push, p, efield))) return rc;
     if ((rc = ipplb_field_fill(ctx, rho, cells, 0.0))) return rc;

@@ -12,7 +12,9 @@ class IpplbError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libippl_b200.so")
+    # IPPLB_LIB_VARIANT=<name> loads libippl_b200_<name>.so (A/B builds made by scripts/build_variants.sh; experiments only)
+    v = os.environ.get("IPPLB_LIB_VARIANT")
+    return os.path.join(_HERE, f"libippl_b200_{v}.so" if v else "libippl_b200.so")
 
 
 def lib():

@@ -343,8 +343,11 @@ def test_landau_energy_history_vs_oracle(ctx, mode):
         ctx.field_density(mg, rho, cell, Q / size)
 
     def solve_and_dump(t):
+        if mode == 2:
+            ef.fill_(float("nan"))   # the fused single-rank step must not read E's ghost layers (periodic aliasing)
         sol.solve(rho, ef)
-        ctx.halo_fill_periodic(mg, ef, 3)
+        if mode != 2:
+            ctx.halo_fill_periodic(mg, ef, 3)
         e2, emax = ctx.field_ex_stats(mg, ef)
         hist.append((t, e2 * cell, emax))
 
@@ -463,8 +466,11 @@ def test_full_size_properties(ctx):
         bins.step(push, pb, sc, ef, rho)
         nloc, ntail, nexit, flags = bins.status()
         assert nloc == n and nexit == 0 and (flags & 7) == 0 and ntail < n // 100
-        assert float((rho - rho_b).norm()) / float(rho_b.norm()) < 1e-12
-        ctx.halo_accumulate_periodic(mg, rho)
+        ctx.halo_accumulate_periodic(mg, rho_b)
+        ctx.halo_accumulate_periodic(mg, rho)   # adds zeros: the fused step has aliased the ghost nodes itself
+        e3 = [k + 2 for k in nr][::-1]
+        ia, ib_ = (f.view(*e3)[1:-1, 1:-1, 1:-1] for f in (rho, rho_b))
+        assert float((ia - ib_).norm()) / float(ib_.norm()) < 1e-12
         assert abs((Q - ctx.field_sum(mg, rho)) / Q) < 1e-10
     st, cp, ct = bins.tables()
     assert int(ct.sum()) + ntail == n and np.all(ct <= cp)
@@ -479,6 +485,15 @@ def test_full_size_properties(ctx):
     assert bins.compact(pb, out) == n
     assert abs(float(out.arr["px"][:n].sum()) - float(parts.arr["px"][:n].sum())) < 1e-6 * n ** 0.5
     bins.close()
+
+
+def _rho_err_periodic(rho_t, want, mo):
+    """relative L2 of the INTERIOR of a fused-step rho against the oracle's scatter + periodic accumulate: on a whole
+    periodic domain ipplb_bins_step aliases ghost nodes to the opposite interior layer itself (its ghost layers stay
+    untouched), which equals the reference's scatter followed by accumulateHalo on the interior"""
+    w = want.copy()
+    oracle.halo_periodic(w, mo.ext, 1, 1, (1, 1, 1), "accumulate")
+    return rel_l2(oracle.interior(rho_t.cpu().numpy(), mo), oracle.interior(w, mo))
 
 
 def _canon(cols):
@@ -531,6 +546,7 @@ def test_fused_step_vs_unfused_and_oracle(ctx, ppc, kind, vscale):
     P = [np.clip(vscale * p, -9.0, 9.0) for p in normal_velocities(n, seed=7)]
     dt = 0.5 * h[0]
     ef = 0.2 * rng.normal(size=mg.cells * 3)   # (a particle must not cross half the domain per step: PeriodicBC)
+    oracle.halo_periodic(ef, mo.ext, 3, 1, (1, 1, 1), "fill")   # E as BareField::fillHalo leaves it (the fused step aliases)
     q = -0.37
     push = ib.leapfrog_push(dt) if kind == "leapfrog" else ib.penning_push(dt, (0, 0, 0), L)
     pa = ib.Particles.from_host(R, P, ctx.device, q=q)   # reference: unfused kernels (bit-exact vs the oracle)
@@ -553,7 +569,7 @@ def test_fused_step_vs_unfused_and_oracle(ctx, ppc, kind, vscale):
         out = ib.Particles(n, ctx.device)
         assert bins.compact(pb, out) == n
         assert np.array_equal(_canon(out.host()), _canon(Ro))
-        assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+        assert _rho_err_periodic(rho, want, mo) <= TOL_SUM
     bins.close()
 
 
@@ -572,6 +588,7 @@ def test_fused_step_overflow_tail_and_append(ctx):
     R = [np.clip(rng.normal(L / 2, L / 10, n + n_add), 0, np.nextafter(L, 0)) for _ in range(3)]
     P = [p + 6.0 for p in normal_velocities(n + n_add, seed=8)]
     ef = 0.1 * rng.normal(size=mg.cells * 3)
+    oracle.halo_periodic(ef, mo.ext, 3, 1, (1, 1, 1), "fill")
     push = ib.leapfrog_push(0.5 * h[0])
     pa = ib.Particles.from_host(R, P, ctx.device, q=1.0)
     cap = 2 * (n + n_add)
@@ -596,7 +613,7 @@ def test_fused_step_overflow_tail_and_append(ctx):
         out = ib.Particles(n + n_add, ctx.device)
         assert bins.compact(pb, out) == n + n_add
         assert np.array_equal(_canon(out.host()), _canon(Ro))
-        assert rel_l2(rho.cpu().numpy(), want) <= TOL_SUM
+        assert _rho_err_periodic(rho, want, mo) <= TOL_SUM
     assert saw_tail, "the drifting blob was meant to overflow some buckets"
     bins.close()
 
@@ -734,6 +751,7 @@ def test_host_batches_pipeline_vs_oracle(ctx):
     for k in range(nb):
         got = [a.numpy() for a in host[k]]
         assert np.array_equal(_canon(got), _canon(want_p[k])), f"batch {k}"
-        assert rel_l2(rho_host[k].numpy(), want_rho[k]) <= TOL_SUM, f"batch {k}"
+        # the fused single-rank step aliases ghost nodes to the interior itself: compare the interior
+        assert rel_l2(oracle.interior(rho_host[k].numpy(), mo), oracle.interior(want_rho[k], mo)) <= TOL_SUM, f"batch {k}"
     for b in slots_b:
         b.close()
