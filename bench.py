@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- particles/s per PIC step (scatter + push + gather) of the alpine LandauDamping hot path.
+"""bench.py -- particles/s per PIC step (scatter + push + gather) of the alpine mini-apps' hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a, through the C-ABI)
-  python bench.py --impl reference [...]                         the reference algorithm on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config landau|bumpontail|penning]   our arm (CUDA, sm_100a, C-ABI)
+  python bench.py --impl reference [...]                                                     the reference algorithm on the host cores
 
-Workload (BASELINE.json configs[1]): LandauDamping, 128^3 cells and 2^27 fp64 particles PER GPU
-(weak scaling: the mesh doubles along x, y, z as N = 2, 4, 8; FieldLayout decomposition), CIC,
-LeapFrog.  A "step" is one pass of the owned path: fillHalo(E) -> rho = 0 -> ONE fused kernel (gather E +
-kick + kick + drift + periodic BC + re-bucketing + charge deposit, ipplb_bins_step) -> [NCCL migration of
-the leavers, N > 1] -> accumulateHalo(rho).  --mode 1 runs the unfused baseline (gather_push, counting sort,
-sorted scatter).
-The FFT field solve is a non-owned stage: it is run once before the timed region to produce a
-self-consistent E and is timed separately (`solve_ms`).  Inputs (6.4 GB of particles) are far larger
-than the 126 MB L2, so no explicit flush is needed between iterations.
+Default workload (BASELINE.json configs[1], the one the metric is quoted on): LandauDamping, 128^3 cells and 2^27 fp64
+particles PER GPU (weak scaling: the mesh doubles along x, y, z as N = 2, 4, 8; FieldLayout decomposition), CIC, LeapFrog.
+A "step" is one pass of the owned path:
+  N = 1: rho = 0 -> ONE fused kernel (gather E + kick + kick + drift + periodic BC + re-bucketing + charge deposit; the
+         periodic fillHalo(E) / accumulateHalo(rho) are folded into it: ghost nodes alias the opposite interior layer);
+  N > 1: fillHalo(E) over NVLink -> rho = 0 -> the fused kernel with the ownership test -> migration of the leavers ->
+         accumulateHalo(rho).
+--config bumpontail = BASELINE.json configs[3] (512^3 mesh held fixed, 2^29 particles per GPU), --config penning =
+configs[2] (256^3 mesh, 2^30 particles over the GPUs, ORB repartition before the timed region, Boris-type push).
+The FFT field solve is a non-owned stage: it is run once before the timed region to produce a self-consistent E and is
+timed separately (`solve_ms`).  Inputs (6.4 GB of particles per GPU) are far larger than the 126 MB L2: no flush needed.
+The mini-app driver itself (initial condition, ORB, step, parity check, end-to-end variants) is ippl_b200/app.py.
 """
 import argparse
 import json
@@ -27,10 +30,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "particles/s per PIC step (scatter+push+gather), LandauDamping"
 UNIT = "particles/s"
 BYTES_PER_PARTICLE_STEP = 120  # gather+push 96 B + scatter 24 B (uniform scalar charge; 32 with a q array)
-BYTES_PER_CELL_STEP = 40      # rho zero + rho write + E read
+BYTES_PER_CELL_STEP = 40       # rho zero + rho write + E read
 
 
 def peaks():
@@ -39,6 +41,19 @@ def peaks():
         p = json.load(open(path))
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, read from the committed summary of
+    an `ncu --set full` capture of this workload (profiles/r2_fused_traffic.json, written by scripts/ncu_traffic.py from
+    the .ncu-rep); None when there is no capture for this kernel."""
+    path = os.path.join(ROOT, "profiles", "r2_fused_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    t = json.load(open(path))
+    if kernel_substr not in t.get("kernel", ""):
+        return None, None
+    return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), {k: t.get(k) for k in ("kernel", "commit", "command", "file")}
 
 
 class ClockSampler:
@@ -52,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -80,68 +95,97 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def workload(n_gpus):
-    """Global mesh for N GPUs (128^3 cells per GPU) and particles per GPU."""
-    dims = [128, 128, 128]
-    v, d = n_gpus, 0
-    while v > 1:
-        dims[d] *= 2
-        v //= 2
-        d = (d + 1) % 3
-    return tuple(dims), 1 << 27
+def config_dict(w, world, bins):
+    ng, n_local = w["ng"], w["n_local"]
+    n_total = n_local * world
+    return {"workload": f"{w['label']} {ng[0]}x{ng[1]}x{ng[2]} mesh, {n_local} particles/GPU fp64, CIC, "
+                        f"{'LeapFrog' if w['push'] == 'leapfrog' else 'Boris-type kicks (PenningTrap LeapFrogStep)'}",
+            "particles_total": n_total, "ppc": n_total / (ng[0] * ng[1] * ng[2]),
+            "decomposition": f"FieldLayout {world} rank(s)" + (", ORB repartition before the timed region"
+                                                              if w["name"] == "penning" and world > 1 else ""),
+            "l2": f"inputs ({48 * n_local / 1e9:.1f} GB/GPU) exceed L2; no flush needed",
+            "sort": "none: single-pass fused step on per-tile buckets" if bins else "counting sort by cell every step",
+            "solve": "excluded (non-owned cuFFT stage)", "charge": "uniform scalar q (24 B/particle scatter)"}
 
 
-def cpu_baseline_run(n_sample, steps, warmup):
-    """The reference algorithm (oracle port, OpenMP, atomic scatter like Kokkos-OpenMP) on the host
-    cores: scatter + push + gather per step on a bounded sample of the workload (same 128^3 mesh)."""
+# ---- reference arm: the reference algorithm on the host cores --------------------------------------------------------
+def cpu_run(w, n_sample, steps, warmup, threads=None):
+    """The reference algorithm (oracle port: OpenMP, atomic scatter like Kokkos-OpenMP, three-kernel leapfrog, per-
+    dimension periodic wrap) on a sample of the workload: same mesh, same distributions, `n_sample` particles."""
     import oracle
-    nr = (128, 128, 128)
-    L = 4 * np.pi
-    h = [L / k for k in nr]
-    m = oracle.Mesh.make(nr, (0, 0, 0), h)
-    rng = np.random.default_rng(42)
-    R = [rng.uniform(0, L, n_sample) for _ in range(3)]
-    P = [rng.normal(size=n_sample) for _ in range(3)]
+    if threads:
+        oracle.set_num_threads(threads)   # torchrun exports OMP_NUM_THREADS=1: set the thread count explicitly
+    ng, h, L = w["ng"], w["h"], w["Lg"]
+    m = oracle.Mesh.make(ng, (0, 0, 0), h)
+    kinds, par = w["dist"]
+    R = []
+    for d in range(3):
+        if kinds[d] == 1:
+            R.append(oracle.sample_landau(n_sample, par[2 * d], par[2 * d + 1], 0.0, L[d], 42 + d))
+        elif kinds[d] == 0:
+            R.append(oracle.sample_landau(n_sample, 0.0, 1.0, 0.0, L[d], 42 + d))      # alpha = 0: uniform
+        else:
+            R.append(np.clip(par[2 * d] + par[2 * d + 1] * oracle.sample_normal(n_sample, 42 + d), 1e-9, L[d]))
+    P = []
+    for d in range(3):
+        p = oracle.sample_normal(n_sample, 52 + d)
+        lo = 0
+        for i, (mu, sd, frac) in enumerate(w["vel"]):
+            hi = n_sample if i == len(w["vel"]) - 1 else lo + int(frac * n_sample)
+            p[lo:hi] = mu[d] + sd[d] * p[lo:hi]
+            lo = hi
+        P.append(p)
     E = [np.zeros(n_sample) for _ in range(3)]
-    ef = 0.05 * rng.normal(size=m.ext[0] * m.ext[1] * m.ext[2] * 3)
+    cells = m.ext[0] * m.ext[1] * m.ext[2]
+    ef = 0.05 * np.sin(np.arange(cells * 3) * 1e-3)   # smooth synthetic E (the solve is a non-owned stage)
     rho = oracle.field_zeros(m)
-    dt, q = 0.5 * h[0], -(L ** 3) / n_sample
+    dt, q = w["dt"], -(L[0] * L[1] * L[2]) / n_sample
     for _ in range(warmup):
         oracle.pic_step_nosolve(m, R, P, E, q, dt, ef, rho)
     t0 = time.perf_counter()
     for _ in range(steps):
         oracle.pic_step_nosolve(m, R, P, E, q, dt, ef, rho)
-    dt_s = (time.perf_counter() - t0) / steps
-    return n_sample / dt_s, dt_s, oracle.num_threads()
+    sec = (time.perf_counter() - t0) / steps
+    return n_sample / sec, sec, oracle.num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 1 << 24
-    value, sec, cores = cpu_baseline_run(n_sample, args.steps, max(1, args.warmup))
-    sample = (f"2^24 of the 2^27 particles on the same 128^3 mesh, {args.steps} steps; oracle port of the "
-              f"reference algorithm (OpenMP, atomic scatter), solve excluded")
+    from ippl_b200 import app
+    world = args.gpus
+    w = app.workload(args.config, world, args.log2_particles)
+    # N = 1: the whole workload (2^27 particles).  N > 1: the N-GPU mesh with one GPU's share of the particles (a bounded
+    # sample: the host's throughput per particle does not depend on how many there are), all host cores either way.
+    n_sample = min(w["n_local"], 1 << 27)
+    steps, warmup = args.steps, max(1, min(args.warmup, 2))
+    cores = os.cpu_count() or 1
+    value, sec, used = cpu_run(w, n_sample, steps, warmup, threads=cores)
+    whole = world == 1 and n_sample == w["n_local"]
+    sample = (f"{'the whole workload: ' if whole else 'bounded sample: '}{n_sample} of the {w['n_local'] * world} particles on the full "
+              f"{w['ng'][0]}x{w['ng'][1]}x{w['ng'][2]} mesh, {w['label']} initial condition, {steps} steps after {warmup} warm-up; "
+              f"OpenMP restatement of the reference algorithm (atomic scatter, three-pass leapfrog), solve excluded")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "alpine LandauDamping 128^3 mesh, CIC, LeapFrog (bounded sample, CPU)",
-                   "sample_particles": n_sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (initial condition sampled on the host)",
+        "config": config_dict(w, world, True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ---- our arm ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log2-particles", type=int, default=27, help="particles per GPU = 2^k (default: the metric's 2^27)")
-    ap.add_argument("--mode", type=int, default=2, help="1: push + counting sort + sorted scatter; 2: fused two-pass step")
+    ap.add_argument("--config", default="landau", choices=["landau", "bumpontail", "penning"])
+    ap.add_argument("--log2-particles", type=int, default=None, help="particles per GPU = 2^k (default: the config's own)")
+    ap.add_argument("--mode", type=int, default=2, help="2: fused single-pass step (default); 1: push + counting sort + sorted scatter")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -152,6 +196,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ippl_b200 as ib
+    from ippl_b200 import app
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -167,97 +212,13 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
 
-    ng, n_local = workload(world)
-    n_local = 1 << args.log2_particles
-    L = 4 * np.pi  # Landau: rmax = 2*pi/kw, kw = 0.5 -- per 128 cells, so h stays 4*pi/128
-    h = [L / 128.0] * 3
-    origin = (0.0, 0.0, 0.0)
-    layout = ib.Layout(ng, world)
-    mesh = layout.mesh(rank, origin, h)
-    if world > 1:
-        ctx.set_layout(layout, origin, h)
-    dt = min(0.05, 0.5 * min(h))
-    n_total = n_local * world
-    Lg = [ng[d] * h[d] for d in range(3)]
-    q = -(Lg[0] * Lg[1] * Lg[2]) / n_total
-
-    # ---- synthetic particles, created on the device the way LandauDampingManager::initializeParticles does
-    # (demos/alpine/LandauDampingManager.h:159-254): inverse-transform sampling of 1 + 0.05 cos(0.5 x) per dimension
-    # inside the rank's region (ipplb_sample_positions), velocities N(0,1) (ipplb_sample_normal), seed 42 + 100 rank
-    cap = int(n_local * 1.25)  # bucket slack + tail of the fused store; migration head-room on N > 1
-    g = torch.Generator(device=dev)
-    g.manual_seed(42 + 100 * rank)
-    parts = ib.Particles(cap, dev, q=q)
-    scratch = ib.Particles(cap, dev)
-    regs = layout.regions(origin, h)
-    reg = regs[rank]
-    landau = ib.Dist.make([1, 1, 1], [0.05, 0.5] * 3)
-    counts, ubounds = ib.sample_counts(landau, [0.0] * 3, Lg, regs, n_total)
-    assert sum(counts) == n_total and abs(counts[rank] - n_local) <= 1, counts
-    n_mine = counts[rank]
-    ctx.sample_positions(landau, ubounds[rank][:3], ubounds[rank][3:], 42 + 100 * rank, 0, n_mine, parts)
-    ctx.sample_normal([0.0] * 3, [1.0] * 3, 42 + 100 * rank, 0, n_mine, parts)
-    for d, k in enumerate("xyz"):   # Newton's 1e-12 tolerance may leave a sample a hair outside the region
-        parts.arr[k][:n_mine].clamp_(min=float(np.nextafter(reg[d], np.inf)), max=float(reg[3 + d]))
-    parts.n = n_mine
-    off = ctx.offsets_buffer(mesh)
-    bins = ib.Bins(ctx, mesh, cap) if args.mode == 2 else None
-    rho, ef = ctx.field(mesh), ctx.field(mesh, 3)
-
-    # ---- self-consistent E from one solve (single GPU); synthetic smooth E on N > 1 (solver is non-owned)
-    solve_ms = None
-    if world == 1:
-        ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho, end=n_mine)  # only the sampled slots
-        ctx.halo_accumulate_periodic(mesh, rho)
-        cell = h[0] * h[1] * h[2]
-        ctx.field_density(mesh, rho, cell, q * n_total / (Lg[0] * Lg[1] * Lg[2]))
-        sol = ib.Poisson(ctx, mesh)
-        sol.solve(rho, ef)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sol.solve(rho, ef)
-        e1.record()
-        torch.cuda.synchronize()
-        solve_ms = e0.elapsed_time(e1)
-        sol.close()
-    else:
-        ef.normal_(0.0, 0.02, generator=g)
-
-    def fill_e_halo():
-        if world > 1:
-            ctx.halo_exchange(ef, 3, "fill")
-        else:
-            ctx.halo_fill_periodic(mesh, ef, 3)
-
-    exit_cap = max(n_local // 16, 1 << 16)
-    exit_buf = torch.zeros(6 * exit_cap, dtype=torch.float64, device=dev) if (bins is not None and world > 1) else None
-    region = list(reg) if world > 1 else None
-
-    def step(first=False):
-        push = ib.leapfrog_push(dt, kick2=0 if first else 1)
-        if bins is not None and world == 1:
-            # one rank owns the whole periodic domain: the fused kernel aliases ghost nodes itself, which replaces the
-            # fillHalo(E) / accumulateHalo(rho) passes (HaloCells::applyPeriodicSerialDim)
-            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=2, bins=bins)
-            return
-        fill_e_halo()
-        if bins is not None:
-            # fused step with ownership test -> NCCL migration (arrivals appended + deposited) -> accumulateHalo
-            ctx.field_fill(rho, 0.0)
-            bins.step(push, parts, scratch, ef, rho, exit_buf=exit_buf, region=region)
-            bins.migrate(parts, exit_buf, rho)
-            ctx.halo_exchange(rho, 1, "accumulate")
-        elif world == 1:
-            ctx.pic_step(mesh, push, parts, scratch, off, ef, rho, do_sort=args.mode)
-        else:
-            ctx.gather_push(mesh, push, parts, ef)
-            ctx.update(parts)
-            ctx.sort_by_cell(mesh, parts, scratch, off)
-            parts.arr, scratch.arr = scratch.arr, parts.arr
-            ctx.field_fill(rho, 0.0)
-            ctx.scatter_sorted(mesh, parts.n, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, off, rho)
-            ctx.halo_exchange(rho, 1, "accumulate")
+    run = app.MiniApp(ctx, app.workload(args.config, world, args.log2_particles), rank, world, mode=args.mode,
+                      dist=dist if world > 1 else None)
+    w = run.w
+    n_local, n_total = w["n_local"], w["n_local"] * world
+    run.initialise()                # particles sampled on the device, [ORB], first solve, bucketing
+    mesh, bins = run.mesh, run.bins
+    parity = run.parity_check() if world > 1 else None     # one small oracle-checked multi-rank step (not timed)
 
     def barrier():
         torch.cuda.synchronize()
@@ -265,185 +226,104 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if bins is not None:
-        bins.build(parts, scratch)                # initial bucketing (the fused step keeps the particles bucketed)
-    else:
-        ctx.sort_by_cell(mesh, parts, scratch, off)
-    parts.arr, scratch.arr = scratch.arr, parts.arr
-    step(first=True)
+    run.step(first=True)
     for _ in range(args.warmup - 1):
-        step()
+        run.step()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
+    if bins is not None:
+        bins.set_timing(True)
     l0 = ctx.launches
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
     for _ in range(args.steps):
-        step()
+        run.step()
     t1.record()
     barrier()
     launches = ctx.launches - l0
     clocks = sampler.stop() if rank == 0 else None
     ms = t0.elapsed_time(t1)
-    n_now = bins.status()[0] if bins is not None else parts.n
+    kernel_ms = bins.kernel_ms() if bins is not None else []
+    if bins is not None:
+        bins.set_timing(False)
+    st = run.status()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
-        c = torch.tensor([n_now], device=dev, dtype=torch.int64)
+        c = torch.tensor([st["n_local"], st["flags"] & 7], device=dev, dtype=torch.int64)
         dist.all_reduce(c)
-        assert int(c[0]) == n_total, "particles lost in migration"
+        assert int(c[0]) == n_total and int(c[1]) == 0, f"particles lost in migration: {c.tolist()} of {n_total}"
+    else:
+        assert st["n_local"] == run.n_mine and (st["flags"] & 7) == 0 and st["n_exit"] == 0, f"fused store lost particles: {st}"
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
-    # ---- per-kernel timing of the same step (CUDA events on the launching stream) -----------------
-    def timed(fn, reps=3):
-        best = []
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            torch.cuda.synchronize()
-            best.append(a.elapsed_time(b))
-        return float(np.mean(best))
-
-    kern = {}
-    push = ib.leapfrog_push(dt)
+    # ---- roofline of the dominant kernel: algorithmic bytes per launch / its CUDA-event time INSIDE the timed region --
     peak, peak_src = peaks()
     ncell_int = mesh.nl[0] * mesh.nl[1] * mesh.nl[2]
+    kern = dict(run.phase_ms())     # per-phase CUDA-event times of one more step (outside the timed region)
     if bins is not None:
-        nloc, ntail, nexit, flags = bins.status()
-        assert (flags & 7) == 0 and (world > 1 or (nloc == n_mine and nexit == 0)), f"fused store lost particles: {bins.status()}"
-        if world == 1:
-            kern["fused_step"] = timed(lambda: bins.step(push, parts, scratch, ef, rho), reps=5)
-        else:
-            def fused_and_migrate():
-                bins.step(push, parts, scratch, ef, rho, exit_buf=exit_buf, region=region)
-                bins.migrate(parts, exit_buf, rho)
-            t_all = timed(fused_and_migrate, reps=3)
-            kern["fused_step+migrate"] = t_all
-            kern["fused_step"] = t_all  # (the migration part is host-synchronous; see halo/migrate split below)
-        kern["rho_zero"] = timed(lambda: ctx.field_fill(rho, 0.0))
-        kern["halo_accumulate"] = timed(lambda: ctx.halo_accumulate_periodic(mesh, rho))
-        kern["halo_fill_E"] = timed(fill_e_halo)
-        rk = "fused_step"
-        # the fused kernel does all per-particle work of the step: SURVEY 8d algorithmic bytes, 120 B/particle
-        # (96 gather+push, 24 scatter with a uniform scalar charge) + E read and rho written once per cell
-        alg_bytes = {rk: float(BYTES_PER_PARTICLE_STEP) * nloc + 32.0 * ncell_int}
-        dom = rk
-        tail_frac = ntail / max(nloc, 1)
+        rk = "fused_step3_kernel"
+        ms_launch = float(np.mean(kernel_ms))
+        alg = float(BYTES_PER_PARTICLE_STEP) * st["n_local"] + 32.0 * ncell_int
+        traffic, traffic_src = (profiled_traffic(rk) if (world == 1 and args.config == "landau" and n_local == 1 << 27)
+                                else (None, None))
+        kern[rk] = ms_launch
+        how = f"mean of {len(kernel_ms)} CUDA-event pairs around the kernel alone, inside the timed region"
     else:
-        kern["gather_push"] = timed(lambda: ctx.gather_push(mesh, push, parts, ef))
-        if world > 1:
-            ctx.update(parts)
-
-        def do_sort():
-            ctx.sort_by_cell(mesh, parts, scratch, off)
-            parts.arr, scratch.arr = scratch.arr, parts.arr
-        kern["sort_by_cell"] = timed(do_sort)
-        kern["scatter_sorted"] = timed(lambda: ctx.scatter_sorted(mesh, parts.n, parts.arr["x"], parts.arr["y"],
-                                                                  parts.arr["z"], q, off, rho))
-        kern["scatter_atomic"] = timed(lambda: ctx.scatter(mesh, parts.arr["x"], parts.arr["y"], parts.arr["z"], q, rho))
-        dom = max(("gather_push", "sort_by_cell", "scatter_sorted"), key=lambda k: kern[k])
-        alg_bytes = {"gather_push": 96.0 * parts.n + 24.0 * mesh.cells,
-                     "scatter_sorted": 24.0 * parts.n + 8.0 * mesh.cells,
-                     "sort_by_cell": 0.0}
-        # unfused path: the roofline object describes the gather+push kernel (96 of the 120 B/particle); the
-        # sort is pure overhead above the algorithmic bytes and is listed beside it
-        rk = "gather_push"
-        tail_frac = None
-    achieved = alg_bytes[rk] / (kern[rk] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one fused_step3_kernel launch on this exact workload, from the
-    # committed `ncu --set full` capture (profiles/r1_fused3_ncu_full.md: 6.603 GB + 6.454 GB); null otherwise
-    traffic = 13.056e9 if (bins is not None and world == 1 and args.log2_particles == 27) else None
+        rk = "gather_push_kernel"
+        ms_launch = kern["gather_push"]
+        alg = 96.0 * st["n_local"] + 24.0 * mesh.cells
+        traffic, traffic_src, how = None, None, "CUDA events around one launch"
+    achieved = alg / (ms_launch * 1e-3) / 1e9
     step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * ncell_int
     step_achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
+    cfg = config_dict(w, world, bins is not None)
+    cfg["tail_fraction"] = st["n_tail"] / max(st["n_local"], 1)
+    cfg.update(run.extra_config())
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic (Landau initial condition sampled on the device)",
-        "config": {"workload": f"alpine LandauDamping {ng[0]}x{ng[1]}x{ng[2]} mesh, 2^{args.log2_particles} particles/GPU fp64, CIC, LeapFrog",
-                   "particles_total": n_total, "ppc": n_total / (ng[0] * ng[1] * ng[2]),
-                   "decomposition": f"FieldLayout {world} rank(s), 128^3 cells per GPU",
-                   "l2": "inputs (6.4 GB/GPU) exceed L2; no flush needed",
-                   "sort": ("none: single-pass fused step on per-tile buckets" if bins is not None
-                            else "counting sort by cell every step"),
-                   "tail_fraction": tail_frac, "solve": "excluded (non-owned cuFFT stage)",
-                   "charge": "uniform scalar q (24 B/particle scatter)"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (initial condition sampled on the device)",
+        "config": cfg, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes[rk], "ms_per_launch": kern[rk]},
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch, "ms_per_launch_how": how},
         "step_roofline": {"bytes_per_particle": BYTES_PER_PARTICLE_STEP, "achieved": step_achieved, "peak": peak,
                           "unit": "GB/s", "frac": step_achieved / peak},
-        "kernels_ms": kern, "dominant_kernel_by_time": dom, "solve_ms": solve_ms,
+        "kernels_ms": kern, "solve_ms": run.solve_ms,
     }
+    if parity is not None:
+        out["parity"] = parity
 
     if rank == 0 and not args.no_cpu and world == 1:
-        v, sec, cores = cpu_baseline_run(1 << 23, 2, 1)
+        v, sec, cores = cpu_run(w, 1 << 24, 3, 1, threads=os.cpu_count())
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "2^23 of the 2^27 particles on the same 128^3 mesh, 2 steps after 1 warm-up; "
-                                         "OpenMP restatement of the reference algorithm, solve excluded"}
+                               "sample": f"2^24 of the {n_local} particles on the same {w['ng'][0]}^3 mesh, same initial condition, 3 steps "
+                                         "after 1 warm-up; OpenMP restatement of the reference algorithm, solve excluded "
+                                         "(`--impl reference` times the whole workload)"}
 
-    # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), copies inside the timed region.
-    # ipplb_pic_step_host_batches streams independent batches (one batch = one step of the workload): upload of
-    # batch k+1, compute of batch k and download of batch k-1 overlap; the timed region covers whole batches
-    # including pipeline fill and drain.
-    if not args.no_e2e:
-        import ctypes as C
-        if world == 1:
-            lib = ib.lib()
-            if bins is not None:   # contiguous copy of the bucketed particles as the synthetic host input
-                bins.compact(parts, scratch)
-                parts.arr, scratch.arr = scratch.arr, parts.arr
-            nb_warm, nb = 2, 6
-            hostbuf = [[torch.empty(n_local, dtype=torch.float64).pin_memory() for _ in range(6)] for _ in range(2)]
-            for hs in hostbuf:
-                for hb, k in zip(hs, ib.Particles.NAMES):
-                    hb.copy_(parts.arr[k][:n_local])
-            rho_host = [torch.empty(mesh.cells, dtype=torch.float64).pin_memory() for _ in range(2)]
-            slots_p = [parts, ib.Particles(cap, dev, q=q)]
-            slots_s = [scratch, ib.Particles(cap, dev, q=q)]
-            slots_b = [bins if bins is not None else ib.Bins(ctx, mesh, cap), ib.Bins(ctx, mesh, cap)]
-            slots_r = [rho, ctx.field(mesh)]
-            pushs = ib.leapfrog_push(dt)
-
-            def run_batches(nbatch):
-                harr = (C.c_void_p * (6 * nbatch))(*[hostbuf[k & 1][a].data_ptr() for k in range(nbatch) for a in range(6)])
-                rarr = (C.c_void_p * nbatch)(*[rho_host[k & 1].data_ptr() for k in range(nbatch)])
-                PA = ib.lib_particles_array([p.struct() for p in slots_p])
-                SA = ib.lib_particles_array([p.struct() for p in slots_s])
-                BA = (C.c_void_p * 2)(*[b._h.value for b in slots_b])
-                RA = (C.c_void_p * 2)(*[r.data_ptr() for r in slots_r])
-                rc = lib.ipplb_pic_step_host_batches(ctx._h, C.byref(mesh), C.byref(pushs), C.c_long(n_local), nbatch, harr,
-                                                     C.c_double(q), C.c_void_p(ef.data_ptr()), rarr, PA, SA, BA, RA)
-                if rc:
-                    raise RuntimeError(lib.ipplb_last_error().decode())
-            run_batches(nb_warm)
-            barrier()
-            w0 = time.perf_counter()
-            run_batches(nb)
-            barrier()
-            e2e_ms = (time.perf_counter() - w0) * 1e3 / nb
-            # sanity: the batch came back complete (same particle multiset size, finite, inside the box)
-            xs = hostbuf[0][0]
-            assert bool(torch.isfinite(xs).all()) and float(xs.min()) >= 0.0 and float(xs.max()) <= Lg[0]
-            out["e2e"] = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT,
-                          "h2d_bytes_per_step": 48 * n_local, "d2h_bytes_per_step": 48 * n_local + 8 * mesh.cells,
-                          "ms_per_step": e2e_ms, "steps": nb,
-                          "what": "ipplb_pic_step_host_batches: per batch pinned host R,P -> device, bucket, fused step, "
-                                  "compact, R,P + rho -> host; upload / compute / download of consecutive batches overlap"}
-        else:
-            out["e2e"] = None
+    # ---- e2e: the same step through the C-ABI with HOST buffers, copies inside the timed region ----------------------
+    if not args.no_e2e and bins is not None:
+        e2e = run.e2e(steps=max(4, min(args.steps, 10)), barrier=barrier)
+        if world > 1:
+            t = torch.tensor([e2e["ms_per_step"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e["ms_per_step"] = float(t[0])
+        e2e["value"] = n_total / (e2e["ms_per_step"] * 1e-3)
+        e2e["unit"] = UNIT
+        out["e2e"] = e2e
+        if world == 1 and args.config == "landau":
+            out["e2e_particles_streamed"] = run.e2e_streamed(barrier)
 
     if rank == 0:
         print(json.dumps(out))
+    run.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

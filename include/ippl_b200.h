@@ -280,6 +280,11 @@ int ipplb_bins_compact(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* 
                        ipplb_particles* out);
 /* the same reduction as ipplb_particles_kinetic over the bucketed store (buckets + tail), no compaction needed */
 int ipplb_bins_kinetic(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* cur, double* out_host);
+/* Measurement (bench.py's roofline object): with timing on, every ipplb_bins_step brackets its fused kernel -- the kernel
+ * alone, not the table planning behind it -- with CUDA events on the context's stream (up to 256 launches after the
+ * last set_timing call).  ipplb_bins_kernel_ms synchronises the stream and returns the per-launch durations. */
+int ipplb_bins_set_timing(ipplb_bins* bins, int on);
+int ipplb_bins_kernel_ms(ipplb_ctx* ctx, ipplb_bins* bins, double* ms_out_host, int max_out, int* n_out);
 /* read-only access for tests: copies start/cap/count of the current buffer to host arrays [ntiles] */
 int ipplb_bins_ntiles(const ipplb_bins* bins);
 int ipplb_bins_tables(ipplb_ctx* ctx, ipplb_bins* bins, int* start_host, int* cap_host, int* count_host);
@@ -373,6 +378,14 @@ int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push
                         double* const host_arrays[6], double q_scalar, const double* efield_dev,
                         double* rho_host, ipplb_particles* dev, ipplb_particles* scratch,
                         ipplb_bins* bins, double* rho_dev);
+
+/* Steady-state end-to-end step: the particles stay bucketed on the device (the reference's ParticleAttrib views are
+ * device allocations too); per call the ghosted E field comes from HOST memory and the ghosted rho goes back to HOST memory
+ * -- what a host-side (or non-owned) field solve exchanges with the particle path every step.  Single rank that owns the
+ * whole periodic domain (ipplb_pic_step with do_sort = 2 in between).  Host pointers should be pinned.  Synchronises. */
+int ipplb_pic_step_host_fields(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
+                               ipplb_particles* scratch, ipplb_bins* bins, const double* efield_host, double* rho_host,
+                               double* efield_dev, double* rho_dev);
 
 /* The same through a sequence of `nbatch` independent host batches (host_arrays[nbatch][6], rho_host[nbatch] or
  * NULL): upload of batch k+1, compute of batch k and download of batch k-1 overlap (three streams, two device

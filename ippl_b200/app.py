@@ -1,0 +1,314 @@
+"""Host-side mini-app driver on the C-ABI: the alpine managers' run loop for the hot path (what bench.py times).
+
+Mirrors, for one rank of N: AlpineManager::pre_run / the managers' initializeParticles (device-side sampling per rank
+region, demos/alpine/LandauDampingManager.h:159-254, PenningTrapManager.h:140-229, BumponTailInstabilityManager.h:
+180-300), LoadBalancer's first repartition on the analytic density (LandauDampingManager.h:188-199 +
+demos/alpine/LoadBalancer.hpp:54-161), and LeapFrogStep (LandauDampingManager.h:265-320, PenningTrapManager.h:231-337)
+as ONE fused step per time step.  The field solve is the non-owned cuFFT stage: run once here for a self-consistent E.
+torch owns device memory and the process group; nothing in here computes on the CPU.
+"""
+import math
+
+import numpy as np
+
+import ippl_b200 as ib
+
+
+def workload(config, n_gpus, log2n=None):
+    """Global mesh, physics constants and particles per GPU of BASELINE.json's configs on N GPUs."""
+    w = {"name": config}
+    if config == "landau":      # configs[1]: 128^3 cells and 2^27 particles per GPU, the mesh doubles with N (weak scaling)
+        dims, v, d = [128, 128, 128], n_gpus, 0
+        while v > 1:
+            dims[d] *= 2
+            v //= 2
+            d = (d + 1) % 3
+        h = 4 * math.pi / 128.0   # rmax = 2 pi / kw, kw = 0.5, per 128 cells (LandauDampingManager.h:81-101)
+        w.update(ng=tuple(dims), h=[h] * 3, n_local=1 << (log2n or 27), push="leapfrog",
+                 dist=([1, 1, 1], [0.05, 0.5] * 3), vel=[([0.0] * 3, [1.0] * 3, 1.0)],
+                 label="alpine LandauDamping", metric="particles/s per PIC step (scatter+push+gather), LandauDamping")
+    elif config == "bumpontail":  # configs[3]: 512^3 mesh held fixed, 2^29 particles per GPU (4 ... 32 particles per cell)
+        kb = 0.21
+        h = 2 * math.pi / kb / 512.0   # BumponTailInstabilityManager.h:110-135
+        sd = 1.0 / math.sqrt(2.0)
+        w.update(ng=(512, 512, 512), h=[h] * 3, n_local=1 << (log2n or 29), push="leapfrog",
+                 dist=([0, 0, 1], [0.01, kb] * 3), vel=[([0.0] * 3, [sd] * 3, 0.9), ([0.0, 0.0, 4.0], [sd] * 3, 0.1)],
+                 label="alpine BumponTailInstability", metric="particles/s per PIC step (scatter+push+gather), BumponTail")
+    elif config == "penning":     # configs[2]: 256^3 mesh, 2^30 particles over the GPUs (2^27 per GPU at N = 8), ORB
+        h = 20.0 / 256.0              # PenningTrapManager.h:56-74
+        w.update(ng=(256, 256, 256), h=[h] * 3, n_local=(1 << 30) // n_gpus if log2n is None else 1 << log2n,
+                 push="penning", dist=([2, 2, 2], [10.0, 3.0, 10.0, 1.0, 10.0, 4.0]), vel=[([0.0] * 3, [1.0] * 3, 1.0)],
+                 label="alpine PenningTrap", metric="particles/s per PIC step (scatter+push+gather), PenningTrap")
+    else:
+        raise ValueError(f"unknown config {config}")
+    w["Lg"] = [w["ng"][d] * w["h"][d] for d in range(3)]
+    # dt: min(0.05, 0.5 h) (Landau / BumponTail), 0.5 * L / 2048 (PenningTrapManager.h:66-68)
+    w["dt"] = min(0.05, 0.5 * min(w["h"])) if config != "penning" else 0.5 * 20.0 / 2048.0
+    return w
+
+
+class MiniApp:
+    def __init__(self, ctx, w, rank, world, mode=2, dist=None, seed=42):
+        import torch
+        self.torch, self.ctx, self.w, self.rank, self.world, self.mode, self.dist = torch, ctx, w, rank, world, mode, dist
+        self.dev, self.seed = ctx.device, seed
+        self.origin = (0.0, 0.0, 0.0)
+        self.solve_ms, self.orb, self.bins = None, None, None
+
+    # ---- set-up --------------------------------------------------------------------------------------------------
+    def initialise(self):
+        torch, ctx, w, rank, world = self.torch, self.ctx, self.w, self.rank, self.world
+        ng, h, Lg = w["ng"], w["h"], w["Lg"]
+        self.n_total = n_total = w["n_local"] * world
+        self.q = -(Lg[0] * Lg[1] * Lg[2]) / n_total if w["name"] != "penning" else -1562.5 / n_total
+        self.layout = layout = ib.Layout(ng, world)
+        dist_s = ib.Dist.make(*w["dist"])
+        if world > 1:
+            ctx.set_layout(layout, self.origin, h)
+        mesh = layout.mesh(rank, self.origin, h)
+        if w["name"] == "penning" and world > 1:
+            # LoadBalancer's first repartition (the reference calls it before creating the particles): ORB on the analytic
+            # density, then FieldLayout::updateLayout
+            wf = ctx.field(mesh)
+            ctx.field_fill_pdf(mesh, dist_s, wf)
+            boxes, ok = ctx.orb_repartition(mesh, world, wf)
+            old = layout.boxes()
+            if ok:
+                layout.set_boxes(boxes)
+                ctx.set_layout(layout, self.origin, h)
+                mesh = layout.mesh(rank, self.origin, h)
+            self.orb = {"applied": bool(ok), "boxes_before": old.tolist(), "boxes_after": layout.boxes().tolist()}
+        self.mesh = mesh
+        regs = layout.regions(self.origin, h)
+        self.region = list(regs[rank])
+        counts, ub = ib.sample_counts(dist_s, [0.0] * 3, Lg, regs, n_total)
+        assert sum(counts) == n_total
+        if self.orb is not None:
+            eq = ib.Layout(ng, world)
+            ceq, _ = ib.sample_counts(dist_s, [0.0] * 3, Lg, eq.regions(self.origin, h), n_total)
+            self.orb.update(imbalance_before=max(ceq) * world / n_total, imbalance_after=max(counts) * world / n_total)
+            eq.close()
+        self.n_mine = n = counts[rank]
+        self.cap = cap = int(1.25 * max(n, n_total // world)) + (1 << 16)
+        self.parts, self.scratch = ib.Particles(cap, self.dev, q=self.q), ib.Particles(cap, self.dev, q=self.q)
+        p = self.parts
+        seed = self.seed + 100 * rank
+        ctx.sample_positions(dist_s, ub[rank][:3], ub[rank][3:], seed, 0, n, p)
+        lo = 0
+        for i, (mu, sd, frac) in enumerate(w["vel"]):   # velocity components (bulk + beam for BumponTail)
+            hi = n if i == len(w["vel"]) - 1 else lo + int(frac * n)
+            if hi > lo:
+                if lo == 0:
+                    ctx.sample_normal(mu, sd, seed, 0, hi - lo, p)
+                else:
+                    tmp = ib.Particles(hi - lo, self.dev)
+                    ctx.sample_normal(mu, sd, seed, lo, hi - lo, tmp)
+                    for k in ("px", "py", "pz"):
+                        p.arr[k][lo:hi].copy_(tmp.arr[k])
+                    del tmp
+            lo = hi
+        for d, k in enumerate("xyz"):   # Newton's 1e-12 tolerance may leave a sample a hair outside the region
+            p.arr[k][:n].clamp_(min=float(np.nextafter(self.region[d], np.inf)), max=float(self.region[3 + d]))
+        p.n = n
+        self.rho, self.ef = ctx.field(mesh), ctx.field(mesh, 3)
+        self.off = ctx.offsets_buffer(mesh) if self.mode != 2 else None
+        self.push = (ib.leapfrog_push(w["dt"]) if w["push"] == "leapfrog" else ib.penning_push(w["dt"], self.origin, Lg))
+        self._first_solve()
+        if self.mode == 2:
+            self.bins = ib.Bins(ctx, mesh, cap)
+            self.bins.build(self.parts, self.scratch)
+        else:
+            ctx.sort_by_cell(mesh, self.parts, self.scratch, self.off)
+        self.parts.arr, self.scratch.arr = self.scratch.arr, self.parts.arr
+        if world > 1 and self.mode == 2:
+            self.exit_cap = max(self.n_mine // 16, 1 << 16)
+            self.exit_buf = torch.zeros(6 * self.exit_cap, dtype=torch.float64, device=self.dev)
+
+    def _first_solve(self):
+        """scatter -> density -> FFT solve: a self-consistent E for the timed steps (AlpineManager::pre_run)"""
+        torch, ctx, w, mesh = self.torch, self.ctx, self.w, self.mesh
+        p, n, Lg, h = self.parts, self.n_mine, w["Lg"], w["h"]
+        ctx.scatter(mesh, p.arr["x"], p.arr["y"], p.arr["z"], self.q, self.rho, end=n)   # only the sampled slots
+        if self.world > 1:
+            ctx.halo_exchange(self.rho, 1, "accumulate")
+            sol = ib.Poisson(ctx, None, layout=self.layout, origin=self.origin, h=h)
+        else:
+            ctx.halo_accumulate_periodic(mesh, self.rho)
+            sol = ib.Poisson(ctx, mesh)
+        ctx.field_density(mesh, self.rho, h[0] * h[1] * h[2], self.q * self.n_total / (Lg[0] * Lg[1] * Lg[2]))
+        sol.solve(self.rho, self.ef)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sol.solve(self.rho, self.ef)
+        e1.record()
+        torch.cuda.synchronize()
+        self.solve_ms = e0.elapsed_time(e1)
+        sol.close()
+
+    # ---- one step of the hot path -----------------------------------------------------------------------------------
+    def fill_e_halo(self):
+        if self.world > 1:
+            self.ctx.halo_exchange(self.ef, 3, "fill")
+        else:
+            self.ctx.halo_fill_periodic(self.mesh, self.ef, 3)
+
+    def step(self, first=False):
+        ctx, mesh, push = self.ctx, self.mesh, self.push
+        push.do_kick2 = 0 if first else 1   # the very first step has no closing kick pending
+        if self.bins is not None and self.world == 1:
+            # one rank owns the whole periodic domain: the fused kernel aliases ghost nodes itself, which replaces the
+            # fillHalo(E) / accumulateHalo(rho) passes (HaloCells::applyPeriodicSerialDim)
+            ctx.pic_step(mesh, push, self.parts, self.scratch, None, self.ef, self.rho, do_sort=2, bins=self.bins)
+            return
+        self.fill_e_halo()
+        if self.bins is not None:
+            ctx.field_fill(self.rho, 0.0)
+            self.bins.step(push, self.parts, self.scratch, self.ef, self.rho, exit_buf=self.exit_buf, region=self.region)
+            self.bins.migrate(self.parts, self.exit_buf, self.rho)
+            ctx.halo_exchange(self.rho, 1, "accumulate")
+        elif self.world == 1:
+            ctx.pic_step(mesh, push, self.parts, self.scratch, self.off, self.ef, self.rho, do_sort=self.mode)
+        else:
+            ctx.gather_push(mesh, push, self.parts, self.ef)
+            ctx.update(self.parts)
+            ctx.sort_by_cell(mesh, self.parts, self.scratch, self.off)
+            self.parts.arr, self.scratch.arr = self.scratch.arr, self.parts.arr
+            ctx.field_fill(self.rho, 0.0)
+            ctx.scatter_sorted(mesh, self.parts.n, self.parts.arr["x"], self.parts.arr["y"], self.parts.arr["z"], self.q,
+                               self.off, self.rho)
+            ctx.halo_exchange(self.rho, 1, "accumulate")
+
+    def status(self):
+        if self.bins is not None:
+            n, t, e, f = self.bins.status()
+            return {"n_local": n, "n_tail": t, "n_exit": e, "flags": f}
+        return {"n_local": self.parts.n, "n_tail": 0, "n_exit": 0, "flags": 0}
+
+    def _timed(self, fn, reps=3):
+        torch = self.torch
+        out = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            out.append(a.elapsed_time(b))
+        return float(np.mean(out))
+
+    def phase_ms(self):
+        """CUDA-event time of every phase of one step, each from an idle start (diagnostic: the phases of the timed
+        region run back to back and are faster)."""
+        ctx, mesh = self.ctx, self.mesh
+        k = {}
+        if self.bins is not None and self.world == 1:
+            k["rho_zero"] = self._timed(lambda: ctx.field_fill(self.rho, 0.0))
+            k["step_from_idle"] = self._timed(lambda: self.step())
+        elif self.bins is not None:
+            k["halo_fill_E"] = self._timed(self.fill_e_halo)
+            k["rho_zero"] = self._timed(lambda: ctx.field_fill(self.rho, 0.0))
+
+            def fused():
+                self.bins.step(self.push, self.parts, self.scratch, self.ef, self.rho, exit_buf=self.exit_buf, region=self.region)
+            k["fused_step"] = self._timed(fused, reps=1)
+            k["migrate"] = self._timed(lambda: self.bins.migrate(self.parts, self.exit_buf, self.rho), reps=1)
+            k["halo_accumulate_rho"] = self._timed(lambda: ctx.halo_exchange(self.rho, 1, "accumulate"))
+        else:
+            k["gather_push"] = self._timed(lambda: ctx.gather_push(mesh, self.push, self.parts, self.ef))
+        return k
+
+    def extra_config(self):
+        c = {}
+        if self.orb is not None:
+            c["orb"] = {k: self.orb[k] for k in ("applied", "imbalance_before", "imbalance_after")}
+        return c
+
+    # ---- parity inside the multi-rank bench run ------------------------------------------------------------------------
+    def parity_check(self):
+        from . import parity
+        return parity.multi_rank_step(self.ctx, self.dist, self.rank, self.world)
+
+    # ---- end to end: host buffers, copies inside the timed region -------------------------------------------------------
+    def e2e(self, steps, barrier):
+        """Steady state: the particles stay bucketed on the device (the reference's ParticleAttrib views are device
+        allocations too); every step the ghosted E field comes from pinned HOST memory and the ghosted rho goes back to
+        pinned HOST memory -- what a host-side / non-owned field solve exchanges with the particle path per step."""
+        import time
+        torch, ctx, mesh = self.torch, self.ctx, self.mesh
+        ef_host = torch.empty(mesh.cells * 3, dtype=torch.float64).pin_memory()
+        rho_host = torch.empty(mesh.cells, dtype=torch.float64).pin_memory()
+        ef_host.copy_(self.ef)
+
+        def one():
+            if self.world == 1:
+                ctx.pic_step_host_fields(mesh, self.push, self.parts, self.scratch, self.bins, ef_host, rho_host, self.ef, self.rho)
+            else:
+                self.ef.copy_(ef_host, non_blocking=True)
+                self.step()
+                rho_host.copy_(self.rho, non_blocking=True)
+                torch.cuda.synchronize()
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        assert bool(torch.isfinite(rho_host).all())
+        return {"ms_per_step": ms, "steps": steps, "h2d_bytes_per_step": 24 * mesh.cells, "d2h_bytes_per_step": 8 * mesh.cells,
+                "what": ("ipplb_pic_step_host_fields" if self.world == 1 else "H2D E + step + D2H rho") +
+                        ": per step the ghosted E field from pinned host memory -> device, the fused step on the resident "
+                        "bucketed particles, the ghosted rho -> pinned host memory, host-synchronous (wall clock)"}
+
+    def e2e_streamed(self, barrier):
+        """The other end-to-end shape: every batch of particles comes from and returns to HOST memory
+        (ipplb_pic_step_host_batches: upload / bucket + fused step + compact / download overlap).  PCIe bound."""
+        import ctypes as C
+        import time
+        torch, ctx, mesh, w = self.torch, self.ctx, self.mesh, self.w
+        n, cap, q = self.n_mine, self.cap, self.q
+        lib = ib.lib()
+        self.bins.compact(self.parts, self.scratch)
+        self.parts.arr, self.scratch.arr = self.scratch.arr, self.parts.arr
+        nb_warm, nb = 2, 6
+        hostbuf = [[torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(6)] for _ in range(2)]
+        for hs in hostbuf:
+            for hb, k in zip(hs, ib.Particles.NAMES):
+                hb.copy_(self.parts.arr[k][:n])
+        rho_host = [torch.empty(mesh.cells, dtype=torch.float64).pin_memory() for _ in range(2)]
+        slots_p = [self.parts, ib.Particles(cap, self.dev, q=q)]
+        slots_s = [self.scratch, ib.Particles(cap, self.dev, q=q)]
+        slots_b = [self.bins, ib.Bins(ctx, mesh, cap)]
+        slots_r = [self.rho, ctx.field(mesh)]
+        push = ib.leapfrog_push(w["dt"])
+
+        def run_batches(nbatch):
+            harr = (C.c_void_p * (6 * nbatch))(*[hostbuf[k & 1][a].data_ptr() for k in range(nbatch) for a in range(6)])
+            rarr = (C.c_void_p * nbatch)(*[rho_host[k & 1].data_ptr() for k in range(nbatch)])
+            PA = ib.lib_particles_array([p.struct() for p in slots_p])
+            SA = ib.lib_particles_array([p.struct() for p in slots_s])
+            BA = (C.c_void_p * 2)(*[b._h.value for b in slots_b])
+            RA = (C.c_void_p * 2)(*[r.data_ptr() for r in slots_r])
+            rc = lib.ipplb_pic_step_host_batches(ctx._h, C.byref(mesh), C.byref(push), C.c_long(n), nbatch, harr,
+                                                 C.c_double(q), C.c_void_p(self.ef.data_ptr()), rarr, PA, SA, BA, RA)
+            if rc:
+                raise RuntimeError(lib.ipplb_last_error().decode())
+        run_batches(nb_warm)
+        barrier()
+        t0 = time.perf_counter()
+        run_batches(nb)
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / nb
+        xs = hostbuf[0][0]
+        assert bool(torch.isfinite(xs).all()) and float(xs.min()) >= 0.0 and float(xs.max()) <= w["Lg"][0]
+        slots_b[1].close()
+        return {"value": n / (ms * 1e-3), "unit": "particles/s", "ms_per_step": ms, "steps": nb,
+                "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n + 8 * mesh.cells,
+                "what": "ipplb_pic_step_host_batches: per batch pinned host R,P -> device, bucket, fused step, compact, "
+                        "R,P + rho -> host; upload / compute / download of consecutive batches overlap (PCIe bound)"}
+
+    def close(self):
+        if self.bins is not None:
+            self.bins.close()
+            self.bins = None

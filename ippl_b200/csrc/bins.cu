@@ -336,11 +336,39 @@ int ipplb_bins_destroy(ipplb_bins* b) {
     if (b->d_plan) cudaFree(b->d_plan);
     if (b->d_exit_cnt) cudaFree(b->d_exit_cnt);
     if (b->h_status) cudaFreeHost(b->h_status);
+    if (b->ev) {
+        for (int i = 0; i < 2 * ipplb_bins::NEV; ++i) cudaEventDestroy(b->ev[i]);
+        delete[] b->ev;
+    }
     delete b;
     return IPPLB_OK;
 }
 
 int ipplb_bins_ntiles(const ipplb_bins* b) { return b ? b->ntiles : -1; }
+
+int ipplb_bins_set_timing(ipplb_bins* b, int on) {
+    IPPLB_REQUIRE(b, "bins_set_timing: bad arguments");
+    if (on && !b->ev) {
+        b->ev = new cudaEvent_t[2 * ipplb_bins::NEV];
+        for (int i = 0; i < 2 * ipplb_bins::NEV; ++i) IPPLB_CUDA(cudaEventCreate(&b->ev[i]));
+    }
+    b->timing = on ? 1 : 0;
+    b->ev_n   = 0;
+    return IPPLB_OK;
+}
+
+int ipplb_bins_kernel_ms(ipplb_ctx* ctx, ipplb_bins* b, double* ms_out, int max_out, int* n_out) {
+    IPPLB_REQUIRE(ctx && b && n_out, "bins_kernel_ms: bad arguments");
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = b->ev_n < ipplb_bins::NEV ? b->ev_n : ipplb_bins::NEV;
+    *n_out      = n;
+    for (int i = 0; i < n && i < max_out; ++i) {
+        float ms = 0.f;
+        IPPLB_CUDA(cudaEventElapsedTime(&ms, b->ev[2 * i], b->ev[2 * i + 1]));
+        ms_out[i] = ms;
+    }
+    return IPPLB_OK;
+}
 
 int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_particles* in, ipplb_particles* out) {
     IPPLB_REQUIRE(ctx && b && in && out, "bins_build: bad arguments");

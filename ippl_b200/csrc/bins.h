@@ -28,6 +28,10 @@ struct ipplb_bins {
     long long* d_plan = nullptr;  // planning kernel scratch (partial sums + grid barrier words)
     int* d_exit_cnt = nullptr;    // [2][MAX_RANKS] leavers per destination rank: live counters, snapshot of the last step
     int exit_ranks  = 1;          // how many of them the last step used
+    // optional CUDA-event timing of the fused kernel alone, on the launching stream (ipplb_bins_set_timing)
+    static constexpr int NEV = 256;
+    cudaEvent_t* ev = nullptr;  // [2 * NEV]: start / stop per launch
+    int ev_n = 0, timing = 0;
     int* h_status = nullptr;  // pinned [BM_WORDS]
     // slack = total / slack_div + slack_sqrt * sqrt(total) + slack_const  (elements per bucket)
     int slack_div = 32, slack_sqrt = 4, slack_const = 16;

@@ -1009,6 +1009,8 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
     // instantiated: the tuned set (V_OWNER_TAIL | V_HINT | V_P5U2) with every combination of the two call-dependent
     // bits, and the plain kernel (0) as the A/B baseline; any other request runs the plain kernel
     constexpr int T = V_OWNER_TAIL | V_HINT | V_P5U2;
+    const bool timed = b->timing && b->ev && b->ev_n < ipplb_bins::NEV;
+    if (timed) IPPLB_CUDA(cudaEventRecord(b->ev[2 * b->ev_n], ctx->stream));
     switch (var) {
 #define IPPLB_VAR_CASE(v) case v: rc = launch_fused3<480, 2, 2, v>(ctx, A); break;
         IPPLB_VAR_CASE(T)
@@ -1018,6 +1020,10 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
         IPPLB_VAR_CASE(V_LEAPFROG | V_PERIODIC1)
 #undef IPPLB_VAR_CASE
         default: rc = launch_fused3<480, 2, 2, 0>(ctx, A); break;
+    }
+    if (timed) {
+        IPPLB_CUDA(cudaEventRecord(b->ev[2 * b->ev_n + 1], ctx->stream));
+        ++b->ev_n;
     }
     if (rc) return rc;
     rc = bins_plan(ctx, b, o, A.seg_cap);

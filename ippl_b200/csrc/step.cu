@@ -90,6 +90,23 @@ int ipplb_pic_step_host(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push
     return IPPLB_OK;
 }
 
+// Steady-state end-to-end step (bench.py's e2e): the particles live on the device -- as they do in the reference, whose
+// ParticleAttrib views are device allocations -- and what crosses the host boundary every step is what the (host-side or
+// non-owned) field solve exchanges with the particle path: E comes in, rho goes out.
+int ipplb_pic_step_host_fields(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push, ipplb_particles* p,
+                               ipplb_particles* scratch, ipplb_bins* bins, const double* efield_host, double* rho_host,
+                               double* efield_dev, double* rho_dev) {
+    IPPLB_REQUIRE(ctx && mesh && push && p && scratch && bins && efield_host && rho_host && efield_dev && rho_dev,
+                  "pic_step_host_fields: bad arguments");
+    const size_t cells = (size_t)ghosted_cells(mesh);
+    IPPLB_CUDA(cudaMemcpyAsync(efield_dev, efield_host, sizeof(double) * 3 * cells, cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
+    if ((rc = ipplb_pic_step(ctx, mesh, push, p, scratch, nullptr, bins, efield_dev, rho_dev, 2))) return rc;
+    IPPLB_CUDA(cudaMemcpyAsync(rho_host, rho_dev, sizeof(double) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+    IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IPPLB_OK;
+}
+
 // Pipelined variant over a sequence of independent batches (a "step" = one pass of the hot path over one batch):
 // upload of batch k+1, compute of batch k and download of batch k-1 overlap on three streams, two device slots.
 // Per slot: H2D -> dev; build dev -> scratch; fused step scratch -> dev; compact dev -> scratch; D2H <- scratch.

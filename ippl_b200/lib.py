@@ -351,6 +351,17 @@ class Context:
             parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
         parts.n = int(s.n)
 
+    def pic_step_host_fields(self, mesh, push, parts, scratch, bins, efield_host, rho_host, efield_dev, rho_dev):
+        """ipplb_pic_step_host_fields: E from (pinned) host memory, fused step on the resident bucketed particles, rho back
+        to (pinned) host memory; synchronises.  `parts` and `scratch` swap storage."""
+        s, sc = parts.struct(), scratch.struct()
+        _check(lib().ipplb_pic_step_host_fields(self._h, C.byref(mesh), C.byref(push), C.byref(s), C.byref(sc), bins._h,
+                                                C.c_void_p(efield_host.data_ptr()), C.c_void_p(rho_host.data_ptr()),
+                                                _ptr(efield_dev), _ptr(rho_dev)))
+        parts.arr, scratch.arr = scratch.arr, parts.arr
+        parts.qarr, scratch.qarr = scratch.qarr, parts.qarr
+        parts.n = int(s.n)
+
     # -- diagnostics, sampling, ORB (SURVEY 8f) -----------------------------------------------
     def field_energy_stats(self, mesh, ef):
         """(sum E_d^2 [3], max|E_d| [3], sum dot(E,E)) over the interior"""
@@ -465,6 +476,15 @@ class Bins:
                                      _ptr(rho), _ptr(exit_buf), cap, rmin, rmax))
         cur.arr, nxt.arr = nxt.arr, cur.arr
         cur.qarr, nxt.qarr = nxt.qarr, cur.qarr
+
+    def set_timing(self, on=True):
+        _check(lib().ipplb_bins_set_timing(self._h, 1 if on else 0))
+
+    def kernel_ms(self):
+        """per-launch durations (ms) of the fused kernel since set_timing(True) (synchronises)"""
+        out, n = (C.c_double * 256)(), C.c_int()
+        _check(lib().ipplb_bins_kernel_ms(self.ctx._h, self._h, out, 256, C.byref(n)))
+        return [out[i] for i in range(n.value)]
 
     def status(self):
         """(n_local, n_tail, n_exit, flags) after the last build / step / append (synchronises)"""

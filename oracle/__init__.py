@@ -75,6 +75,24 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
+def sample_landau(n, alpha, k, lo, hi, seed):
+    """positions of LandauDampingManager::initializeParticles along one dimension (bench.py's CPU baseline)"""
+    x = np.empty(n)
+    lib().orc_sample_landau(C.c_long(n), C.c_double(alpha), C.c_double(k), C.c_double(lo), C.c_double(hi),
+                            C.c_ulonglong(seed), _p(x))
+    return x
+
+
+def sample_normal(n, seed):
+    p = np.empty(n)
+    lib().orc_sample_normal(C.c_long(n), C.c_ulonglong(seed), _p(p))
+    return p
+
+
 def field_zeros(mesh, ncomp=1):
     ex, ey, ez = mesh.ext
     return np.zeros(ex * ey * ez * ncomp, dtype=np.float64)

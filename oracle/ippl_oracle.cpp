@@ -59,6 +59,54 @@ int orc_num_threads() {
 #endif
 }
 
+// bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: the arm sets the thread count itself
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic Landau initial condition for the timed CPU baseline (bench.py only; the parity tests feed identical arrays
+// to both sides instead).  Same distributions as LandauDampingManager::initializeParticles
+// (demos/alpine/LandauDampingManager.h:159-254): per dimension x by inverse transform of
+// cdf(x) = x + (alpha / k) sin(k x) on [lo, hi] with the reference's Newton iteration (Random/Utility.h:27-60:
+// while iter < 20 && |f| > 1e-12: x -= f / pdf), velocities N(0, 1).  The uniform stream is a counter hash
+// (splitmix64), not Kokkos' pool: only the distribution matters for a throughput baseline.
+// ---------------------------------------------------------------------------
+static inline double orc_u01(unsigned long long i, unsigned long long seed) {
+    unsigned long long z = i * 0x9E3779B97F4A7C15ULL + seed * 0xD1B54A32D192ED03ULL + 0x632BE59BD9B4E019ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+void orc_sample_landau(long n, double alpha, double k, double lo, double hi, unsigned long long seed, double* x) {
+    const double c0 = lo + (alpha / k) * std::sin(k * lo), c1 = hi + (alpha / k) * std::sin(k * hi);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        const double u = c0 + (c1 - c0) * orc_u01((unsigned long long)i, seed);
+        double v       = u;  // estimate(u) = u (LandauDampingManager.h:36-38)
+        for (int it = 0; it < 20; ++it) {
+            const double f = v + (alpha / k) * std::sin(k * v) - u;
+            if (std::fabs(f) <= 1e-12) break;
+            v -= f / (1.0 + alpha * std::cos(k * v));
+        }
+        x[i] = v < lo ? lo : (v > hi ? hi : v);
+    }
+}
+
+void orc_sample_normal(long n, unsigned long long seed, double* p) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        const double u1 = orc_u01((unsigned long long)(2 * i), seed), u2 = orc_u01((unsigned long long)(2 * i + 1), seed);
+        p[i] = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // CIC index/weights: src/Particle/ParticleAttrib.hpp:174-179 (scatter) and
 // :229-234 (gather):  l = (x - origin) * invdx + 0.5; index = (int) l;
