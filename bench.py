@@ -216,9 +216,13 @@ def main():
                       dist=dist if world > 1 else None)
     w = run.w
     n_local, n_total = w["n_local"], w["n_local"] * world
+    parity = None
+    if world > 1:    # one small oracle-checked multi-rank step on the same communicator, before the workload is set up
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import mgpu_parity
+        parity = mgpu_parity.multi_rank_step(ctx, dist, rank, world)
     run.initialise()                # particles sampled on the device, [ORB], first solve, bucketing
     mesh, bins = run.mesh, run.bins
-    parity = run.parity_check() if world > 1 else None     # one small oracle-checked multi-rank step (not timed)
 
     def barrier():
         torch.cuda.synchronize()

@@ -32,6 +32,7 @@ extern "C" {
 typedef struct ipplb_ctx ipplb_ctx;
 typedef struct ipplb_layout ipplb_layout;   /* host-only: rank boxes + neighbour tables */
 typedef struct ipplb_poisson ipplb_poisson; /* cuFFT periodic Poisson solver (non-owned stage) */
+typedef struct ipplb_bins ipplb_bins;       /* cell-ordered particle store behind the fused step (see below) */
 
 enum {
     IPPLB_OK = 0,
@@ -214,11 +215,37 @@ int ipplb_halo_exchange(ipplb_ctx* ctx, double* field, int ncomp, int mode);
  * p->n is updated; arrays must have capacity for the arrivals (IPPLB_ERR_CAPACITY otherwise).
  * sent_host / recv_host (may be NULL): per-rank counts [nranks] for parity checks. */
 int ipplb_update(ipplb_ctx* ctx, ipplb_particles* p, long* sent_host, long* recv_host);
+/* The same in two collective halves, for callers that own growable arrays (the facade's ParticleAttrib, which the
+ * reference grows on receive, src/Particle/ParticleBase.hpp:300-393): ipplb_update_plan locates the particles and
+ * exchanges the counts (no particle moves); *n_after_host = this rank's count after the migration, so the caller can
+ * reserve; ipplb_update_commit then packs, exchanges and unpacks.  Errors are COLLECTIVE: every rank's count, capacity
+ * and outcome travel with the count exchange, so when one rank cannot hold its arrivals every rank returns
+ * IPPLB_ERR_CAPACITY (from plan: reserve and call commit; from commit: fatal) and none is left waiting in a receive. */
+int ipplb_update_plan(ipplb_ctx* ctx, ipplb_particles* p, long* n_after_host, long* sent_host, long* recv_host);
+int ipplb_update_commit(ipplb_ctx* ctx, ipplb_particles* p);
 /* sum over ranks of one double / one long (rho.sum(), particle count: AlpineManager.h:169, 212) */
 int ipplb_allreduce_sum_f64(ipplb_ctx* ctx, double* value_host);
 int ipplb_allreduce_sum_i64(ipplb_ctx* ctx, long* value_host);
 /* max over ranks of one double (the dumps' max norms: Comm->reduce(..., std::greater<double>()), LandauDampingManager.h:360-366) */
 int ipplb_allreduce_max_f64(ipplb_ctx* ctx, double* value_host);
+
+/* ---- all ranks of a small job in ONE process on ONE device (no NCCL) ------------------------------------------
+ * The multi-rank path is written as local phases (kernels of one rank) around a transport step.  ipplb_loop_* drive
+ * every rank of an in-process group through the SAME phases -- same kernels, same tables, same host logic as the NCCL
+ * entry points above -- with device-to-device copies (and, for the bucketed store, plain pointers into the other
+ * contexts' inboxes) as the transport.  This is how ownership (ParticleSpatialLayout.hpp:316-330, 372-395), the
+ * send / receive / compaction of update (:150-314, ParticleBase.hpp:175-393) and HaloCells::exchangeBoundaries
+ * (HaloCells.hpp:109-242) are held to the oracle on a single GPU.  ctxs[r] becomes rank r of nranks; bind each with
+ * ipplb_ctx_set_layout afterwards.  Arrays below are indexed by rank. */
+typedef struct ipplb_loop ipplb_loop;
+int ipplb_loop_create(ipplb_loop** out, ipplb_ctx* const* ctxs, int nranks);
+int ipplb_loop_destroy(ipplb_loop* loop);
+int ipplb_loop_halo_exchange(ipplb_loop* loop, double* const* fields, int ncomp, int mode);
+/* parts[nranks]; sent_host / recv_host (may be NULL): [nranks][nranks] counts, row r = rank r's */
+int ipplb_loop_update(ipplb_loop* loop, ipplb_particles* parts, long* sent_host, long* recv_host);
+int ipplb_loop_migrate_connect(ipplb_loop* loop, long seg_cap);
+/* bins[nranks], cur[nranks], rho[nranks] (rho or its entries may be NULL) */
+int ipplb_loop_bins_migrate(ipplb_loop* loop, ipplb_bins* const* bins, ipplb_particles* cur, double* const* rho);
 
 /* ---- cell-ordered particle store + fused single-pass PIC step (the B200-first path) ------------------ */
 /* ipplb_bins keeps the particles of one rank grouped in per-tile buckets (tile = 4x4x4 key cells, key =
@@ -230,7 +257,6 @@ int ipplb_allreduce_max_f64(ipplb_ctx* ctx, double* value_host);
  * The tables live in device memory and are re-planned on the device after every step: no host sync.
  * This is storage behind ParticleAttrib (src/Particle/ParticleAttrib.h:33-277): ipplb_bins_compact gives
  * the contiguous [0,n) view the reference API exposes. */
-typedef struct ipplb_bins ipplb_bins;
 enum {
     IPPLB_FLAG_EXIT_OVERFLOW = 1,  /* more leavers than exit_cap (leavers beyond it were dropped) */
     IPPLB_FLAG_CAPACITY      = 2,  /* arrays too small for buckets + tail (particles were dropped) */
@@ -275,6 +301,18 @@ int ipplb_bins_append(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, co
  * Synchronises the stream.  With one rank it only refreshes cur->n. */
 int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, const double* exit_buf,
                        int exit_cap, double* rho, long* sent_host, long* recv_host);
+/* Peer-memory migration (the default multi-GPU path).  ipplb_migrate_connect (collective, once per communicator)
+ * allocates this rank's inbox -- [nranks][seg_cap] 48-byte records, two copies for alternating steps -- and maps every
+ * peer's inbox into this process (cudaIpc over NVLink / NVSwitch).  From then on ipplb_bins_step with exit_buf == NULL
+ * writes each leaver STRAIGHT into segment `rank` of its destination's inbox, and ipplb_bins_migrate_async finishes the
+ * update with one small all-gather of the counts (which is also the barrier behind which the records have landed) and
+ * one kernel that drops the arrivals into their buckets (overflow: tail) and deposits their charge into rho (may be
+ * NULL).  Nothing synchronises with the host: cur->n is NOT refreshed (ipplb_bins_status reports the device truth) and
+ * errors surface as the sticky IPPLB_FLAG_* bits.  ipplb_migrate_counts (synchronises) returns the per-rank counts of
+ * the last migration for checks. */
+int ipplb_migrate_connect(ipplb_ctx* ctx, long seg_cap);
+int ipplb_bins_migrate_async(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, double* rho);
+int ipplb_migrate_counts(ipplb_ctx* ctx, long* sent_host, long* recv_host);
 /* Contiguous copy (bucket order, then tail) of the bucketed `cur` into out[0..n). Sets out->n (syncs). */
 int ipplb_bins_compact(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* cur,
                        ipplb_particles* out);

@@ -28,6 +28,7 @@ struct ipplb_bins {
     long long* d_plan = nullptr;  // planning kernel scratch (partial sums + grid barrier words)
     int* d_exit_cnt = nullptr;    // [2][MAX_RANKS] leavers per destination rank: live counters, snapshot of the last step
     int exit_ranks  = 1;          // how many of them the last step used
+    int exit_p2p    = 0;          // the last step wrote its leavers into the peers' inboxes (not into an exit buffer)
     // optional CUDA-event timing of the fused kernel alone, on the launching stream (ipplb_bins_set_timing)
     static constexpr int NEV = 256;
     cudaEvent_t* ev = nullptr;  // [2 * NEV]: start / stop per launch

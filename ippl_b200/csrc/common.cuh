@@ -74,6 +74,7 @@ struct Scratch {
 }  // namespace ipplb
 
 struct ncclComm;
+struct ipplb_loop;
 
 struct ipplb_ctx {
     int device          = 0;
@@ -89,6 +90,8 @@ struct ipplb_ctx {
     ncclComm* nccl = nullptr;
     int rank = 0, nranks = 1;
     void* plan = nullptr;  // ipplb::CommPlan*
+    void* mig  = nullptr;  // ipplb::MigBox*: peer-memory inboxes of the bucketed store's migration (ipplb_migrate_connect)
+    ipplb_loop* loop = nullptr;  // set when this context is one rank of an in-process rank group (ipplb_loop_create)
     const double* d_regions = nullptr;  // [nranks][6] physical regions (device), set by ipplb_ctx_set_layout
     // copy streams + events of the host-buffer pipeline (ipplb_pic_step_host_batches), created on first use
     cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -75,6 +75,8 @@ struct StepArgs {
     double* rho;
     double q;
     double* exit_buf;  // [nranks][seg_cap][6]: leavers grouped by destination rank, one (x y z px py pz) record each
+    double* const* peer_seg;  // peer mode: [nranks] the destination ranks' inboxes ([nranks][seg_cap][6] each); this rank
+                              // writes segment `me` of inbox d over peer memory (NVLink) -- or nullptr
     int* exit_cnt;     // [nranks]
     int seg_cap;
     const double* regions;  // [nranks][6] (device) or nullptr on a single rank
@@ -180,7 +182,8 @@ static __device__ IPPLB_SLOW_ATTR void place_exit(const StepArgs& A, double x, d
     const int e = base + __popc(peers & ((1u << lane) - 1u));
     if (e < A.seg_cap) {
         // one 48-byte record per leaver: a destination's segment is one contiguous message
-        double2* rec = reinterpret_cast<double2*>(A.exit_buf + ((size_t)d * A.seg_cap + e) * 6);
+        double* base = A.peer_seg ? A.peer_seg[d] + (size_t)A.me * A.seg_cap * 6 : A.exit_buf + (size_t)d * A.seg_cap * 6;
+        double2* rec = reinterpret_cast<double2*>(base + (size_t)e * 6);
         rec[0]       = make_double2(x, y);
         rec[1]       = make_double2(z, px);
         rec[2]       = make_double2(py, pz);
@@ -928,6 +931,8 @@ static int launch_fused3(ipplb_ctx* ctx, const StepArgs& A) {
     return IPPLB_OK;
 }
 
+double* const* mig_peer_table(ipplb_ctx* ctx, long* seg_cap);  // comm.cu
+
 // tuning knob (experiments only): IPPLB_FUSED_VAR selects the kernel variant mask (V_*); the default is the measured best
 static int fused_var() {
     int var = -1;
@@ -981,6 +986,16 @@ int ipplb_bins_step(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_push* push, const
     A.exit_buf   = exit_buf;
     A.exit_cnt   = b->d_exit_cnt;
     A.seg_cap    = exit_buf ? exit_cap / nrk : 0;
+    A.peer_seg   = nullptr;
+    b->exit_p2p  = 0;
+    if (!exit_buf && nrk > 1 && ctx->mig) {
+        // peer mode (ipplb_migrate_connect): leavers go straight into the destination ranks' inboxes
+        long seg = 0;
+        A.peer_seg = mig_peer_table(ctx, &seg);
+        IPPLB_REQUIRE(seg < (1L << 31), "bins_step: inbox segment too large");
+        A.seg_cap   = (int)seg;
+        b->exit_p2p = 1;
+    }
     A.regions    = ctx->d_regions;
     A.nranks     = nrk;
     A.me         = ctx->rank;

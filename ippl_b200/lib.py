@@ -429,6 +429,27 @@ class Context:
         parts.n = int(s.n)
         return list(sent), list(recv)
 
+    def update_plan(self, parts):
+        """ipplb_update_plan: (n_after, sent, recv) -- collective; IpplbError (on every rank) when some rank does not fit"""
+        s = parts.struct()
+        n_after = C.c_long()
+        sent, recv = (C.c_long * self.nranks)(), (C.c_long * self.nranks)()
+        rc = lib().ipplb_update_plan(self._h, C.byref(s), C.byref(n_after), sent, recv)
+        return rc, n_after.value, list(sent), list(recv)
+
+    def update_commit(self, parts):
+        s = parts.struct()
+        _check(lib().ipplb_update_commit(self._h, C.byref(s)))
+        parts.n = int(s.n)
+
+    def migrate_connect(self, seg_cap):
+        _check(lib().ipplb_migrate_connect(self._h, C.c_long(int(seg_cap))))
+
+    def migrate_counts(self):
+        sent, recv = (C.c_long * self.nranks)(), (C.c_long * self.nranks)()
+        _check(lib().ipplb_migrate_counts(self._h, sent, recv))
+        return list(sent), list(recv)
+
     def allreduce_sum(self, v):
         if isinstance(v, int):
             c = C.c_long(v)
@@ -508,6 +529,11 @@ class Bins:
         _check(lib().ipplb_bins_migrate(self.ctx._h, self._h, C.byref(s), _ptr(exit_buf), cap, _ptr(rho), sent, recv))
         cur.n = int(s.n)
         return list(sent), list(recv)
+
+    def migrate_async(self, cur, rho=None):
+        """ipplb_bins_migrate_async: peer-memory migration of the leavers of the last step; no host synchronisation"""
+        s = cur.struct()
+        _check(lib().ipplb_bins_migrate_async(self.ctx._h, self._h, C.byref(s), _ptr(rho)))
 
     def compact(self, cur, out):
         s, d = cur.struct(), out.struct()
@@ -596,3 +622,45 @@ class Layout:
         m = Mesh()
         _check(lib().ipplb_layout_mesh(self._h, rank, (C.c_double * 3)(*origin), (C.c_double * 3)(*h), C.byref(m)))
         return m
+
+
+class Loop:
+    """ipplb_loop: all ranks of a small job in ONE process on ONE device (no NCCL); the same kernels and tables as the
+    NCCL path with device-to-device copies as the transport.  ctxs[r] becomes rank r."""
+
+    def __init__(self, ctxs):
+        self.ctxs = list(ctxs)
+        self.n = len(self.ctxs)
+        self._h = C.c_void_p()
+        arr = (C.c_void_p * self.n)(*[c._h.value for c in self.ctxs])
+        _check(lib().ipplb_loop_create(C.byref(self._h), arr, self.n))
+        for r, c in enumerate(self.ctxs):
+            c.rank, c.nranks = r, self.n
+
+    def close(self):
+        if self._h:
+            lib().ipplb_loop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def halo_exchange(self, fields, ncomp, mode):
+        arr = (C.c_void_p * self.n)(*[f.data_ptr() for f in fields])
+        _check(lib().ipplb_loop_halo_exchange(self._h, arr, ncomp, 0 if mode == "fill" else 1))
+
+    def update(self, parts):
+        """parts[r]: Particles of rank r (contiguous).  Returns (sent[r][t], recv[r][t])."""
+        structs = lib_particles_array([p.struct() for p in parts])
+        sent, recv = (C.c_long * (self.n * self.n))(), (C.c_long * (self.n * self.n))()
+        _check(lib().ipplb_loop_update(self._h, structs, sent, recv))
+        for r, p in enumerate(parts):
+            p.n = int(structs[r].n)
+        n = self.n
+        return ([[sent[r * n + t] for t in range(n)] for r in range(n)], [[recv[r * n + t] for t in range(n)] for r in range(n)])
+
+    def migrate_connect(self, seg_cap):
+        _check(lib().ipplb_loop_migrate_connect(self._h, C.c_long(int(seg_cap))))
+
+    def bins_migrate(self, bins, cur, rho=None):
+        structs = lib_particles_array([p.struct() for p in cur])
+        barr = (C.c_void_p * self.n)(*[b._h.value for b in bins])
+        rarr = (C.c_void_p * self.n)(*[r.data_ptr() for r in rho]) if rho is not None else None
+        _check(lib().ipplb_loop_bins_migrate(self._h, barr, structs, rarr))
