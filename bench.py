@@ -18,6 +18,7 @@ timed separately (`solve_ms`).  Inputs (6.4 GB of particles per GPU) are far lar
 The mini-app driver itself (initial condition, ORB, step, parity check, end-to-end variants) is ippl_b200/app.py.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -207,7 +208,8 @@ def main():
     ctx = ib.Context(local)
     dev = ctx.device
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies must not leave its peers waiting for the whole time limit: collectives give up after 3 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         uid = [ib.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])

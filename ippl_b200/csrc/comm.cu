@@ -857,6 +857,12 @@ __global__ void __launch_bounds__(256) arrivals_p2p_kernel(const ArriveArgs a) {
         Cic c;
         cic_setup(a.m, r0.x, r0.y, r1.x, c);
         const int cx = c.a[0] - a.m.nghost, cy = c.a[1] - a.m.nghost, cz = c.a[2] - a.m.nghost;
+        if (cx < 0 || cx > a.m.nl[0] || cy < 0 || cy > a.m.nl[1] || cz < 0 || cz > a.m.nl[2]) {
+            // not a position of this rank's box (a non-finite position ends up here through the "stay" fallback of
+            // the destination search): no bucket can take it -- flag it instead of indexing the tables with it
+            atomicOr(&a.misc[BM_ST_FLAGS], IPPLB_FLAG_INTERNAL);
+            continue;
+        }
         const int tile = (cx >> 2) + a.ntx * ((cy >> 2) + a.nty * (cz >> 2));
         long g;
         const int slot = atomicAdd(&a.count[tile], 1);
