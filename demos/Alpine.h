@@ -4,6 +4,7 @@
 // loop, and -- B200 specific -- the fused single-pass step (ipplb_bins_step) any of the apps can switch to with
 // --fused.  Each driver defines `Dim`, `T` and `TestName` before including this header, like the reference's .cpp files.
 #pragma once
+#include <algorithm>
 #include "ippl/Ippl.h"
 
 #include <filesystem>
@@ -43,15 +44,31 @@ public:
         this->addAttribute(E);
         this->setParticleBC(ippl::BC::PERIODIC);
     }
-    // multi-rank exchange of R, P, q (E is recomputed by the next gather)
+    // multi-rank exchange of R, P, q (E is recomputed by the next gather).  Two collective halves, like the reference,
+    // which grows the attributes on receive (src/Particle/ParticleBase.hpp:300-393): the plan exchanges the counts, the
+    // attributes are grown to hold the arrivals (times the over-allocation factor), the commit moves the particles.
     void migrate() override {
-        ipplb_particles b{};
-        b.x = this->R.component(0); b.y = this->R.component(1); b.z = this->R.component(2);
-        b.px = P.component(0); b.py = P.component(1); b.pz = P.component(2);
-        b.q = q.component(0);
-        b.n = (long)this->getLocalNum();
-        b.capacity = (long)this->R.size();
-        ippl::b200::check(ipplb_update(ippl::b200::ctx(), &b, nullptr, nullptr), "ParticleContainer::migrate");
+        auto bundle = [&]() {
+            ipplb_particles b{};
+            b.x = this->R.component(0); b.y = this->R.component(1); b.z = this->R.component(2);
+            b.px = P.component(0); b.py = P.component(1); b.pz = P.component(2);
+            b.q = q.component(0);
+            b.n = (long)this->getLocalNum();
+            b.capacity = (long)std::min(std::min(this->R.size(), P.size()), q.size());
+            return b;
+        };
+        ipplb_particles b = bundle();
+        long n_after = b.n;
+        const int rc = ipplb_update_plan(ippl::b200::ctx(), &b, &n_after, nullptr, nullptr);
+        if (rc != IPPLB_OK && rc != IPPLB_ERR_CAPACITY) ippl::b200::check(rc, "ParticleContainer::migrate (plan)");
+        if (n_after > b.capacity) {
+            const std::size_t want = (std::size_t)n_after * (std::size_t)std::max(1, (int)ippl::Comm->getDefaultOverallocation());
+            this->R.reserve(want);
+            P.reserve(want);
+            q.reserve(want);
+            b = bundle();
+        }
+        ippl::b200::check(ipplb_update_commit(ippl::b200::ctx(), &b), "ParticleContainer::migrate (commit)");
         this->setLocalNum((size_type)b.n);
     }
 
@@ -422,6 +439,7 @@ int alpine_main(int argc, char* argv[]) {
             if (ippl::Comm->rank() == 0) std::cout << "ORB repartitions during the run: " << manager.repartitions() << std::endl;
             IpplTimings::stopTimer(mainTimer);
             IpplTimings::print();
+            IpplTimings::print(std::string("timing.dat"));   // demos/alpine/LandauDamping.cpp:102-103
         } catch (const IpplException& ex) {
             Inform err(TestName);
             err << "IPPL exception: " << ex.what() << endl;

@@ -30,7 +30,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <functional>
+#include <iomanip>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -128,7 +130,15 @@ class Communicator {
 public:
     int rank() const { return rank_; }
     int size() const { return size_; }
-    void barrier() { b200::check(ipplb_sync(b200::ctx()), "Comm::barrier"); }
+    // Communicator::barrier (src/Communicate/Communicator.h): drains this rank's stream, then a rank barrier (one small
+    // all-reduce over NCCL, host-synchronous like MPI_Barrier)
+    void barrier() {
+        b200::check(ipplb_sync(b200::ctx()), "Comm::barrier");
+        if (size_ > 1) {
+            long one = 1;
+            b200::check(ipplb_allreduce_sum_i64(b200::ctx(), &one), "Comm::barrier");
+        }
+    }
     [[noreturn]] void abort() {
         std::cerr << "ippl::Comm->abort()" << std::endl;
         std::abort();
@@ -964,6 +974,9 @@ private:
 }  // namespace ippl
 
 // ---- IpplTimings (src/Utility/IpplTimings.h): named wall timers with a stream fence on start/stop -----------------------------------------------
+// IpplTimings (src/Utility/IpplTimings.h / .cpp:226-330): wall-clock timers fenced on the context's stream (the reference
+// fences Kokkos); print() reduces every timer over the ranks (max / average / min) and lists the measurement counts,
+// print(file) writes the same block to a file (the drivers' "timing.dat").
 class IpplTimings {
 public:
     using TimerRef = int;
@@ -973,6 +986,7 @@ public:
         if (it != s.index.end()) return it->second;
         s.names.push_back(name);
         s.total.push_back(0.0);
+        s.count.push_back(0);
         s.start.push_back({});
         return s.index[name] = (int)s.names.size() - 1;
     }
@@ -983,14 +997,55 @@ public:
     static void stopTimer(TimerRef t) {
         if (ippl::b200::ctx_ref()) ipplb_sync(ippl::b200::ctx_ref());
         state().total[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - state().start[t]).count();
+        state().count[t] += 1;
     }
     static double seconds(TimerRef t) { return state().total[t]; }
     static void print(std::ostream& os = std::cout) {
         auto& s = state();
-        os << "---------------------------------------------\n     Timings (wall, stream-fenced)\n";
-        for (std::size_t i = 0; i < s.names.size(); ++i)
-            os << s.names[i] << std::string(s.names[i].size() < 24 ? 24 - s.names[i].size() : 1, '.') << " " << s.total[i] << " s\n";
-        os << "---------------------------------------------" << std::endl;
+        if (s.names.empty()) return;
+        const int nranks = ippl::Comm ? ippl::Comm->size() : 1;
+        const int rank   = ippl::Comm ? ippl::Comm->rank() : 0;
+        std::ostringstream msg;
+        msg << "---------------------------------------------\n";
+        msg << "     Timing results for " << nranks << " rank(s):\n";
+        msg << "---------------------------------------------\n";
+        for (std::size_t i = 0; i < s.names.size(); ++i) {
+            double wmax = s.total[i], wneg = -s.total[i], wsum = s.total[i];
+            if (nranks > 1) {   // collective: every rank walks the same timer list (IpplTimings.cpp:254-258)
+                ippl::Comm->allreduce(wmax, 1, std::greater<double>());
+                ippl::Comm->allreduce(wneg, 1, std::greater<double>());
+                ippl::Comm->allreduce(wsum, 1, std::plus<double>());
+            }
+            const std::string nm = s.names[i].substr(0, std::min<std::size_t>(s.names[i].size(), 19));
+            const std::string pad(20 - nm.size(), '.');
+            if (i == 0) {
+                msg << nm << pad << " Wall tot = " << std::setw(10) << wmax << "\n\n";
+            } else {
+                msg << nm << pad << " Wall max = " << std::setw(10) << wmax << "\n"
+                    << std::string(20, ' ') << " Wall avg = " << std::setw(10) << wsum / nranks << "\n"
+                    << std::string(20, ' ') << " Wall min = " << std::setw(10) << -wneg << "\n\n";
+            }
+        }
+        msg << "---------------------------------------------\n     Measurement counts:\n---------------------------------------------\n";
+        for (std::size_t i = 0; i < s.names.size(); ++i) {
+            const std::string nm = s.names[i].substr(0, std::min<std::size_t>(s.names[i].size(), 19));
+            msg << nm << std::string(20 - nm.size(), '.') << " Count = " << std::setw(10) << s.count[i] << "\n";
+        }
+        msg << "---------------------------------------------\n";
+        if (rank == 0) os << msg.str() << std::flush;
+    }
+    // Timing::print(fn, problemSize) (IpplTimings.cpp:311-330): the same block into a file, written by rank 0
+    static void print(const std::string& fn, const std::map<std::string, unsigned int>& problemSize = {}) {
+        std::ostringstream body;
+        print(body);
+        if (ippl::Comm && ippl::Comm->rank() != 0) return;
+        std::ofstream f(fn.c_str(), std::ios::out);
+        if (!problemSize.empty()) {
+            f << "Problem size:\n";
+            for (auto& kv : problemSize) f << "    " << std::setw(10) << kv.first << ": " << kv.second << "\n";
+            f << "\n";
+        }
+        f << body.str();
     }
 
 private:
@@ -998,6 +1053,7 @@ private:
         std::map<std::string, int> index;
         std::vector<std::string> names;
         std::vector<double> total;
+        std::vector<long> count;
         std::vector<std::chrono::steady_clock::time_point> start;
     };
     static State& state() {
