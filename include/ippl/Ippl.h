@@ -42,6 +42,7 @@
 #include <string>
 #include <thread>
 #include <type_traits>
+#include <variant>
 #include <vector>
 
 #include <unistd.h>
@@ -542,13 +543,33 @@ namespace detail {
         double a;
         const A* x;
     };
+    // detail::hash_type (src/Types/ViewTypes.h): an index remap in device memory (the reference: Kokkos::View<int*>);
+    // here a non-owning (pointer, length) pair
+    struct hash_type {
+        const int* d = nullptr;
+        std::size_t n = 0;
+        hash_type() = default;
+        hash_type(const int* device_ptr, std::size_t count) : d(device_ptr), n(count) {}
+        const int* data() const { return d; }
+        std::size_t extent(int) const { return n; }
+    };
 }  // namespace detail
+
+// Kokkos::RangePolicy<exec_space>(begin, end) as the alpine drivers build it for scatter (AlpineManager.h:178-181)
+struct RangePolicy1D {
+    long b = 0, e = 0;
+    RangePolicy1D() = default;
+    RangePolicy1D(long begin_, long end_) : b(begin_), e(end_) {}
+    long begin() const { return b; }
+    long end() const { return e; }
+};
 
 template <typename T>
 class ParticleAttrib : public detail::ParticleAttribBase {
 public:
     static constexpr int ncomp = detail::ncomp_of<T>::value;
     using value_type           = T;
+    using hash_type            = detail::hash_type;
     ParticleAttrib()           = default;
     ~ParticleAttrib() override {
         for (auto p : d_)
@@ -638,6 +659,18 @@ public:
             for (std::size_t i = 0; i < count_; ++i) comp(h[i], c) = tmp[i];
         }
     }
+    // scatter(f, pp, policy, hash) (ParticleAttrib.hpp:132-191): deposits the particles policy.begin() .. policy.end(),
+    // taken through the index remap hash_array when one is given
+    template <typename Field, typename PT>
+    void scatter(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp, const RangePolicy1D& policy,
+                 const hash_type& hash_array = {}) const {
+        static_assert(ncomp == 1, "scatter deposits a scalar attribute");
+        b200::check(ipplb_scatter_cic(b200::ctx(), &f.b200_mesh(), policy.begin(), policy.end(), pp.component(0),
+                                      pp.component(1), pp.component(2), d_[0], 0.0, hash_array.extent(0) ? hash_array.data() : nullptr,
+                                      f.data()),
+                    "ParticleAttrib::scatter");
+        f.accumulateHalo();
+    }
     // scatter / gather members (ParticleAttrib.hpp:132-246)
     template <typename Field, typename PT>
     void scatter(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp) const {
@@ -686,6 +719,12 @@ template <typename Attrib1, typename Field, typename Attrib2>
 void scatter(const Attrib1& attrib, Field& f, const Attrib2& pp) { attrib.scatter(f, pp); }
 template <typename Attrib1, typename Field, typename Attrib2>
 void gather(Attrib1& attrib, Field& f, const Attrib2& pp, bool addToAttribute = false) { attrib.gather(f, pp, addToAttribute); }
+// ... and the (policy, hash) overload (ParticleAttrib.hpp:332-334)
+template <typename Attrib1, typename Field, typename Attrib2>
+void scatter(const Attrib1& attrib, Field& f, const Attrib2& pp, const RangePolicy1D& iteration_policy,
+             const typename Attrib1::hash_type& hash_array = {}) {
+    attrib.scatter(f, pp, iteration_policy, hash_array);
+}
 
 // ---- ParticleSpatialLayout (src/Particle/ParticleSpatialLayout.h / .hpp) -----------------------------------------------------------
 template <typename T, unsigned Dim, class Mesh = UniformCartesian<T, Dim>>
@@ -974,6 +1013,74 @@ private:
 }  // namespace ippl
 
 // ---- IpplTimings (src/Utility/IpplTimings.h): named wall timers with a stream fence on start/stop -----------------------------------------------
+namespace ippl {
+// ippl::ParameterList (src/Utility/ParameterList.h:29-160): named solver / FFT parameters of mixed type, nested lists
+// allowed.  Same interface (add / get / get with default / contains / merge / update / operator<<).
+class ParameterList {
+public:
+    using variant_t = std::variant<double, float, bool, std::string, unsigned int, int, std::shared_ptr<ParameterList>>;
+    template <typename T>
+    void add(const std::string& key, const T& value) {
+        if (params_.count(key)) throw IpplException("ParameterList::add()", "Parameter '" + key + "' already exists.");
+        params_[key] = wrap(value);
+    }
+    template <typename T>
+    T get(const std::string& key) const {
+        auto it = params_.find(key);
+        if (it == params_.end()) throw IpplException("ParameterList::get()", "Parameter '" + key + "' not contained.");
+        return unwrap<T>(it->second);
+    }
+    template <typename T>
+    T get(const std::string& key, const T& defval) const {
+        auto it = params_.find(key);
+        return it == params_.end() ? defval : unwrap<T>(it->second);
+    }
+    bool contains(const std::string& key) const { return params_.count(key) != 0; }
+    void merge(const ParameterList& p) noexcept {
+        for (const auto& kv : p.params_) params_[kv.first] = kv.second;
+    }
+    void update(const ParameterList& p) noexcept {
+        for (const auto& kv : p.params_)
+            if (params_.count(kv.first)) params_[kv.first] = kv.second;
+    }
+    template <typename T>
+    void update(const std::string& key, const T& value) {
+        if (!params_.count(key)) throw IpplException("ParameterList::update()", "Parameter '" + key + "' does not exist.");
+        params_[key] = wrap(value);
+    }
+    friend std::ostream& operator<<(std::ostream& os, const ParameterList& p) {
+        p.print(os, 0);
+        return os;
+    }
+
+private:
+    template <typename T>
+    static variant_t wrap(const T& v) {
+        if constexpr (std::is_same_v<T, ParameterList>) return std::make_shared<ParameterList>(v);
+        else if constexpr (std::is_convertible_v<T, std::string> && !std::is_arithmetic_v<T>) return std::string(v);
+        else return v;
+    }
+    template <typename T>
+    static T unwrap(const variant_t& v) {
+        if constexpr (std::is_same_v<T, ParameterList>) return *std::get<std::shared_ptr<ParameterList>>(v);
+        else return std::get<T>(v);
+    }
+    void print(std::ostream& os, int indent) const {
+        std::size_t k = 0;
+        for (const auto& kv : params_) {
+            os << std::string(indent, ' ') << std::left << std::setw(20) << kv.first << " ";
+            std::visit([&](const auto& a) {
+                using A = std::decay_t<decltype(a)>;
+                if constexpr (std::is_same_v<A, std::shared_ptr<ParameterList>>) { os << "\n"; a->print(os, indent + 4); }
+                else os << a;
+            }, kv.second);
+            if (++k != params_.size()) os << "\n";
+        }
+    }
+    std::map<std::string, variant_t> params_;
+};
+}  // namespace ippl
+
 // IpplTimings (src/Utility/IpplTimings.h / .cpp:226-330): wall-clock timers fenced on the context's stream (the reference
 // fences Kokkos); print() reduces every timer over the ranks (max / average / min) and lists the measurement counts,
 // print(file) writes the same block to a file (the drivers' "timing.dat").
