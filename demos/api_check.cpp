@@ -8,7 +8,12 @@ const char* TestName = "api_check";
 #include "Alpine.h"
 
 int main(int argc, char* argv[]) {
-    ippl::initialize(argc, argv);
+    try {
+        ippl::initialize(argc, argv);
+    } catch (const IpplException& ex) {
+        std::cerr << TestName << ": cannot start: " << ex.what() << " (a CUDA device is required; there is no CPU fallback)" << std::endl;
+        return 2;
+    }
     int rc = 0;
     {
         ippl::ParameterList params, fft;
