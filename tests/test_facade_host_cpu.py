@@ -1,0 +1,49 @@
+"""Host-only parts of the C++ facade (include/ippl/Ippl.h) that need no GPU: IpplTimings::print in both forms
+(src/Utility/IpplTimings.cpp:226-330: max / avg / min block, measurement counts, the timing.dat form with the problem
+size) and ippl::ParameterList (src/Utility/ParameterList.h: add / get / default / update / merge / nested lists)."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SRC = r'''
+#include "ippl/Ippl.h"
+int main() {
+    auto a = IpplTimings::getTimer("total");
+    auto b = IpplTimings::getTimer("pushVelocity");
+    IpplTimings::startTimer(a);
+    for (int i = 0; i < 3; ++i) { IpplTimings::startTimer(b); IpplTimings::stopTimer(b); }
+    IpplTimings::stopTimer(a);
+    IpplTimings::print();
+    std::map<std::string, unsigned int> ps{{"nx", 32}};
+    IpplTimings::print(std::string("timing.dat"), ps);
+    ippl::ParameterList p, q, over;
+    p.add("a", 1); p.add("s", "FFT"); p.add("tol", 1e-10); q.add("x", 2.5); p.add("sub", q);
+    over.add("tol", 1e-8); over.add("unknown", 3);
+    p.update(over);
+    bool threw = false;
+    try { p.add("a", 2); } catch (const IpplException&) { threw = true; }
+    int rc = 0;
+    rc |= !threw || p.contains("unknown") || p.get<double>("tol") != 1e-8 || p.get<int>("missing", 7) != 7;
+    rc |= p.get<std::string>("s") != "FFT" || p.get<ippl::ParameterList>("sub").get<double>("x") != 2.5;
+    p.merge(over);
+    rc |= !p.contains("unknown");
+    std::cout << p << std::endl;
+    return rc;
+}
+'''
+
+
+def test_timings_and_parameter_list(tmp_path):
+    (tmp_path / "t.cpp").write_text(SRC)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", f"-I{ROOT}/include", "-I/usr/local/cuda/include", "t.cpp", "-o", "t",
+                           f"-L{ROOT}/ippl_b200", "-lippl_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+                           f"-Wl,-rpath,{ROOT}/ippl_b200"], cwd=tmp_path)
+    out = subprocess.run(["./t"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Timing results for 1 rank(s):" in out.stdout and "Wall tot" in out.stdout
+    assert "pushVelocity........ Wall max" in out.stdout and "Wall avg" in out.stdout and "Wall min" in out.stdout
+    assert "pushVelocity........ Count =          3" in out.stdout
+    dat = (tmp_path / "timing.dat").read_text()
+    assert dat.startswith("Problem size:") and "nx: 32" in dat and "Measurement counts" in dat
