@@ -49,6 +49,14 @@
 
 #include "../ippl_b200.h"
 
+// functions that driver-side device lambdas may call (include/ippl/KokkosShim.cuh, nvcc): host + device under nvcc,
+// plain host functions for the host compiler
+#ifdef __CUDACC__
+#define IPPL_HD __host__ __device__
+#else
+#define IPPL_HD
+#endif
+
 // ---- errors (src/Utility/IpplException.h) ---------------------------------------------------------------------
 class IpplException : public std::runtime_error {
 public:
@@ -244,36 +252,40 @@ inline void fence() { b200::check(ipplb_sync(b200::ctx()), "ippl::fence"); }
 template <typename T, unsigned Dim>
 class Vector {
 public:
-    Vector() { data_.fill(T()); }
-    Vector(const T& v) { data_.fill(v); }
-    Vector(std::initializer_list<T> l) {
-        data_.fill(T());
-        std::copy_n(l.begin(), std::min<std::size_t>(l.size(), Dim), data_.begin());
+    IPPL_HD Vector() {
+        for (unsigned i = 0; i < Dim; ++i) data_[i] = T();
     }
-    T& operator[](unsigned i) { return data_[i]; }
-    const T& operator[](unsigned i) const { return data_[i]; }
-    T* begin() { return data_.data(); }
-    T* end() { return data_.data() + Dim; }
-    const T* begin() const { return data_.data(); }
-    const T* end() const { return data_.data() + Dim; }
-#define IPPL_VEC_OP(op)                                                   \
-    Vector& operator op##=(const Vector& o) {                             \
-        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = o.data_[i];    \
-        return *this;                                                     \
-    }                                                                     \
-    Vector& operator op##=(const T& s) {                                  \
-        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = s;             \
-        return *this;                                                     \
-    }                                                                     \
-    friend Vector operator op(Vector a, const Vector& b) { return a op## = b; } \
-    friend Vector operator op(Vector a, const T& s) { return a op## = s; }
+    IPPL_HD Vector(const T& v) {
+        for (unsigned i = 0; i < Dim; ++i) data_[i] = v;
+    }
+    Vector(std::initializer_list<T> l) {
+        for (unsigned i = 0; i < Dim; ++i) data_[i] = T();
+        std::copy_n(l.begin(), std::min<std::size_t>(l.size(), Dim), data_);
+    }
+    IPPL_HD T& operator[](unsigned i) { return data_[i]; }
+    IPPL_HD const T& operator[](unsigned i) const { return data_[i]; }
+    IPPL_HD T* begin() { return data_; }
+    IPPL_HD T* end() { return data_ + Dim; }
+    IPPL_HD const T* begin() const { return data_; }
+    IPPL_HD const T* end() const { return data_ + Dim; }
+#define IPPL_VEC_OP(op)                                                           \
+    IPPL_HD Vector& operator op##=(const Vector& o) {                             \
+        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = o.data_[i];            \
+        return *this;                                                             \
+    }                                                                             \
+    IPPL_HD Vector& operator op##=(const T& s) {                                  \
+        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = s;                     \
+        return *this;                                                             \
+    }                                                                             \
+    IPPL_HD friend Vector operator op(Vector a, const Vector& b) { return a op## = b; } \
+    IPPL_HD friend Vector operator op(Vector a, const T& s) { return a op## = s; }
     IPPL_VEC_OP(+)
     IPPL_VEC_OP(-)
     IPPL_VEC_OP(*)
     IPPL_VEC_OP(/)
 #undef IPPL_VEC_OP
-    friend Vector operator*(const T& s, Vector a) { return a *= s; }
-    friend Vector operator/(const T& s, const Vector& a) {
+    IPPL_HD friend Vector operator*(const T& s, Vector a) { return a *= s; }
+    IPPL_HD friend Vector operator/(const T& s, const Vector& a) {
         Vector r;
         for (unsigned i = 0; i < Dim; ++i) r[i] = s / a[i];
         return r;
@@ -285,8 +297,75 @@ public:
     }
 
 private:
-    std::array<T, Dim> data_;
+    T data_[Dim];
 };
+
+// ---- views handed to driver-side device lambdas (Kokkos::View stand-ins; see include/ippl/KokkosShim.cuh) -----------------------
+namespace detail {
+    // view(i)[d] on SoA component arrays: what ParticleAttrib<Vector<T, 3>>::getView() returns in the reference
+    // (Kokkos::View<Vector<T, 3>*>, AoS) seen through a proxy
+    struct SoARef3 {
+        double *x, *y, *z;
+        IPPL_HD double& operator[](unsigned d) const { return d == 0 ? *x : (d == 1 ? *y : *z); }
+        IPPL_HD operator Vector<double, 3>() const {
+            Vector<double, 3> v;
+            v[0] = *x; v[1] = *y; v[2] = *z;
+            return v;
+        }
+        IPPL_HD const SoARef3& operator=(const Vector<double, 3>& v) const {
+            *x = v[0]; *y = v[1]; *z = v[2];
+            return *this;
+        }
+    };
+    template <int NC>
+    struct AttribView;
+    template <>
+    struct AttribView<3> {
+        double* c[3];
+        std::size_t n;
+        IPPL_HD SoARef3 operator()(std::size_t i) const { return SoARef3{c[0] + i, c[1] + i, c[2] + i}; }
+        IPPL_HD std::size_t extent(int) const { return n; }
+        IPPL_HD std::size_t size() const { return n; }
+    };
+    template <>
+    struct AttribView<1> {
+        double* c[1];
+        std::size_t n;
+        IPPL_HD double& operator()(std::size_t i) const { return c[0][i]; }
+        IPPL_HD std::size_t extent(int) const { return n; }
+        IPPL_HD std::size_t size() const { return n; }
+    };
+    // ghosted field view, x fastest: view(i, j, k) -> double& (scalar field) or a Vector-like reference (AoS-3 field)
+    struct AoSRef3 {
+        double* p;
+        IPPL_HD double& operator[](unsigned d) const { return p[d]; }
+        IPPL_HD operator Vector<double, 3>() const {
+            Vector<double, 3> v;
+            v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+            return v;
+        }
+        IPPL_HD const AoSRef3& operator=(const Vector<double, 3>& v) const {
+            p[0] = v[0]; p[1] = v[1]; p[2] = v[2];
+            return *this;
+        }
+    };
+    template <int NC>
+    struct FieldView;
+    template <>
+    struct FieldView<1> {
+        double* d;
+        int e[3];  // ghosted extents
+        IPPL_HD double& operator()(long i, long j, long k) const { return d[i + (long)e[0] * (j + (long)e[1] * k)]; }
+        IPPL_HD int extent(int a) const { return e[a]; }
+    };
+    template <>
+    struct FieldView<3> {
+        double* d;
+        int e[3];
+        IPPL_HD AoSRef3 operator()(long i, long j, long k) const { return AoSRef3{d + 3 * (i + (long)e[0] * (j + (long)e[1] * k))}; }
+        IPPL_HD int extent(int a) const { return e[a]; }
+    };
+}  // namespace detail
 
 // ---- Index / NDIndex (src/Index) -------------------------------------------------------------------------------------
 class Index {
@@ -484,6 +563,14 @@ public:
     void accumulateHalo() { halo(1); }
     void fillHalo() { halo(0); }
     int getNghost() const { return nghost_; }
+    // getView(): ghosted local array for driver-side kernels, view(i, j, k) with ghosted local indices (BareField.h)
+    using view_type = detail::FieldView<ncomp>;
+    view_type getView() const {
+        view_type v;
+        v.d = data_;
+        for (int d = 0; d < 3; ++d) v.e[d] = mesh_.nl[d] + 2 * nghost_;
+        return v;
+    }
     Mesh& get_mesh() const { return *mesh_p_; }
     Layout_t& getLayout() const { return *layout_p_; }
     const ipplb_mesh& b200_mesh() const { return mesh_; }
@@ -611,6 +698,15 @@ public:
         capacity_ = n;
     }
     std::size_t size() const { return capacity_; }
+    // getView(): the reference returns a Kokkos::View<T*> for driver-side kernels; here a view(i)[d] / view(i) proxy over
+    // the SoA component arrays, usable inside device lambdas (include/ippl/KokkosShim.cuh)
+    using view_type = detail::AttribView<ncomp>;
+    view_type getView() const {
+        view_type v;
+        for (int c = 0; c < ncomp; ++c) v.c[c] = d_[c];
+        v.n = count_;
+        return v;
+    }
     std::size_t getParticleCount() const { return count_; }
     double* component(int c) const { return d_[c]; }
     // attrib = scalar (ParticleAttrib.hpp:105-116)

@@ -47,3 +47,25 @@ def test_timings_and_parameter_list(tmp_path):
     assert "pushVelocity........ Count =          3" in out.stdout
     dat = (tmp_path / "timing.dat").read_text()
     assert dat.startswith("Problem size:") and "nx: 32" in dat and "Measurement counts" in dat
+
+
+def test_reference_driver_lambdas_compile_unchanged_on_the_shim():
+    """demos/ref_lambdas.cu: the bodies of the reference drivers' Kokkos lambdas (PenningTrap "Kick1" / "Kick2" / "Particle Kinetic Energy" /
+    "Vector E reduce", Landau "Ex stats" over the field and over the particles, BumponTail "Ex inner product" / "Ex max norm") are cut out of /root/reference at build time and compiled by nvcc
+    for sm_100a on include/ippl/KokkosShim.cuh, unchanged.  Here: it builds, holds one kernel per lambda, leaves no
+    reference text behind, and refuses to run without a GPU (running it is a GPU-box job)."""
+    import pytest
+    if not os.path.isdir("/root/reference/demos/alpine"):
+        pytest.skip("needs the reference tree")
+    demos = os.path.join(ROOT, "demos")
+    subprocess.check_call(["make", "-C", demos, "-s", "ref_lambdas"])
+    exe = os.path.join(demos, "ref_lambdas")
+    assert os.path.exists(exe)
+    syms = subprocess.run(["cuobjdump", "-res-usage", exe], capture_output=True, text=True).stdout
+    kernels = [l for l in syms.splitlines() if "Function" in l]
+    # Kick1, Kick2 | Landau particles, Penning kinetic, Penning vector E, BumponTail inner, BumponTail max | Landau field
+    assert sum("for_kernel" in k for k in kernels) == 2 and sum("reduce1_kernel" in k for k in kernels) == 5 \
+        and sum("reduce2_kernel" in k for k in kernels) == 1, kernels
+    assert not [f for f in os.listdir(demos) if f.endswith(".inc")]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "no CPU fallback" in out.stderr
