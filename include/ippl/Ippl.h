@@ -69,31 +69,49 @@ private:
     std::string meth_, descr_;
 };
 
-// ---- Inform (src/Utility/Inform.h): rank-0 message stream ------------------------------------------------------
+// ---- Inform (src/Utility/Inform.h): message stream of one rank (default: rank 0) to stdout or to a file -----------------
+constexpr int INFORM_ALL_NODES = -1;
 class Inform {
 public:
-    explicit Inform(const char* name = nullptr) : name_(name ? name : "") {}
+    enum WriteMode { OVERWRITE, APPEND };
+    explicit Inform(const char* name = nullptr, int printNode = 0) : name_(name ? name : ""), node_(printNode) {}
+    // Inform(name, file, mode, node): the drivers' CSV dumps (e.g. LandauDampingManager.h:377)
+    Inform(const char* name, const char* fname, WriteMode mode, int printNode = 0) : name_(name ? name : ""), node_(printNode) {
+        if (node_ == INFORM_ALL_NODES || rank_ref() == node_)
+            file_ = std::make_unique<std::ofstream>(fname, mode == APPEND ? std::ios::app : std::ios::trunc);
+        to_file_ = true;
+    }
     template <typename T>
     Inform& operator<<(const T& v) {
         buf_ << v;
         return *this;
     }
     Inform& operator<<(Inform& (*f)(Inform&)) { return f(*this); }
+    std::streamsize precision(std::streamsize p) { return buf_.precision(p); }
+    std::ios::fmtflags setf(std::ios::fmtflags f, std::ios::fmtflags mask) { return buf_.setf(f, mask); }
     void flush() {
-        if (level_on() && rank_ref() == 0) std::cout << (name_.empty() ? "" : name_ + "> ") << buf_.str() << std::endl;
+        const bool mine = node_ == INFORM_ALL_NODES || rank_ref() == node_;
+        if (to_file_) {
+            if (file_) *file_ << buf_.str() << std::endl;
+        } else if (level_on() && mine) {
+            std::cout << (name_.empty() ? "" : name_ + "> ") << buf_.str() << std::endl;
+        }
         buf_.str("");
     }
     static bool& level_on() {
         static bool on = true;
         return on;
     }
-    static int& rank_ref() {  // set by ippl::initialize: only rank 0 prints, like the reference's Inform
+    static int& rank_ref() {  // set by ippl::initialize
         static int r = 0;
         return r;
     }
 
 private:
     std::string name_;
+    int node_ = 0;
+    bool to_file_ = false;
+    std::unique_ptr<std::ofstream> file_;
     std::ostringstream buf_;
 };
 inline Inform& endl(Inform& m) {
@@ -139,6 +157,7 @@ class Communicator {
 public:
     int rank() const { return rank_; }
     int size() const { return size_; }
+    int getCommunicator() const { return 0; }   // the MPI_Comm stand-in of include/ippl/compat (one process per GPU, NCCL underneath)
     // Communicator::barrier (src/Communicate/Communicator.h): drains this rank's stream, then a rank barrier (one small
     // all-reduce over NCCL, host-synchronous like MPI_Barrier)
     void barrier() {
@@ -258,38 +277,39 @@ public:
     IPPL_HD Vector(const T& v) {
         for (unsigned i = 0; i < Dim; ++i) data_[i] = v;
     }
-    Vector(std::initializer_list<T> l) {
-        for (unsigned i = 0; i < Dim; ++i) data_[i] = T();
-        std::copy_n(l.begin(), std::min<std::size_t>(l.size(), Dim), data_);
+    IPPL_HD Vector(std::initializer_list<T> l) {
+        unsigned i = 0;
+        for (const T* p = l.begin(); p != l.end() && i < Dim; ++p, ++i) data_[i] = *p;
+        for (; i < Dim; ++i) data_[i] = T();
     }
     IPPL_HD T& operator[](unsigned i) { return data_[i]; }
     IPPL_HD const T& operator[](unsigned i) const { return data_[i]; }
+    IPPL_HD T& operator()(unsigned i) { return data_[i]; }   // element access with call syntax (src/Types/Vector.h)
+    IPPL_HD const T& operator()(unsigned i) const { return data_[i]; }
     IPPL_HD T* begin() { return data_; }
     IPPL_HD T* end() { return data_ + Dim; }
     IPPL_HD const T* begin() const { return data_; }
     IPPL_HD const T* end() const { return data_ + Dim; }
+    // converting copy (Vector<long> -> Vector<double> etc.)
+    template <typename U>
+    IPPL_HD Vector(const Vector<U, Dim>& o) {
+        for (unsigned i = 0; i < Dim; ++i) data_[i] = static_cast<T>(o[i]);
+    }
 #define IPPL_VEC_OP(op)                                                           \
-    IPPL_HD Vector& operator op##=(const Vector& o) {                             \
-        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = o.data_[i];            \
+    template <typename U>                                                         \
+    IPPL_HD Vector& operator op##=(const Vector<U, Dim>& o) {                     \
+        for (unsigned i = 0; i < Dim; ++i) data_[i] op## = o[i];                  \
         return *this;                                                             \
     }                                                                             \
     IPPL_HD Vector& operator op##=(const T& s) {                                  \
         for (unsigned i = 0; i < Dim; ++i) data_[i] op## = s;                     \
         return *this;                                                             \
-    }                                                                             \
-    IPPL_HD friend Vector operator op(Vector a, const Vector& b) { return a op## = b; } \
-    IPPL_HD friend Vector operator op(Vector a, const T& s) { return a op## = s; }
+    }
     IPPL_VEC_OP(+)
     IPPL_VEC_OP(-)
     IPPL_VEC_OP(*)
     IPPL_VEC_OP(/)
 #undef IPPL_VEC_OP
-    IPPL_HD friend Vector operator*(const T& s, Vector a) { return a *= s; }
-    IPPL_HD friend Vector operator/(const T& s, const Vector& a) {
-        Vector r;
-        for (unsigned i = 0; i < Dim; ++i) r[i] = s / a[i];
-        return r;
-    }
     friend std::ostream& operator<<(std::ostream& os, const Vector& v) {
         os << "( ";
         for (unsigned i = 0; i < Dim; ++i) os << v[i] << (i + 1 < Dim ? " , " : " )");
@@ -299,6 +319,33 @@ public:
 private:
     T data_[Dim];
 };
+
+// element-wise arithmetic with the usual promotions (Vector<long> + 0.5 is a Vector<double>, Vector<double> / Vector<int> too):
+// the drivers mix index vectors and coordinates (LandauDampingManager.h:90-92, :193-194)
+#define IPPL_VEC_BIN(op)                                                                                          \
+    template <typename T, typename U, unsigned Dim>                                                               \
+    IPPL_HD Vector<std::common_type_t<T, U>, Dim> operator op(const Vector<T, Dim>& a, const Vector<U, Dim>& b) {  \
+        Vector<std::common_type_t<T, U>, Dim> r;                                                                   \
+        for (unsigned i = 0; i < Dim; ++i) r[i] = a[i] op b[i];                                                    \
+        return r;                                                                                                  \
+    }                                                                                                              \
+    template <typename T, typename U, unsigned Dim, std::enable_if_t<std::is_arithmetic<U>::value, int> = 0>       \
+    IPPL_HD Vector<std::common_type_t<T, U>, Dim> operator op(const Vector<T, Dim>& a, const U& s) {               \
+        Vector<std::common_type_t<T, U>, Dim> r;                                                                   \
+        for (unsigned i = 0; i < Dim; ++i) r[i] = a[i] op s;                                                       \
+        return r;                                                                                                  \
+    }                                                                                                              \
+    template <typename T, typename U, unsigned Dim, std::enable_if_t<std::is_arithmetic<U>::value, int> = 0>       \
+    IPPL_HD Vector<std::common_type_t<T, U>, Dim> operator op(const U& s, const Vector<T, Dim>& a) {               \
+        Vector<std::common_type_t<T, U>, Dim> r;                                                                   \
+        for (unsigned i = 0; i < Dim; ++i) r[i] = s op a[i];                                                       \
+        return r;                                                                                                  \
+    }
+IPPL_VEC_BIN(+)
+IPPL_VEC_BIN(-)
+IPPL_VEC_BIN(*)
+IPPL_VEC_BIN(/)
+#undef IPPL_VEC_BIN
 
 // ---- views handed to driver-side device lambdas (Kokkos::View stand-ins; see include/ippl/KokkosShim.cuh) -----------------------
 namespace detail {
@@ -370,12 +417,12 @@ namespace detail {
 // ---- Index / NDIndex (src/Index) -------------------------------------------------------------------------------------
 class Index {
 public:
-    Index() : first_(0), length_(0) {}
-    explicit Index(int n) : first_(0), length_(n) {}
-    Index(int first, int last) : first_(first), length_(last - first + 1) {}
-    int first() const { return first_; }
-    int last() const { return first_ + length_ - 1; }
-    int length() const { return length_; }
+    IPPL_HD Index() : first_(0), length_(0) {}
+    IPPL_HD explicit Index(int n) : first_(0), length_(n) {}
+    IPPL_HD Index(int first, int last) : first_(first), length_(last - first + 1) {}
+    IPPL_HD int first() const { return first_; }
+    IPPL_HD int last() const { return first_ + length_ - 1; }
+    IPPL_HD int length() const { return length_; }
 
 private:
     int first_, length_;
@@ -383,19 +430,55 @@ private:
 template <unsigned Dim>
 class NDIndex {
 public:
-    NDIndex() = default;
+    IPPL_HD NDIndex() {}
     template <typename... Idx>
-    NDIndex(const Idx&... i) : idx_{i...} {}
-    Index& operator[](unsigned d) { return idx_[d]; }
-    const Index& operator[](unsigned d) const { return idx_[d]; }
-    std::size_t size() const {
+    IPPL_HD NDIndex(const Idx&... i) : idx_{i...} {}
+    IPPL_HD Index& operator[](unsigned d) { return idx_[d]; }
+    IPPL_HD const Index& operator[](unsigned d) const { return idx_[d]; }
+    IPPL_HD std::size_t size() const {
         std::size_t s = 1;
-        for (auto& i : idx_) s *= i.length();
+        for (unsigned d = 0; d < Dim; ++d) s *= idx_[d].length();
         return s;
+    }
+    // first / last / length of every dimension as index vectors (src/Index/NDIndex.hpp)
+    IPPL_HD Vector<int, Dim> first() const {
+        Vector<int, Dim> v;
+        for (unsigned d = 0; d < Dim; ++d) v[d] = idx_[d].first();
+        return v;
+    }
+    IPPL_HD Vector<int, Dim> last() const {
+        Vector<int, Dim> v;
+        for (unsigned d = 0; d < Dim; ++d) v[d] = idx_[d].last();
+        return v;
+    }
+    IPPL_HD Vector<int, Dim> length() const {
+        Vector<int, Dim> v;
+        for (unsigned d = 0; d < Dim; ++d) v[d] = idx_[d].length();
+        return v;
     }
 
 private:
-    std::array<Index, Dim> idx_;
+    Index idx_[Dim];
+};
+
+template <unsigned Dim>
+std::ostream& operator<<(std::ostream& os, const NDIndex<Dim>& n) {
+    os << "{";
+    for (unsigned d = 0; d < Dim; ++d) os << "[" << n[d].first() << ":" << n[d].last() << ":1]" << (d + 1 < Dim ? "," : "");
+    return os << "}";
+}
+
+// ippl::RangePolicy<Dim> (src/Utility/ParallelDispatch.h): the index box of a field kernel; the device side of
+// ippl::parallel_for / parallel_reduce over it is in include/ippl/KokkosShim.cuh
+template <unsigned Dim>
+struct RangePolicy {
+    static_assert(Dim == 3, "the B200 path is three-dimensional");
+    using index_type       = long;
+    using index_array_type = Vector<long, Dim>;
+    struct policy_type {
+        long lo[3], hi[3];   // [lo, hi) in ghosted local indices
+        long count() const { return (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]); }
+    };
 };
 
 enum BC { PERIODIC, REFLECTIVE, SINK, NO };
@@ -543,6 +626,12 @@ public:
         b200::check(ipplb_field_fill(b200::ctx(), data_, (long)(cells_ * ncomp), v), "Field::operator=");
         return *this;
     }
+    // field = expression object that knows how to evaluate itself into a field (include/ippl/compat: dot(E, E))
+    template <class Expr, class = decltype(std::declval<const Expr&>().assign_to(std::declval<Field&>()))>
+    Field& operator=(const Expr& e) {
+        e.assign_to(*this);
+        return *this;
+    }
     // field = field / c  and  field = field - s on the interior (expression assignment, BareField.hpp:187-205)
     Field& operator=(const detail::FieldAffine<Field>& e) {
         if (e.f != this) throw IpplException("Field::operator=", "only f = f / c and f = f - s are supported by the facade");
@@ -563,6 +652,21 @@ public:
     void accumulateHalo() { halo(1); }
     void fillHalo() { halo(0); }
     int getNghost() const { return nghost_; }
+    // field boundary conditions: the drivers set an all-periodic set for the potential of the CG / FEM solvers; the
+    // periodic FFT path has the periodicity in the FieldLayout, so the object is only accepted
+    template <class B>
+    void setFieldBC(const B&) {}
+    int getFieldBC() const { return 0; }
+    // getFieldRangePolicy(nghost): the field's index box without its ghost layers (BareField.hpp)
+    typename RangePolicy<Dim>::policy_type getFieldRangePolicy(int nghost = -1) const {
+        typename RangePolicy<Dim>::policy_type p;
+        const int g = nghost < 0 ? nghost_ : nghost;
+        for (int d = 0; d < 3; ++d) {
+            p.lo[d] = g;
+            p.hi[d] = mesh_.nl[d] + 2 * nghost_ - g;
+        }
+        return p;
+    }
     // getView(): ghosted local array for driver-side kernels, view(i, j, k) with ghosted local indices (BareField.h)
     using view_type = detail::FieldView<ncomp>;
     view_type getView() const {
@@ -612,6 +716,11 @@ namespace detail {
         virtual ~ParticleAttribBase()                 = default;
         virtual void create(std::size_t n)            = 0;
         virtual void setCount(std::size_t n)          = 0;
+        // what the multi-rank exchange needs to know about an attribute without its type
+        virtual int components() const                = 0;
+        virtual double* component_ptr(int c) const    = 0;
+        virtual std::size_t capacity() const          = 0;
+        virtual void reserve_storage(std::size_t n)   = 0;
         void set_name(const std::string& n) { name_ = n; }
         const std::string& get_name() const { return name_; }
 
@@ -698,15 +807,21 @@ public:
         capacity_ = n;
     }
     std::size_t size() const { return capacity_; }
+    int components() const override { return ncomp; }
+    double* component_ptr(int c) const override { return d_[c]; }
+    std::size_t capacity() const override { return capacity_; }
+    void reserve_storage(std::size_t n) override { reserve(n); }
     // getView(): the reference returns a Kokkos::View<T*> for driver-side kernels; here a view(i)[d] / view(i) proxy over
     // the SoA component arrays, usable inside device lambdas (include/ippl/KokkosShim.cuh)
     using view_type = detail::AttribView<ncomp>;
-    view_type getView() const {
+    IPPL_HD view_type getView() const {
         view_type v;
         for (int c = 0; c < ncomp; ++c) v.c[c] = d_[c];
         v.n = count_;
         return v;
     }
+    // attrib(i): element access inside kernels (src/Particle/ParticleAttrib.h)
+    IPPL_HD auto operator()(std::size_t i) const -> decltype(std::declval<view_type>()(i)) { return getView()(i); }
     std::size_t getParticleCount() const { return count_; }
     double* component(int c) const { return d_[c]; }
     // attrib = scalar (ParticleAttrib.hpp:105-116)
@@ -907,8 +1022,42 @@ public:
     }
     PLayout& getLayout() { return *layout_; }
     void update() { layout_->update(*this); }
-    // multi-rank exchange of R and the attributes a derived container exposes through migration_bundle()
-    virtual void migrate() { throw IpplException("ParticleBase::migrate", "container does not expose a migration bundle"); }
+    // Multi-rank exchange behind update() (ParticleSpatialLayout.hpp:150-314, ParticleBase.hpp:175-393).  The C-ABI moves a
+    // fixed bundle: the positions R, one vector attribute (the first one registered: the alpine containers' velocity P) and
+    // one scalar attribute (the first one registered: the charge q).  Further attributes (the alpine containers' E) are
+    // resized only: the drivers recompute them before they read them (gather after every update).  Two collective halves:
+    // the plan exchanges the counts, the attributes grow to hold the arrivals (times the over-allocation factor), the
+    // commit moves the particles.
+    virtual void migrate() {
+        detail::ParticleAttribBase *vec = nullptr, *sca = nullptr;
+        for (auto* a : attributes_) {
+            if (a == &R) continue;
+            if (!vec && a->components() == 3) vec = a;
+            if (!sca && a->components() == 1) sca = a;
+        }
+        auto bundle = [&]() {
+            ipplb_particles b{};
+            b.x = R.component(0); b.y = R.component(1); b.z = R.component(2);
+            if (vec) { b.px = vec->component_ptr(0); b.py = vec->component_ptr(1); b.pz = vec->component_ptr(2); }
+            if (sca) b.q = sca->component_ptr(0);
+            b.n        = (long)localNum_;
+            b.capacity = (long)R.size();
+            if (vec) b.capacity = std::min<long>(b.capacity, (long)vec->capacity());
+            if (sca) b.capacity = std::min<long>(b.capacity, (long)sca->capacity());
+            return b;
+        };
+        ipplb_particles b = bundle();
+        long n_after      = b.n;
+        const int rc      = ipplb_update_plan(b200::ctx(), &b, &n_after, nullptr, nullptr);
+        if (rc != IPPLB_OK && rc != IPPLB_ERR_CAPACITY) b200::check(rc, "ParticleBase::update (plan)");
+        if (n_after > b.capacity) {
+            const std::size_t want = (std::size_t)n_after * (std::size_t)std::max(1, (int)Comm->getDefaultOverallocation());
+            for (auto* a : attributes_) a->reserve_storage(want);
+            b = bundle();
+        }
+        b200::check(ipplb_update_commit(b200::ctx(), &b), "ParticleBase::update (commit)");
+        setLocalNum((std::size_t)b.n);
+    }
 
 protected:
     PLayout* layout_ = nullptr;
@@ -939,6 +1088,8 @@ namespace detail {
 }  // namespace detail
 
 // ---- Random (src/Random/Distribution.h, NormalDistribution.h, InverseTransformSampling.h, Randn.h) on the device sampler ------------------
+// (include/ippl/compat/Random/*.h provide the reference's functor-shaped classes instead when the reference's own drivers are compiled)
+#ifndef IPPL_B200_REFERENCE_SHAPED_RANDOM
 namespace random {
     // Distribution<T, Dim, 2 * Dim, Functions>: the reference takes host/device functors (CDF, PDF, Estimate); the
     // facade names the three families the alpine managers use (one per dimension) and the device evaluates them
@@ -1023,6 +1174,7 @@ namespace random {
                     "random::randn");
     }
 }  // namespace random
+#endif  // IPPL_B200_REFERENCE_SHAPED_RANDOM
 
 // ---- OrthogonalRecursiveBisection (src/Decomposition/OrthogonalRecursiveBisection.h / .hpp) ---------------------------------------------
 template <class FieldT, class Tp = double>
@@ -1081,6 +1233,9 @@ public:
     ~FFTPeriodicPoissonSolver() {
         if (h_) ipplb_poisson_destroy(h_);
     }
+    // heFFTe options / output type: the cuFFT stage always returns the gradient (GRAD), the rest does not apply
+    template <class PL>
+    void mergeParameters(const PL&) {}
     void setRhs(FieldRHS& rhs) {
         rhs_ = &rhs;
         if (h_) ipplb_poisson_destroy(h_);
@@ -1153,6 +1308,7 @@ private:
     template <typename T>
     static variant_t wrap(const T& v) {
         if constexpr (std::is_same_v<T, ParameterList>) return std::make_shared<ParameterList>(v);
+        else if constexpr (std::is_enum_v<T>) return static_cast<int>(v);
         else if constexpr (std::is_convertible_v<T, std::string> && !std::is_arithmetic_v<T>) return std::string(v);
         else return v;
     }

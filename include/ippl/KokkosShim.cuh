@@ -232,6 +232,7 @@ template <class T>
 struct View;
 template <class T>
 struct View<T*> {
+    using execution_space = DefaultExecutionSpace;
     T* d = nullptr;
     std::size_t n = 0;
     std::shared_ptr<void> own;   // host-side ownership; device copies of the view carry only (d, n)
@@ -269,17 +270,6 @@ __host__ __device__ inline detail::DotValue dot(const Vector<double, 3>& a, cons
 
 // ---- ippl::parallel_for / parallel_reduce over a field's index range (src/Utility/ParallelDispatch.h) --------------------------
 namespace ippl {
-
-template <unsigned Dim>
-struct RangePolicy {
-    static_assert(Dim == 3, "the B200 path is three-dimensional");
-    using index_type       = long;
-    using index_array_type = Vector<long, Dim>;
-    struct policy_type {
-        long lo[3], hi[3];   // [lo, hi) in ghosted local indices
-        long count() const { return (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]); }
-    };
-};
 
 // getRangePolicy(view, shift): the view's index range without `shift` ghost layers on every side
 template <class View>
