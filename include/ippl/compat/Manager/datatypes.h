@@ -31,10 +31,6 @@ namespace detail {
     private:
         NoSpace space_;
     };
-    template <bool B, class T>
-    using ConditionalType = T;   // every alias below is used with Dim == 3
-    template <class... T>
-    using VariantFromConditionalTypes = std::variant<T...>;
 }  // namespace detail
 template <class Lhs, class Rhs> using PoissonCG = detail::UnavailableSolver<0, Lhs, Rhs>;
 template <class Lhs, class Rhs> using NullSolver = detail::UnavailableSolver<1, Lhs, Rhs>;
@@ -44,47 +40,42 @@ template <class Lhs, class Rhs> using FEMPoissonSolver = detail::UnavailableSolv
 template <class Lhs, class Rhs> using PreconditionedFEMPoissonSolver = detail::UnavailableSolver<5, Lhs, Rhs>;
 }  // namespace ippl
 
-template <unsigned Dim>
-using Mesh_t = ippl::UniformCartesian<double, Dim>;
-template <typename T, unsigned Dim>
-using PLayout_t = typename ippl::ParticleSpatialLayout<T, Dim, Mesh_t<Dim>>;
-template <unsigned Dim>
-using Centering_t = typename Mesh_t<Dim>::DefaultCentering;
-template <unsigned Dim>
-using FieldLayout_t = ippl::FieldLayout<Dim>;
+// ---- the global aliases the drivers spell (names fixed by the reference's src/Manager/datatypes.h) -------------------
+// geometry and layouts
+template <unsigned D> using Mesh_t = ippl::UniformCartesian<double, D>;
+template <unsigned D> using Centering_t = typename Mesh_t<D>::DefaultCentering;
+template <unsigned D> using FieldLayout_t = ippl::FieldLayout<D>;
+template <typename Real, unsigned D> using PLayout_t = ippl::ParticleSpatialLayout<Real, D, Mesh_t<D>>;
 using size_type = ippl::detail::size_type;
-template <typename T, unsigned Dim>
-using Vector = ippl::Vector<T, Dim>;
-template <typename T, unsigned Dim = 3, class... ViewArgs>
-using Field = ippl::Field<T, Dim, Mesh_t<Dim>, Centering_t<Dim>>;
-template <typename T = double, unsigned Dim = 3>
-using ORB = ippl::OrthogonalRecursiveBisection<Field<double, Dim>, T>;
-template <typename T>
-using ParticleAttrib = ippl::ParticleAttrib<T>;
-template <typename T, unsigned Dim>
-using Vector_t = ippl::Vector<T, Dim>;
-template <unsigned Dim, class... ViewArgs>
-using Field_t = Field<double, Dim>;
-template <typename T = double, unsigned Dim = 3, class... ViewArgs>
-using VField_t = Field<Vector_t<T, Dim>, Dim>;
-template <typename T = double, unsigned Dim = 3>
-using CGSolver_t = ippl::PoissonCG<Field<T, Dim>, Field_t<Dim>>;
-template <typename T = double, unsigned Dim = 3>
-using NullSolver_t = ippl::NullSolver<VField_t<T, Dim>, Field_t<Dim>>;
-using ippl::detail::ConditionalType, ippl::detail::VariantFromConditionalTypes;
-template <typename T = double, unsigned Dim = 3>
-using FFTSolver_t = ConditionalType<Dim == 2 || Dim == 3, ippl::FFTPeriodicPoissonSolver<VField_t<T, Dim>, Field_t<Dim>>>;
-template <typename T = double, unsigned Dim = 3>
-using FFTTruncatedGreenSolver_t = ConditionalType<Dim == 3, ippl::FFTTruncatedGreenPeriodicPoissonSolver<VField_t<T, Dim>, Field_t<Dim>>>;
-template <typename T = double, unsigned Dim = 3>
-using OpenSolver_t = ConditionalType<Dim == 3, ippl::FFTOpenPoissonSolver<VField_t<T, Dim>, Field_t<Dim>>>;
-template <typename T = double, unsigned Dim = 3>
-using FEMSolver_t = ippl::FEMPoissonSolver<Field<T, Dim>, Field<T, Dim>>;
-template <typename T = double, unsigned Dim = 3>
-using FEMPreconSolver_t = ippl::PreconditionedFEMPoissonSolver<Field<T, Dim>, Field<T, Dim>>;
-template <typename T = double, unsigned Dim = 3>
-using Solver_t = VariantFromConditionalTypes<CGSolver_t<T, Dim>, FFTSolver_t<T, Dim>, FFTTruncatedGreenSolver_t<T, Dim>,
-                                             OpenSolver_t<T, Dim>, NullSolver_t<T, Dim>, FEMSolver_t<T, Dim>,
-                                             FEMPreconSolver_t<T, Dim>>;
-extern const char* TestName;
+
+// values, attributes, fields (trailing packs: the reference forwards Kokkos view arguments, the SoA facade has none)
+template <typename V, unsigned D> using Vector = ippl::Vector<V, D>;
+template <typename V, unsigned D> using Vector_t = ippl::Vector<V, D>;
+template <typename V> using ParticleAttrib = ippl::ParticleAttrib<V>;
+template <typename V, unsigned D = 3, class... Unused> using Field = ippl::Field<V, D, Mesh_t<D>, Centering_t<D>>;
+template <unsigned D, class... Unused> using Field_t = Field<double, D>;
+template <typename Real = double, unsigned D = 3, class... Unused> using VField_t = Field<Vector_t<Real, D>, D>;
+template <typename Real = double, unsigned D = 3> using ORB = ippl::OrthogonalRecursiveBisection<Field<double, D>, Real>;
+
+// solvers: IPPLC_SOLVER(alias, class, lhs, rhs) declares `alias<Real, D>`
+#define IPPLC_SOLVER(ALIAS, CLASS, LHS, RHS) \
+    template <typename Real = double, unsigned D = 3> using ALIAS = ippl::CLASS<LHS, RHS>
+#define IPPLC_SCALAR Field<Real, D>
+#define IPPLC_GRAD VField_t<Real, D>
+IPPLC_SOLVER(FFTSolver_t, FFTPeriodicPoissonSolver, IPPLC_GRAD, Field_t<D>);   // the one wired to cuFFT
+IPPLC_SOLVER(CGSolver_t, PoissonCG, IPPLC_SCALAR, Field_t<D>);
+IPPLC_SOLVER(NullSolver_t, NullSolver, IPPLC_GRAD, Field_t<D>);
+IPPLC_SOLVER(FFTTruncatedGreenSolver_t, FFTTruncatedGreenPeriodicPoissonSolver, IPPLC_GRAD, Field_t<D>);
+IPPLC_SOLVER(OpenSolver_t, FFTOpenPoissonSolver, IPPLC_GRAD, Field_t<D>);
+IPPLC_SOLVER(FEMSolver_t, FEMPoissonSolver, IPPLC_SCALAR, IPPLC_SCALAR);
+IPPLC_SOLVER(FEMPreconSolver_t, PreconditionedFEMPoissonSolver, IPPLC_SCALAR, IPPLC_SCALAR);
+#undef IPPLC_SOLVER
+// alternative order = the order the drivers' std::get<> / holds_alternative<> calls were written against
+template <typename Real = double, unsigned D = 3>
+using Solver_t = std::variant<CGSolver_t<Real, D>, FFTSolver_t<Real, D>, FFTTruncatedGreenSolver_t<Real, D>, OpenSolver_t<Real, D>,
+                              NullSolver_t<Real, D>, FEMSolver_t<Real, D>, FEMPreconSolver_t<Real, D>>;
+#undef IPPLC_SCALAR
+#undef IPPLC_GRAD
+
+extern const char* TestName;   // every driver defines it
 #endif

@@ -1,0 +1,68 @@
+"""The reference's OWN alpine drivers, compiled unchanged (`make -C demos ref`: /root/reference/demos/alpine/*.cpp and the
+*Manager.h / FieldContainer / FieldSolver / LoadBalancer / ParticleContainer headers behind them, built here against
+include/ippl/compat; the binaries travel to the GPU box, the reference tree does not), run on a GPU.
+
+STATUS: these binaries were built for sm_100a in round 2 but never executed -- the round's GPU budget was spent before
+the compat layer existed.  The tests are therefore marked xfail(strict=False): a pass shows up as XPASS, a failure does
+not turn the suite red, and either way the first real execution is recorded.  The file sorts last on purpose.
+
+Checks: demos/ref_lambdas (eight driver lambdas cut out of the reference at build time, compared against the C-ABI
+kernels inside the binary); ref_LandauDamping against the reference's known-answer CSV at its own tolerance
+(demos/alpine/validation/CMakeLists.txt:23-26); ref_BumponTailInstability / ref_PenningTrap against the same physical
+anchors tests/test_facade.py uses for the restated drivers."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="reference drivers built unchanged for sm_100a but not yet executed on a GPU")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _exe(name):
+    path = os.path.join(ROOT, "demos", name)
+    if not os.path.exists(path):
+        pytest.skip(f"demos/{name} was not built (needs the reference tree at build time)")
+    return path
+
+
+def _run(tmp_path, exe, grid, np_, nt, csv):
+    d = tmp_path / exe
+    (d / "data").mkdir(parents=True)
+    cmd = [_exe(exe), str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
+           "--info", "0"]
+    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return np.loadtxt(d / "data" / csv, skiprows=1)
+
+
+def test_reference_lambdas_against_cabi_kernels():
+    out = subprocess.run([_exe("ref_lambdas")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_reference_landau_driver_reproduces_known_answer(tmp_path):
+    golden = np.loadtxt(os.path.join(ROOT, "tests", "golden", "FieldLandau_valid_result.csv"), skiprows=1)
+    got = _run(tmp_path, "ref_LandauDamping", 16, 10000000, 25, "FieldLandau_1_manager.csv")
+    assert got.shape == golden.shape == (26, 3)
+    assert np.allclose(got[:, 0], golden[:, 0], atol=1e-12)
+    assert np.max(np.abs(got[:, 1:] - golden[:, 1:])) <= 0.4
+    assert got[-1, 1] < 0.7 * got[0, 1]
+
+
+def test_reference_bumpontail_driver(tmp_path):
+    got = _run(tmp_path, "ref_BumponTailInstability", 16, 4000000, 10, "FieldBumponTail_1_manager.csv")
+    assert got.shape == (11, 3) and np.isfinite(got).all()
+    k, delta = 0.21, 0.01
+    theory = 0.5 * (delta / k) ** 2 * (2 * np.pi / k) ** 3
+    assert 0.8 * theory <= got[0, 1] <= 1.6 * theory, (got[0, 1], theory)
+
+
+def test_reference_penningtrap_driver(tmp_path):
+    got = _run(tmp_path, "ref_PenningTrap", 32, 2000000, 12, "ParticleField_1_manager.csv")
+    assert got.shape == (13, 8) and np.isfinite(got).all() and (got[:, 1:] > 0).all()
+    assert abs(got[0, 2] / (1.5 * 2000000) - 1.0) <= 5e-3
+    h3 = (20.0 / 32) ** 3
+    assert np.allclose(got[:, 1], 0.5 * h3 * (got[:, 5] ** 2 + got[:, 6] ** 2 + got[:, 7] ** 2), rtol=1e-8)
