@@ -309,7 +309,8 @@ int ipplb_bins_migrate(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, c
  * one kernel that drops the arrivals into their buckets (overflow: tail) and deposits their charge into rho (may be
  * NULL).  Nothing synchronises with the host: cur->n is NOT refreshed (ipplb_bins_status reports the device truth) and
  * errors surface as the sticky IPPLB_FLAG_* bits.  ipplb_migrate_counts (synchronises) returns the per-rank counts of
- * the last migration for checks. */
+ * the last migration for checks.  seg_cap must be ONE number for the job (senders and receivers address the segments
+ * with it): the ranks agree on the largest value any of them passed. */
 int ipplb_migrate_connect(ipplb_ctx* ctx, long seg_cap);
 int ipplb_bins_migrate_async(ipplb_ctx* ctx, ipplb_bins* bins, ipplb_particles* cur, double* rho);
 int ipplb_migrate_counts(ipplb_ctx* ctx, long* sent_host, long* recv_host);

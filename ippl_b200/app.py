@@ -123,7 +123,8 @@ class MiniApp:
         self.exit_buf, self.p2p = None, False
         if world > 1 and self.mode == 2:
             # leavers per (source, destination) pair and step: ~n / 100 across a face at C2; 8x head-room
-            seg = max(self.n_mine // (12 * max(1, round(world ** (1 / 3)))), 1 << 16)
+            # (one number for the whole job: sized from the largest rank; ipplb_migrate_connect also takes the max over ranks)
+            seg = max(max(counts) // (12 * max(1, round(world ** (1 / 3)))), 1 << 16)
             try:
                 ctx.migrate_connect(seg)     # peer-memory inboxes over NVLink (cudaIpc): no message, no host sync
                 self.p2p = True

@@ -952,6 +952,19 @@ int ipplb_migrate_connect(ipplb_ctx* ctx, long seg_cap) {
         IPPLB_NCCL(ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
         IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    // One segment size for the whole job: a sender addresses segment `me` of the destination's inbox with ITS seg_cap, the
+    // destination reads segment s with its own -- the two must be the same number.  Callers size seg_cap from rank-local
+    // particle counts (unequal after an ORB repartition), so the ranks agree on the largest request here.
+    {
+        if ((rc = ensure(ctx, ctx->reduce, sizeof(double) * 2048))) return rc;
+        long long* d_seg = (long long*)((double*)ctx->reduce.ptr + 1904);
+        long long h_seg  = seg_cap;
+        IPPLB_CUDA(cudaMemcpyAsync(d_seg, &h_seg, sizeof(h_seg), cudaMemcpyHostToDevice, ctx->stream));
+        IPPLB_NCCL(ncclAllReduce(d_seg, d_seg, 1, ncclInt64, ncclMax, (ncclComm_t)ctx->nccl, ctx->stream));
+        IPPLB_CUDA(cudaMemcpyAsync(&h_seg, d_seg, sizeof(h_seg), cudaMemcpyDeviceToHost, ctx->stream));
+        IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        seg_cap = (long)h_seg;
+    }
     if ((rc = mig_alloc(ctx, seg_cap))) return rc;
     MigBox* M = (MigBox*)ctx->mig;
     // exchange the two inbox handles of every rank (one all-gather of 128 bytes per rank), then map the peers' inboxes
