@@ -33,13 +33,13 @@ def _run(tmp_path, exe, grid, np_, nt, csv):
     (d / "data").mkdir(parents=True)
     cmd = [_exe(exe), str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
            "--info", "0"]
-    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=150)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return np.loadtxt(d / "data" / csv, skiprows=1)
 
 
 def test_reference_lambdas_against_cabi_kernels():
-    out = subprocess.run([_exe("ref_lambdas")], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([_exe("ref_lambdas")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 
@@ -62,7 +62,10 @@ def test_reference_bumpontail_driver(tmp_path):
 
 def test_reference_penningtrap_driver(tmp_path):
     got = _run(tmp_path, "ref_PenningTrap", 32, 2000000, 12, "ParticleField_1_manager.csv")
-    assert got.shape == (13, 8) and np.isfinite(got).all() and (got[:, 1:] > 0).all()
+    # column 4 is rhoNorm_m, which the reference driver prints without ever assigning it (AlpineManager.h:71,
+    # PenningTrapManager.h:412): whatever the member holds; not checked
+    cols = [1, 2, 3, 5, 6, 7]
+    assert got.shape == (13, 8) and np.isfinite(got[:, cols]).all() and (got[:, cols] > 0).all()
     assert abs(got[0, 2] / (1.5 * 2000000) - 1.0) <= 5e-3
     h3 = (20.0 / 32) ** 3
     assert np.allclose(got[:, 1], 0.5 * h3 * (got[:, 5] ** 2 + got[:, 6] ** 2 + got[:, 7] ** 2), rtol=1e-8)
