@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--config", default="landau", choices=["landau", "bumpontail", "penning"])
     ap.add_argument("--log2-particles", type=int, default=None, help="particles per GPU = 2^k (default: the config's own)")
     ap.add_argument("--mode", type=int, default=2, help="2: fused single-pass step (default); 1: push + counting sort + sorted scatter")
+    ap.add_argument("--fft", default="replicated", choices=["replicated", "slab"],
+                    help="multi-GPU field solve (not part of the timed step; reported as solve_ms): replicated cuFFT solve or the slab-decomposed one")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -214,7 +216,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
 
-    run = app.MiniApp(ctx, app.workload(args.config, world, args.log2_particles), rank, world, mode=args.mode,
+    run = app.MiniApp(ctx, app.workload(args.config, world, args.log2_particles), rank, world, mode=args.mode, fft=args.fft,
                       dist=dist if world > 1 else None)
     w = run.w
     n_local, n_total = w["n_local"], w["n_local"] * world

@@ -31,6 +31,7 @@ extern "C" {
 
 typedef struct ipplb_ctx ipplb_ctx;
 typedef struct ipplb_layout ipplb_layout;   /* host-only: rank boxes + neighbour tables */
+typedef struct ipplb_loop ipplb_loop;       /* in-process rank group (tests): see the multi-rank section */
 typedef struct ipplb_poisson ipplb_poisson; /* cuFFT periodic Poisson solver (non-owned stage) */
 typedef struct ipplb_bins ipplb_bins;       /* cell-ordered particle store behind the fused step (see below) */
 
@@ -174,6 +175,27 @@ int ipplb_poisson_create_dist(ipplb_ctx* ctx, const ipplb_layout* layout, const 
                               ipplb_poisson** out);
 int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* efield);
 int ipplb_poisson_destroy(ipplb_poisson* s);
+/* Multi-rank variant 2: the SLAB-DECOMPOSED solve -- what heFFTe does for the reference (src/FFT/FFT.hpp:118-193: fft3d_r2c
+ * between the FieldLayout boxes; src/FFT/Transform/RC.h): boxes -> z-slabs (2-D real-to-complex transforms of whole planes)
+ * -> y-slabs (1-D transforms along z, k-space multipliers, 1-D inverses) -> z-slabs (2-D inverses, three gradient
+ * components) -> boxes.  Four message exchanges per solve (NCCL send / recv groups; device copies inside an in-process rank
+ * group), every rank transforms 1/N of the domain and holds ~(1 + 3 + 3 + 4) / N of it as work space.  ipplb_poisson_solve
+ * and _destroy work on the handle as usual; ipplb_loop_poisson_solve drives the solvers of all ranks of an in-process
+ * group.  `layout` may be any box layout (ORB).  E's halo is NOT filled. */
+int ipplb_poisson_create_slab(ipplb_ctx* ctx, const ipplb_layout* layout, const double origin[3], const double h[3],
+                              ipplb_poisson** out);
+int ipplb_loop_poisson_solve(ipplb_loop* loop, ipplb_poisson* const* solvers, double* const* rho, double* const* efield);
+/* The host-side plan behind it (no GPU needed): the sub-box copies and messages of the four phases, for checks.
+ * info[16] = nranks, rank, ng[3], nx/2+1, z-slab [zs, ze), y-slab [ys, ye), doubles in REAL, SPEC2D, SPECZ, SEND, RECV, nghost.
+ * rows: 16 longs per row.  which = 0 / 2 (copies before / after the exchange): src_buf, dst_buf, src_off, dst_off, src
+ * strides[3], dst strides[3], extents[3], elem (1 real, 2 complex; offsets and strides in elements); buffers 0 rho, 1 E,
+ * 2 REAL, 3 SPEC2D, 4 SPECZ, 5 SEND, 6 RECV.  which = 1 (messages): peer, send offset, send count, recv offset, recv count
+ * (doubles). */
+typedef struct ipplb_slabplan ipplb_slabplan;
+int ipplb_slabplan_create(const ipplb_layout* layout, int rank, ipplb_slabplan** out);
+int ipplb_slabplan_info(const ipplb_slabplan* p, long info[16]);
+int ipplb_slabplan_rows(const ipplb_slabplan* p, int phase, int which, long* rows, int max_rows, int* nrows);
+int ipplb_slabplan_destroy(ipplb_slabplan* p);
 
 /* ---- layout (host only; FieldLayout / Partitioner / RegionLayout) ---------------------------- */
 /* FieldLayout(comm, domain, decomp, isAllPeriodic, nghost) for `nranks` ranks,
@@ -237,7 +259,6 @@ int ipplb_allreduce_max_f64(ipplb_ctx* ctx, double* value_host);
  * send / receive / compaction of update (:150-314, ParticleBase.hpp:175-393) and HaloCells::exchangeBoundaries
  * (HaloCells.hpp:109-242) are held to the oracle on a single GPU.  ctxs[r] becomes rank r of nranks; bind each with
  * ipplb_ctx_set_layout afterwards.  Arrays below are indexed by rank. */
-typedef struct ipplb_loop ipplb_loop;
 int ipplb_loop_create(ipplb_loop** out, ipplb_ctx* const* ctxs, int nranks);
 int ipplb_loop_destroy(ipplb_loop* loop);
 int ipplb_loop_halo_exchange(ipplb_loop* loop, double* const* fields, int ncomp, int mode);

@@ -7,9 +7,9 @@ facade that keeps IPPL's ParticleAttrib / Field / FieldLayout / ParticleSpatialL
 include/ippl/.  There is NO CPU fallback: without the library or without a CUDA device every
 compute call raises.
 """
-from .lib import (Bins, Context, Dist, IpplbError, Layout, Loop, Mesh, Orb, Particles, Poisson, Push, lib,  # noqa: F401
+from .lib import (Bins, Context, Dist, IpplbError, Layout, Loop, Mesh, Orb, Particles, Poisson, Push, SlabPlan, lib,  # noqa: F401
                   lib_path, exported_symbols, leapfrog_push, lib_particles_array, nccl_unique_id, penning_push,
                   sample_counts)
 
-__all__ = ["Bins", "Context", "Dist", "IpplbError", "Layout", "Loop", "Mesh", "Orb", "Particles", "Poisson", "Push", "lib",
+__all__ = ["Bins", "Context", "Dist", "IpplbError", "Layout", "Loop", "Mesh", "Orb", "Particles", "Poisson", "Push", "SlabPlan", "lib",
            "lib_path", "exported_symbols", "leapfrog_push", "nccl_unique_id", "penning_push", "sample_counts"]

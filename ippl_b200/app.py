@@ -48,12 +48,13 @@ def workload(config, n_gpus, log2n=None):
 
 
 class MiniApp:
-    def __init__(self, ctx, w, rank, world, mode=2, dist=None, seed=42):
+    def __init__(self, ctx, w, rank, world, mode=2, dist=None, seed=42, fft="replicated"):
         import torch
         self.torch, self.ctx, self.w, self.rank, self.world, self.mode, self.dist = torch, ctx, w, rank, world, mode, dist
         self.dev, self.seed = ctx.device, seed
         self.origin = (0.0, 0.0, 0.0)
         self.solve_ms, self.orb, self.bins = None, None, None
+        self.fft = fft   # multi-rank field solve: "replicated" (every GPU transforms the whole domain) or "slab" (slab-decomposed)
 
     # ---- set-up --------------------------------------------------------------------------------------------------
     def initialise(self):
@@ -140,7 +141,7 @@ class MiniApp:
         ctx.scatter(mesh, p.arr["x"], p.arr["y"], p.arr["z"], self.q, self.rho, end=n)   # only the sampled slots
         if self.world > 1:
             ctx.halo_exchange(self.rho, 1, "accumulate")
-            sol = ib.Poisson(ctx, None, layout=self.layout, origin=self.origin, h=h)
+            sol = ib.Poisson(ctx, None, layout=self.layout, origin=self.origin, h=h, slab=(self.fft == "slab"))
         else:
             ctx.halo_accumulate_periodic(mesh, self.rho)
             sol = ib.Poisson(ctx, mesh)
@@ -233,6 +234,8 @@ class MiniApp:
 
     def extra_config(self):
         c = {}
+        if self.world > 1:
+            c["field_solve"] = self.fft
         if self.orb is not None:
             c["orb"] = {k: self.orb[k] for k in ("applied", "imbalance_before", "imbalance_after")}
         if self.world > 1 and self.bins is not None:

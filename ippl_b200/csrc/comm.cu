@@ -23,6 +23,7 @@
 #include "bins.h"
 #include "cic.cuh"
 #include "layout.h"
+#include "transport.h"
 
 namespace ipplb {
 
@@ -283,20 +284,11 @@ static void build_regions(const std::vector<NeighborEntry>& nb, int nranks, Comm
 }  // namespace ipplb
 
 
-struct ipplb_loop {
-    std::vector<ipplb_ctx*> ctx;
-};
 
 namespace ipplb {
 
 // ---- transport ----------------------------------------------------------------------------------------------------
-struct Xfer {
-    int peer;
-    const void* sptr; size_t sbytes;
-    void* rptr; size_t rbytes;
-};
-
-static int nccl_exchange(ipplb_ctx* ctx, const std::vector<Xfer>& x) {
+int nccl_exchange(ipplb_ctx* ctx, const std::vector<Xfer>& x) {
     IPPLB_NCCL(ncclGroupStart());
     for (auto& t : x) {
         if (t.sbytes) IPPLB_NCCL(ncclSend(t.sptr, t.sbytes, ncclChar, t.peer, (ncclComm_t)ctx->nccl, ctx->stream));
@@ -308,7 +300,7 @@ static int nccl_exchange(ipplb_ctx* ctx, const std::vector<Xfer>& x) {
 }
 
 // all ranks in one process: rank a's send to b is matched with b's receive from a
-static int loop_exchange(ipplb_loop* L, const std::vector<std::vector<Xfer>>& all) {
+int loop_exchange(ipplb_loop* L, const std::vector<std::vector<Xfer>>& all) {
     const int nr = (int)L->ctx.size();
     for (int a = 0; a < nr; ++a) IPPLB_CUDA(cudaStreamSynchronize(L->ctx[a]->stream));
     for (int a = 0; a < nr; ++a)

@@ -9,36 +9,9 @@
 
 #include "common.cuh"
 #include "layout.h"
-
-struct ipplb_poisson {
-    ipplb_ctx* ctx = nullptr;
-    ipplb::MeshDev m;
-    int nx = 0, ny = 0, nz = 0, nxh = 0;
-    cufftHandle fwd = 0, inv = 0;
-    double* real     = nullptr;          // 3 * N (component planes after the inverse)
-    cufftDoubleComplex* spec = nullptr;  // 4 * Nh: [0] rho_hat, [1..3] gradient spectra
-    double* kx = nullptr;                // kx[nxh] ky[ny] kz[nz]
-    double *ky = nullptr, *kz = nullptr;
-    // multi-rank (replicated solve): every rank gathers all rho boxes, solves the whole domain, keeps its box of E
-    bool dist       = false;
-    ipplb::MeshDev g;               // the whole domain as one box (m is this rank's box)
-    int nranks      = 1;
-    double* stage   = nullptr;      // all boxes back to back, box r at off[r]
-    int* d_boxes    = nullptr;      // [nranks][6] lo, hi (inclusive)
-    long* d_off     = nullptr;      // [nranks + 1]
-    std::vector<long> off;
-};
+#include "poisson.h"
 
 namespace ipplb {
-
-#define IPPLB_CUFFT(call)                                                          \
-    do {                                                                           \
-        cufftResult r__ = (call);                                                  \
-        if (r__ != CUFFT_SUCCESS) {                                                \
-            set_error("%s:%d: %s -> cufft error %d", __FILE__, __LINE__, #call, (int)r__); \
-            return IPPLB_ERR_CUFFT;                                                \
-        }                                                                          \
-    } while (0)
 
 __global__ void pack_interior_kernel(MeshDev m, const double* __restrict__ f, double* __restrict__ o) {
     const long ni = (long)m.nl[0] * m.nl[1] * m.nl[2];
@@ -136,6 +109,27 @@ __global__ void unpack_box_kernel(MeshDev m, int gx, int gy, long N, const doubl
     }
 }
 
+// kVec[d] = notMid * 2 * pi / Len * (iVec[d] - shift * N[d]), Len = rmax - origin,
+// rmax = origin + N*h  (FFTPeriodicPoissonSolver.hpp:66-70, 127-137)
+std::vector<double> poisson_k_tables(const int ng[3], const double origin[3], const double h[3]) {
+    const int cnt[3] = {ng[0] / 2 + 1, ng[1], ng[2]};
+    std::vector<double> kh((size_t)cnt[0] + cnt[1] + cnt[2]);
+    const double pi = M_PI;
+    int off = 0;
+    for (int d = 0; d < 3; ++d) {
+        const int Nd      = ng[d];
+        const double rmax = origin[d] + (Nd * h[d]);
+        const double Len  = rmax - origin[d];
+        for (int i = 0; i < cnt[d]; ++i) {
+            bool shift  = (i > (Nd / 2));
+            bool notMid = (i != (Nd / 2));
+            kh[off + i] = notMid * 2 * pi / Len * (i - shift * Nd);
+        }
+        off += cnt[d];
+    }
+    return kh;
+}
+
 }  // namespace ipplb
 
 using namespace ipplb;
@@ -158,29 +152,14 @@ int ipplb_poisson_create(ipplb_ctx* ctx, const ipplb_mesh* mesh, ipplb_poisson**
     IPPLB_CUDA(cudaMalloc(&s->kx, sizeof(double) * (s->nxh + s->ny + s->nz)));
     s->ky = s->kx + s->nxh;
     s->kz = s->ky + s->ny;
-    // kVec[d] = notMid * 2 * pi / Len * (iVec[d] - shift * N[d]), Len = rmax - origin,
-    // rmax = origin + N*h  (FFTPeriodicPoissonSolver.hpp:66-70, 127-137)
-    std::vector<double> kh(s->nxh + s->ny + s->nz);
-    const double pi = M_PI;
-    int off = 0;
-    const int cnt[3] = {s->nxh, s->ny, s->nz};
-    for (int d = 0; d < 3; ++d) {
-        const int Nd      = mesh->ng[d];
-        const double rmax = mesh->origin[d] + (Nd * mesh->h[d]);
-        const double Len  = rmax - mesh->origin[d];
-        for (int i = 0; i < cnt[d]; ++i) {
-            bool shift  = (i > (Nd / 2));
-            bool notMid = (i != (Nd / 2));
-            kh[off + i] = notMid * 2 * pi / Len * (i - shift * Nd);
-        }
-        off += cnt[d];
-    }
+    const std::vector<double> kh = poisson_k_tables(mesh->ng, mesh->origin, mesh->h);
     IPPLB_CUDA(cudaMemcpy(s->kx, kh.data(), sizeof(double) * kh.size(), cudaMemcpyHostToDevice));
     int dims[3] = {s->nz, s->ny, s->nx};
     IPPLB_CUFFT(cufftPlan3d(&s->fwd, s->nz, s->ny, s->nx, CUFFT_D2Z));
     IPPLB_CUFFT(cufftSetStream(s->fwd, ctx->stream));
     IPPLB_CUFFT(cufftPlanMany(&s->inv, 3, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, 3));
     IPPLB_CUFFT(cufftSetStream(s->inv, ctx->stream));
+    s->plans = true;
     *out = s;
     return IPPLB_OK;
 }
@@ -233,6 +212,7 @@ int ipplb_poisson_create_dist(ipplb_ctx* ctx, const ipplb_layout* layout, const 
 
 int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* efield) {
     IPPLB_REQUIRE(s && rho && efield, "poisson_solve: bad arguments");
+    if (s->slab) return slab_solve(s, rho, efield);
     ipplb_ctx* ctx = s->ctx;
     const long N = (long)s->nx * s->ny * s->nz, Nh = (long)s->nxh * s->ny * s->nz;
     const int g  = (int)((N + 255) / 256 < 148 * 16 ? (N + 255) / 256 : 148 * 16);
@@ -278,8 +258,11 @@ int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* efield) {
 
 int ipplb_poisson_destroy(ipplb_poisson* s) {
     if (!s) return IPPLB_OK;
-    cufftDestroy(s->fwd);
-    cufftDestroy(s->inv);
+    if (s->slab) slab_free(s->slab);
+    if (s->plans) {
+        cufftDestroy(s->fwd);
+        cufftDestroy(s->inv);
+    }
     cudaFree(s->real);
     cudaFree(s->spec);
     cudaFree(s->kx);

@@ -560,12 +560,13 @@ class Poisson:
     """cuFFT periodic Poisson solve (non-owned stage).  Single rank: Poisson(ctx, mesh) with the whole domain;
     multi rank: Poisson(ctx, None, layout=layout, origin=..., h=...) = replicated solve over NCCL."""
 
-    def __init__(self, ctx, mesh, layout=None, origin=None, h=None):
+    def __init__(self, ctx, mesh, layout=None, origin=None, h=None, slab=False):
         self.ctx = ctx
         self._h = C.c_void_p()
         if layout is not None:
-            _check(lib().ipplb_poisson_create_dist(ctx._h, layout._h, (C.c_double * 3)(*origin), (C.c_double * 3)(*h),
-                                                   C.byref(self._h)))
+            # slab=True: the slab-decomposed solve (ipplb_poisson_create_slab) instead of the replicated one
+            create = lib().ipplb_poisson_create_slab if slab else lib().ipplb_poisson_create_dist
+            _check(create(ctx._h, layout._h, (C.c_double * 3)(*origin), (C.c_double * 3)(*h), C.byref(self._h)))
         else:
             _check(lib().ipplb_poisson_create(ctx._h, C.byref(mesh), C.byref(self._h)))
 
@@ -624,6 +625,41 @@ class Layout:
         return m
 
 
+class SlabPlan:
+    """Host-only plan of the slab-decomposed FFT solve (ipplb_slabplan_*; works without a GPU): the sub-box copies and
+    messages of the four phases for one rank of a layout."""
+    BUFS = ("rho", "ef", "real", "spec2d", "specz", "send", "recv")
+
+    def __init__(self, layout, rank):
+        self._h = C.c_void_p()
+        _check(lib().ipplb_slabplan_create(layout._h, rank, C.byref(self._h)))
+        info = (C.c_long * 16)()
+        _check(lib().ipplb_slabplan_info(self._h, info))
+        v = list(info)
+        self.nranks, self.rank, self.ng, self.nxh = v[0], v[1], tuple(v[2:5]), v[5]
+        self.zs, self.ze, self.ys, self.ye = v[6:10]
+        self.size = dict(zip(self.BUFS[2:], v[10:15]))
+        self.nghost = v[15]
+
+    def rows(self, phase, which):
+        """which: 0 copies before the exchange, 1 messages, 2 copies after it.  Copies come back as dicts."""
+        import numpy as np
+        n = C.c_int(0)
+        _check(lib().ipplb_slabplan_rows(self._h, phase, which, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 16), dtype=np.int64)
+        _check(lib().ipplb_slabplan_rows(self._h, phase, which, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        out = out[:n.value]
+        if which == 1:
+            return [dict(peer=int(r[0]), soff=int(r[1]), scount=int(r[2]), roff=int(r[3]), rcount=int(r[4])) for r in out]
+        return [dict(src=self.BUFS[r[0]], dst=self.BUFS[r[1]], src_off=int(r[2]), dst_off=int(r[3]), ss=tuple(int(x) for x in r[4:7]),
+                     ds=tuple(int(x) for x in r[7:10]), n=tuple(int(x) for x in r[10:13]), elem=int(r[13])) for r in out]
+
+    def close(self):
+        if self._h:
+            lib().ipplb_slabplan_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 class Loop:
     """ipplb_loop: all ranks of a small job in ONE process on ONE device (no NCCL); the same kernels and tables as the
     NCCL path with device-to-device copies as the transport.  ctxs[r] becomes rank r."""
@@ -658,6 +694,13 @@ class Loop:
 
     def migrate_connect(self, seg_cap):
         _check(lib().ipplb_loop_migrate_connect(self._h, C.c_long(int(seg_cap))))
+
+    def poisson_solve(self, solvers, rho, efield):
+        """slab-decomposed solve of every in-process rank (solvers[r] = Poisson(ctxs[r], None, layout=..., slab=True))"""
+        sarr = (C.c_void_p * self.n)(*[q._h.value for q in solvers])
+        rarr = (C.c_void_p * self.n)(*[r.data_ptr() for r in rho])
+        earr = (C.c_void_p * self.n)(*[e.data_ptr() for e in efield])
+        _check(lib().ipplb_loop_poisson_solve(self._h, sarr, rarr, earr))
 
     def bins_migrate(self, bins, cur, rho=None):
         structs = lib_particles_array([p.struct() for p in cur])
