@@ -6,7 +6,7 @@
 //
 // --fused runs the step through the single-pass fused kernel (ipplb_bins_step: gather + kick + kick + drift + BC
 // + re-bucketing + scatter in one pass) instead of the reference-shaped sequence of attribute expressions;
-// both paths produce the same energies (tests/test_facade.py).
+// both paths produce the same energies (tests/test_y_facade.py).
 // Particle initialisation runs on the device like the reference's (LandauDampingManager.h:159-254): inverse-transform
 // sampling of 1 + alpha cos(k x) with Newton iterations, Gaussian velocities, seed 42 + 100 * rank.  The uniform
 // stream is counter based (Philox) because Kokkos::Random_XorShift64_Pool's is backend dependent, so the numbers are

@@ -6,7 +6,7 @@
 //
 // --fused runs Kick2 (closing the previous step) + Kick1 + drift + BC + re-bucketing + scatter as ONE pass
 // (ipplb_bins_step with IPPLB_PUSH_PENNING); the unfused path calls ipplb_penning_kick where the reference has its
-// two Kokkos lambdas.  Both produce the same energies (tests/test_facade.py).
+// two Kokkos lambdas.  Both produce the same energies (tests/test_y_facade.py).
 constexpr unsigned Dim = 3;
 using T                = double;
 const char* TestName   = "PenningTrap";

@@ -9,7 +9,7 @@ not turn the suite red, and either way the first real execution is recorded.  Th
 Checks: demos/ref_lambdas (eight driver lambdas cut out of the reference at build time, compared against the C-ABI
 kernels inside the binary); ref_LandauDamping against the reference's known-answer CSV at its own tolerance
 (demos/alpine/validation/CMakeLists.txt:23-26); ref_BumponTailInstability / ref_PenningTrap against the same physical
-anchors tests/test_facade.py uses for the restated drivers."""
+anchors tests/test_y_facade.py uses for the restated drivers."""
 import os
 import subprocess
 
