@@ -89,7 +89,9 @@ public:
     Inform& operator<<(Inform& (*f)(Inform&)) { return f(*this); }
     std::streamsize precision(std::streamsize p) { return buf_.precision(p); }
     std::ios::fmtflags setf(std::ios::fmtflags f, std::ios::fmtflags mask) { return buf_.setf(f, mask); }
-    void flush() {
+    // endl: the message goes out (Inform.cpp:42-45, outputMessage); flush(): only the destination stream is flushed
+    // (Inform.h:113) -- `csvout << endl; csvout.flush();` in the drivers' dumps writes ONE line
+    Inform& outputMessage() {
         const bool mine = node_ == INFORM_ALL_NODES || rank_ref() == node_;
         if (to_file_) {
             if (file_) *file_ << buf_.str() << std::endl;
@@ -97,6 +99,14 @@ public:
             std::cout << (name_.empty() ? "" : name_ + "> ") << buf_.str() << std::endl;
         }
         buf_.str("");
+        return *this;
+    }
+    void flush() {
+        if (to_file_) {
+            if (file_) file_->flush();
+        } else {
+            std::cout.flush();
+        }
     }
     static bool& level_on() {
         static bool on = true;
@@ -114,10 +124,7 @@ private:
     std::unique_ptr<std::ofstream> file_;
     std::ostringstream buf_;
 };
-inline Inform& endl(Inform& m) {
-    m.flush();
-    return m;
-}
+inline Inform& endl(Inform& m) { return m.outputMessage(); }
 
 namespace ippl {
 

@@ -16,8 +16,16 @@
 // demos/ref_lambdas.cu compiles the reference drivers' own lambda bodies -- cut out of the reference tree at build time
 // -- on it, unchanged, and checks them against the C-ABI kernels.
 #pragma once
-#ifndef __CUDACC__
+// IPPL_SHIM_HOST_EMULATION (tests only, never the product): the driver is compiled by the host compiler and linked against
+// the CPU mock of the C-ABI under oracle/mock, where "device" memory is host memory; kernels become host loops.  It exists
+// to run the reference's unchanged drivers through this header and include/ippl/compat on a machine without a GPU.
+#if !defined(__CUDACC__) && !defined(IPPL_SHIM_HOST_EMULATION)
 #error "include/ippl/KokkosShim.cuh needs nvcc (device lambdas): compile the driver with -x cu --extended-lambda"
+#endif
+#if defined(IPPL_SHIM_HOST_EMULATION) && !defined(__CUDACC__)
+#define __host__
+#define __device__
+#define __forceinline__ inline
 #endif
 
 #include <cfloat>
@@ -105,6 +113,7 @@ namespace shim {
         return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
     }
 
+#ifndef IPPL_SHIM_HOST_EMULATION
     template <class F>
     __global__ void __launch_bounds__(256) for_kernel(long b, long e, F f) {
         for (long i = b + (long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long)gridDim.x * blockDim.x) f((std::size_t)i);
@@ -173,6 +182,7 @@ namespace shim {
         }
         ~Slots() { cudaFree(d); }
     };
+#endif  // !IPPL_SHIM_HOST_EMULATION
 }  // namespace shim
 
 // ---- parallel_for --------------------------------------------------------------------------------------------------------
@@ -180,8 +190,12 @@ template <class... P, class F>
 void parallel_for(const std::string&, const RangePolicy<P...>& policy, const F& f) {
     const long n = policy.end() - policy.begin();
     if (n <= 0) return;
+#ifdef IPPL_SHIM_HOST_EMULATION
+    for (long i = policy.begin(); i < policy.end(); ++i) f((std::size_t)i);
+#else
     shim::for_kernel<<<shim::grid_for(n, 256), 256, 0, shim::stream()>>>(policy.begin(), policy.end(), f);
     ippl::b200::cuda_check(cudaGetLastError(), "Kokkos::parallel_for");
+#endif
 }
 template <class... P, class F>
 void parallel_for(const RangePolicy<P...>& policy, const F& f) { parallel_for(std::string(), policy, f); }
@@ -194,6 +208,9 @@ void parallel_for(std::size_t n, const F& f) { parallel_for(std::string(), Range
 template <class... P, class F, class R0>
 void parallel_reduce(const std::string&, const RangePolicy<P...>& policy, const F& f, const R0& r0) {
     double v[1] = {R0::identity()};
+#ifdef IPPL_SHIM_HOST_EMULATION
+    for (long i = policy.begin(); i < policy.end(); ++i) f((std::size_t)i, v[0]);
+#else
     shim::Slots slots(v, 1);
     const long n = policy.end() - policy.begin();
     if (n > 0) {
@@ -201,11 +218,15 @@ void parallel_reduce(const std::string&, const RangePolicy<P...>& policy, const 
         ippl::b200::cuda_check(cudaGetLastError(), "Kokkos::parallel_reduce");
     }
     slots.fetch(v, 1);
+#endif
     r0.ref = v[0];
 }
 template <class... P, class F, class R0, class R1>
 void parallel_reduce(const std::string&, const RangePolicy<P...>& policy, const F& f, const R0& r0, const R1& r1) {
     double v[2] = {R0::identity(), R1::identity()};
+#ifdef IPPL_SHIM_HOST_EMULATION
+    for (long i = policy.begin(); i < policy.end(); ++i) f((std::size_t)i, v[0], v[1]);
+#else
     shim::Slots slots(v, 2);
     const long n = policy.end() - policy.begin();
     if (n > 0) {
@@ -213,6 +234,7 @@ void parallel_reduce(const std::string&, const RangePolicy<P...>& policy, const 
         ippl::b200::cuda_check(cudaGetLastError(), "Kokkos::parallel_reduce");
     }
     slots.fetch(v, 2);
+#endif
     r0.ref = v[0];
     r1.ref = v[1];
 }

@@ -1,0 +1,278 @@
+// ipplb_mock.cpp -- TEST INFRASTRUCTURE, NOT THE PRODUCT.  A CPU stand-in for the part of the C-ABI (include/ippl_b200.h)
+// that the C++ facade calls on ONE rank, implemented on the oracle (oracle/ippl_oracle.cpp) plus a small DFT, together
+// with stand-ins for the handful of CUDA runtime calls the facade makes ("device" memory = host memory).
+//
+// Purpose: run the reference's UNCHANGED alpine drivers through include/ippl/compat + include/ippl/KokkosShim.cuh
+// (host-emulation mode) on a machine without a GPU, so that the host logic of that layer -- managers' call sequences,
+// samplers, reductions, CSV dumps -- is checked against the reference's known-answer file before it ever meets a GPU.
+// Nothing under ippl_b200/, demos/*.cpp or bench.py links this; the product library has no CPU path.
+// Built by oracle/Makefile (target `mock`) into oracle/_build/mock/; used only by tests/test_ref_drivers_host_cpu.py.
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "../../include/ippl_b200.h"
+
+// ---- the oracle's C functions (oracle/ippl_oracle.cpp, compiled into the same library) -------------------------------
+extern "C" {
+struct orc_mesh {
+    int ng[3];
+    int first[3];
+    int nl[3];
+    int nghost;
+    double origin[3];
+    double h[3];
+};
+void orc_scatter_cic(const orc_mesh* m, long begin, long end, const double* x, const double* y, const double* z, const double* q,
+                     double q_scalar, const int* hash, double* rho, int parallel);
+void orc_gather_cic(const orc_mesh* m, long n, const double* x, const double* y, const double* z, const double* efield, int ncomp,
+                    double** out, int add_to_attribute, int parallel);
+void orc_periodic_bc(long n, double* x, double lo, double hi, int parallel);
+void orc_halo_periodic(double* v, const int ext[3], int ncomp, int nghost, const int serial[3], int mode);
+double orc_field_sum(const double* v, const int ext[3], int nghost);
+void orc_density(double* v, const int ext[3], int nghost, double cell_volume, double q_over_size);
+}
+
+struct ipplb_ctx {
+    int dummy = 0;
+};
+struct ipplb_poisson {
+    ipplb_mesh m;
+    std::vector<double> k[3];
+};
+
+namespace {
+std::string g_err;
+}
+namespace ipplb {   // what layout.cpp reports errors through (defined in field.cu in the product)
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+}  // namespace ipplb
+namespace {
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+orc_mesh to_orc(const ipplb_mesh* m) {
+    orc_mesh o;
+    for (int d = 0; d < 3; ++d) {
+        o.ng[d] = m->ng[d]; o.first[d] = m->first[d]; o.nl[d] = m->nl[d]; o.origin[d] = m->origin[d]; o.h[d] = m->h[d];
+    }
+    o.nghost = m->nghost;
+    return o;
+}
+void ext_of(const ipplb_mesh* m, int e[3]) {
+    for (int d = 0; d < 3; ++d) e[d] = m->nl[d] + 2 * m->nghost;
+}
+using cplx = std::complex<double>;
+// plain O(n^2) DFT along one axis of a [n2][n1][n0] array (small grids only)
+void dft_axis(std::vector<cplx>& a, const int n[3], int axis, int sign) {
+    const long s[3] = {1, n[0], (long)n[0] * n[1]};
+    const int len = n[axis];
+    std::vector<cplx> w(len), line(len), out(len);
+    for (int t = 0; t < len; ++t) w[t] = std::polar(1.0, sign * 2.0 * M_PI * t / len);
+    const int o1 = (axis + 1) % 3, o2 = (axis + 2) % 3;
+    for (int p = 0; p < n[o2]; ++p)
+        for (int q = 0; q < n[o1]; ++q) {
+            const long base = p * s[o2] + q * s[o1];
+            for (int t = 0; t < len; ++t) line[t] = a[base + t * s[axis]];
+            for (int f = 0; f < len; ++f) {
+                cplx acc = 0;
+                for (int t = 0; t < len; ++t) acc += line[t] * w[(int)(((long)f * t) % len)];
+                out[f] = acc;
+            }
+            for (int t = 0; t < len; ++t) a[base + t * s[axis]] = out[t];
+        }
+}
+}  // namespace
+
+extern "C" {
+
+// ---- CUDA runtime stand-ins: device memory is host memory --------------------------------------------------------------
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+    *p = std::calloc(bytes ? bytes : 1, 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFree(void* p) {
+    std::free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+    std::memmove(d, s, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    std::memmove(d, s, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+    std::memset(d, v, n);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "mock CUDA runtime (oracle/mock)"; }
+
+// ---- context -----------------------------------------------------------------------------------------------------------
+const char* ipplb_last_error(void) { return g_err.c_str(); }
+int ipplb_ctx_create(ipplb_ctx** out, int, void*, int) {
+    *out = new ipplb_ctx();
+    return IPPLB_OK;
+}
+int ipplb_ctx_destroy(ipplb_ctx* c) {
+    delete c;
+    return IPPLB_OK;
+}
+int ipplb_sync(ipplb_ctx*) { return IPPLB_OK; }
+void* ipplb_ctx_stream(ipplb_ctx*) { return nullptr; }
+
+// ---- particle <-> mesh ----------------------------------------------------------------------------------------------------
+int ipplb_scatter_cic(ipplb_ctx*, const ipplb_mesh* mesh, long begin, long end, const double* x, const double* y, const double* z,
+                      const double* q, double q_scalar, const int* hash, double* rho) {
+    const orc_mesh m = to_orc(mesh);
+    orc_scatter_cic(&m, begin, end, x, y, z, q, q_scalar, hash, rho, 1);
+    return IPPLB_OK;
+}
+int ipplb_gather_cic(ipplb_ctx*, const ipplb_mesh* mesh, long n, const double* x, const double* y, const double* z,
+                     const double* field, int ncomp, double* const* out, int add) {
+    const orc_mesh m = to_orc(mesh);
+    double* o[3] = {out[0], ncomp > 1 ? out[1] : nullptr, ncomp > 2 ? out[2] : nullptr};
+    orc_gather_cic(&m, n, x, y, z, field, ncomp, o, add, 1);
+    return IPPLB_OK;
+}
+// y = y + a * x  (ParticleAttrib::operator=(Expression) for the alpine kick / drift)
+int ipplb_axpy(ipplb_ctx*, long n, double a, const double* x, double* y) {
+    for (long i = 0; i < n; ++i) y[i] = y[i] + a * x[i];
+    return IPPLB_OK;
+}
+int ipplb_apply_periodic_bc(ipplb_ctx*, long n, double* x, double* y, double* z, const double lo[3], const double hi[3], int mask) {
+    double* c[3] = {x, y, z};
+    for (int d = 0; d < 3; ++d)
+        if (mask & (1 << d)) orc_periodic_bc(n, c[d], lo[d], hi[d], 1);
+    return IPPLB_OK;
+}
+
+// ---- fields ----------------------------------------------------------------------------------------------------------------
+int ipplb_field_fill(ipplb_ctx*, double* f, long count, double v) {
+    for (long i = 0; i < count; ++i) f[i] = v;
+    return IPPLB_OK;
+}
+int ipplb_field_sum(ipplb_ctx*, const ipplb_mesh* mesh, const double* f, double* out) {
+    int e[3];
+    ext_of(mesh, e);
+    *out = orc_field_sum(f, e, mesh->nghost);
+    return IPPLB_OK;
+}
+int ipplb_field_density(ipplb_ctx*, const ipplb_mesh* mesh, double* f, double cell_volume, double shift) {
+    int e[3];
+    ext_of(mesh, e);
+    orc_density(f, e, mesh->nghost, cell_volume, shift);
+    return IPPLB_OK;
+}
+static int halo(const ipplb_mesh* mesh, double* f, int ncomp, int mask, int mode) {
+    int e[3];
+    ext_of(mesh, e);
+    const int serial[3] = {mask & 1, (mask >> 1) & 1, (mask >> 2) & 1};
+    orc_halo_periodic(f, e, ncomp, mesh->nghost, serial, mode);
+    return IPPLB_OK;
+}
+int ipplb_halo_accumulate_periodic(ipplb_ctx*, const ipplb_mesh* mesh, double* f, int ncomp, int mask) { return halo(mesh, f, ncomp, mask, 1); }
+int ipplb_halo_fill_periodic(ipplb_ctx*, const ipplb_mesh* mesh, double* f, int ncomp, int mask) { return halo(mesh, f, ncomp, mask, 0); }
+
+// ---- periodic Poisson solve, GRAD output (FFTPeriodicPoissonSolver.hpp:53-169), full complex DFTs ------------------------------
+int ipplb_poisson_create(ipplb_ctx*, const ipplb_mesh* mesh, ipplb_poisson** out) {
+    for (int d = 0; d < 3; ++d)
+        if (mesh->nl[d] != mesh->ng[d]) return fail(IPPLB_ERR_ARG, "mock poisson: single rank only");
+    ipplb_poisson* s = new ipplb_poisson();
+    s->m = *mesh;
+    for (int d = 0; d < 3; ++d) {
+        const int N      = mesh->ng[d];
+        const double Len = (mesh->origin[d] + N * mesh->h[d]) - mesh->origin[d];
+        s->k[d].resize(N);
+        for (int i = 0; i < N; ++i) {
+            const bool shift = i > N / 2, notMid = i != N / 2;
+            s->k[d][i] = notMid * 2 * M_PI / Len * (i - shift * N);
+        }
+    }
+    *out = s;
+    return IPPLB_OK;
+}
+int ipplb_poisson_create_dist(ipplb_ctx* ctx, const ipplb_layout* layout, const double origin[3], const double h[3], ipplb_poisson** out) {
+    if (ipplb_layout_nranks(layout) != 1) return fail(IPPLB_ERR_ARG, "mock poisson: single rank only");
+    ipplb_mesh m;
+    ipplb_layout_mesh(layout, 0, origin, h, &m);
+    return ipplb_poisson_create(ctx, &m, out);
+}
+int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* ef) {
+    const ipplb_mesh& m = s->m;
+    const int n[3] = {m.ng[0], m.ng[1], m.ng[2]}, g = m.nghost;
+    const long ex = n[0] + 2 * g, ey = n[1] + 2 * g, N = (long)n[0] * n[1] * n[2];
+    std::vector<cplx> rh(N);
+    for (int k = 0; k < n[2]; ++k)
+        for (int j = 0; j < n[1]; ++j)
+            for (int i = 0; i < n[0]; ++i) rh[i + (long)n[0] * (j + (long)n[1] * k)] = rho[(i + g) + ex * ((j + g) + ey * (k + g))];
+    for (int a = 0; a < 3; ++a) dft_axis(rh, n, a, -1);
+    for (int c = 0; c < 3; ++c) {
+        std::vector<cplx> t(N);
+        for (int k = 0; k < n[2]; ++k)
+            for (int j = 0; j < n[1]; ++j)
+                for (int i = 0; i < n[0]; ++i) {
+                    const long l    = i + (long)n[0] * (j + (long)n[1] * k);
+                    const double kk[3] = {s->k[0][i], s->k[1][j], s->k[2][k]};
+                    const double Dr = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2];
+                    const double factor = Dr != 0.0 ? 1.0 / Dr : 0.0;
+                    t[l] = (rh[l] / (double)N) * cplx(0.0, -(kk[c] * factor));
+                }
+        for (int a = 0; a < 3; ++a) dft_axis(t, n, a, +1);
+        for (int k = 0; k < n[2]; ++k)
+            for (int j = 0; j < n[1]; ++j)
+                for (int i = 0; i < n[0]; ++i) {
+                    const long cell = (i + g) + ex * ((j + g) + ey * (k + g));
+                    ef[3 * cell + c] = t[i + (long)n[0] * (j + (long)n[1] * k)].real();
+                    if (c == 2) rho[cell] = ef[3 * cell + c];   // the inverse lands in rho's storage (:153)
+                }
+    }
+    return IPPLB_OK;
+}
+int ipplb_poisson_destroy(ipplb_poisson* s) {
+    delete s;
+    return IPPLB_OK;
+}
+
+// ---- one rank: the communicator entry points ---------------------------------------------------------------------------------
+int ipplb_allreduce_sum_f64(ipplb_ctx*, double*) { return IPPLB_OK; }
+int ipplb_allreduce_sum_i64(ipplb_ctx*, long*) { return IPPLB_OK; }
+int ipplb_allreduce_max_f64(ipplb_ctx*, double*) { return IPPLB_OK; }
+int ipplb_update_plan(ipplb_ctx*, ipplb_particles* p, long* n_after, long*, long*) {
+    if (n_after) *n_after = p->n;
+    return IPPLB_OK;
+}
+int ipplb_update_commit(ipplb_ctx*, ipplb_particles*) { return IPPLB_OK; }
+int ipplb_ctx_set_layout(ipplb_ctx*, const ipplb_layout* l, const double*, const double*) {
+    return ipplb_layout_nranks(l) == 1 ? IPPLB_OK : fail(IPPLB_ERR_ARG, "mock: single rank only");
+}
+int ipplb_comm_init(ipplb_ctx*, int, int nranks, const char*) { return nranks == 1 ? IPPLB_OK : fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+int ipplb_nccl_unique_id(char*) { return fail(IPPLB_ERR_NCCL, "mock: single rank only"); }
+int ipplb_halo_exchange(ipplb_ctx*, double*, int, int) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+int ipplb_orb_repartition(ipplb_ctx*, const ipplb_mesh*, int, const double*, int*, int*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+
+}  // extern "C"
