@@ -258,6 +258,69 @@ int ipplb_poisson_destroy(ipplb_poisson* s) {
     return IPPLB_OK;
 }
 
+// ---- the drivers' dump reductions and the PenningTrap kicks (used by demos/ref_lambdas.cu as the other side of its checks) ----
+struct orc_penning {
+    double origin[3], length[3], V0, alpha, Bext, DrInv;
+};
+void orc_penning_kick1(const orc_penning* pp, long n, const double* x, const double* y, const double* z, double* px, double* py,
+                       double* pz, const double* ex, const double* ey, const double* ez);
+void orc_penning_kick2(const orc_penning* pp, long n, const double* x, const double* y, const double* z, double* px, double* py,
+                       double* pz, const double* ex, const double* ey, const double* ez);
+int ipplb_penning_kick(ipplb_ctx*, int which, const ipplb_push* push, long n, const double* x, const double* y, const double* z,
+                       double* px, double* py, double* pz, const double* ex, const double* ey, const double* ez) {
+    orc_penning pp;
+    for (int d = 0; d < 3; ++d) { pp.origin[d] = push->origin[d]; pp.length[d] = push->length[d]; }
+    pp.V0 = push->V0; pp.alpha = push->alpha; pp.Bext = push->Bext; pp.DrInv = push->DrInv;
+    (which == 1 ? orc_penning_kick1 : orc_penning_kick2)(&pp, n, x, y, z, px, py, pz, ex, ey, ez);
+    return IPPLB_OK;
+}
+int ipplb_field_energy_stats(ipplb_ctx*, const ipplb_mesh* mesh, const double* ef, double out[7]) {
+    int e[3];
+    ext_of(mesh, e);
+    const int g = mesh->nghost;
+    for (int i = 0; i < 7; ++i) out[i] = 0.0;
+    for (int k = g; k < e[2] - g; ++k)
+        for (int j = g; j < e[1] - g; ++j)
+            for (int i = g; i < e[0] - g; ++i) {
+                const double* v = ef + 3 * (i + (long)e[0] * (j + (long)e[1] * k));
+                double dot = 0.0;
+                for (int d = 0; d < 3; ++d) {
+                    out[d] += v[d] * v[d];
+                    out[3 + d] = std::fabs(v[d]) > out[3 + d] ? std::fabs(v[d]) : out[3 + d];
+                    dot += v[d] * v[d];
+                }
+                out[6] += dot;
+            }
+    return IPPLB_OK;
+}
+int ipplb_field_ex_stats(ipplb_ctx* c, const ipplb_mesh* mesh, const double* ef, double* out) {
+    double all[7];
+    ipplb_field_energy_stats(c, mesh, ef, all);
+    out[0] = all[0];
+    out[1] = all[3];
+    return IPPLB_OK;
+}
+int ipplb_field_norm_stats(ipplb_ctx*, const ipplb_mesh* mesh, const double* f, double out[2]) {
+    int e[3];
+    ext_of(mesh, e);
+    const int g = mesh->nghost;
+    out[0] = out[1] = 0.0;
+    for (int k = g; k < e[2] - g; ++k)
+        for (int j = g; j < e[1] - g; ++j)
+            for (int i = g; i < e[0] - g; ++i) {
+                const double v = f[i + (long)e[0] * (j + (long)e[1] * k)];
+                out[0] += v * v;
+                out[1] = std::fabs(v) > out[1] ? std::fabs(v) : out[1];
+            }
+    return IPPLB_OK;
+}
+int ipplb_particles_kinetic(ipplb_ctx*, long n, const double* px, const double* py, const double* pz, double* out) {
+    double s = 0.0;
+    for (long i = 0; i < n; ++i) s += px[i] * px[i] + py[i] * py[i] + pz[i] * pz[i];
+    *out = s;
+    return IPPLB_OK;
+}
+
 // ---- one rank: the communicator entry points ---------------------------------------------------------------------------------
 int ipplb_allreduce_sum_f64(ipplb_ctx*, double*) { return IPPLB_OK; }
 int ipplb_allreduce_sum_i64(ipplb_ctx*, long*) { return IPPLB_OK; }

@@ -69,3 +69,12 @@ def test_unchanged_penningtrap_driver(drivers, tmp_path):
     assert np.allclose(got[:, 3], got[:, 1] + got[:, 2], rtol=1e-9)
     # total energy is conserved to a few 1e-3 over the first steps of the trap
     assert abs(got[-1, 3] / got[0, 3] - 1.0) <= 2e-2
+
+
+def test_reference_lambdas_harness_on_the_mock(drivers):
+    """demos/ref_lambdas.cu in host-emulation mode: the eight lambda bodies cut out of the reference drivers against the mock's
+    (= the oracle's) implementation of the same C-ABI calls; Kick1 / Kick2 bit for bit.  Pins the harness the GPU run uses."""
+    out = subprocess.run([os.path.join(drivers, "ref_lambdas_host")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count(": ok") >= 7 and "all reference lambdas agree" in out.stdout
+    assert "Kick1: 0 of" in out.stdout and "Kick2: 0 of" in out.stdout
