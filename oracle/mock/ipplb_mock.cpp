@@ -19,6 +19,7 @@
 #include <cuda_runtime_api.h>
 
 #include "../../include/ippl_b200.h"
+#include "../../include/ippl/philox.h"
 
 // ---- the oracle's C functions (oracle/ippl_oracle.cpp, compiled into the same library) -------------------------------
 extern "C" {
@@ -320,6 +321,87 @@ int ipplb_particles_kinetic(ipplb_ctx*, long n, const double* px, const double* 
     *out = s;
     return IPPLB_OK;
 }
+
+// ---- particle initialisation (host restatement of ippl_b200/csrc/sample.cu: same formulas, same Philox stream) ----------------
+static double m_cdf(const ipplb_dist* D, int d, double x) {
+    switch (D->kind[d]) {
+        case IPPLB_DIST_COSINE: return x + (D->par[2 * d] / D->par[2 * d + 1]) * std::sin(D->par[2 * d + 1] * x);
+        case IPPLB_DIST_NORMAL: return 0.5 * (1 + std::erf((x - D->par[2 * d]) / (D->par[2 * d + 1] * std::sqrt(2.0))));
+        default: return x;
+    }
+}
+static double m_pdf(const ipplb_dist* D, int d, double x) {
+    switch (D->kind[d]) {
+        case IPPLB_DIST_COSINE: return 1.0 + D->par[2 * d] * std::cos(D->par[2 * d + 1] * x);
+        case IPPLB_DIST_NORMAL: {
+            const double pi = 3.14159265358979323846, mean = D->par[2 * d], sd = D->par[2 * d + 1];
+            return (1.0 / (sd * std::sqrt(2 * pi))) * std::exp(-(x - mean) * (x - mean) / (2 * sd * sd));
+        }
+        default: return 1.0;
+    }
+}
+int ipplb_sample_counts(const ipplb_dist* D, const double rmin[3], const double rmax[3], const double* regions, int nranks,
+                        long ntotal, long* nlocal, double* ub) {
+    unsigned long nglobal = 0;
+    for (int r = 0; r < nranks; ++r) {
+        double pnr = 1.0, pdr = 1.0;
+        for (int d = 0; d < 3; ++d) {
+            const double lmin = regions[r * 6 + d], lmax = regions[r * 6 + 3 + d];
+            pnr *= m_cdf(D, d, lmax) - m_cdf(D, d, lmin);
+            pdr *= m_cdf(D, d, rmax[d]) - m_cdf(D, d, rmin[d]);
+            if (ub) {
+                ub[r * 6 + d]     = m_cdf(D, d, lmin);
+                ub[r * 6 + 3 + d] = m_cdf(D, d, lmax);
+            }
+        }
+        nlocal[r] = (long)(unsigned long)((pnr / pdr) * ntotal);
+        nglobal += (unsigned long)nlocal[r];
+    }
+    const int rest = (int)((unsigned long)ntotal - nglobal);
+    for (int r = 0; r < nranks; ++r)
+        if (r < rest) ++nlocal[r];
+    return IPPLB_OK;
+}
+int ipplb_sample_positions(ipplb_ctx*, const ipplb_dist* D, const double umin[3], const double umax[3], uint64_t seed, long first_id,
+                           long n, double* x, double* y, double* z) {
+    double* out[3] = {x, y, z};
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            const double u01 = philox_uniform(seed, (unsigned long long)(first_id + i), (unsigned)d, 0);
+            const double u   = umin[d] + (umax[d] - umin[d]) * u01;
+            double s = D->kind[d] == IPPLB_DIST_NORMAL ? D->par[2 * d] + 0. * u * D->par[2 * d + 1] : u + D->par[d] * 0.;
+            unsigned iter = 0;
+            while (iter < 20u && std::fabs(m_cdf(D, d, s) - u) > 1e-12) {
+                s = s - ((m_cdf(D, d, s) - u) / m_pdf(D, d, s));
+                iter += 1;
+            }
+            out[d][i] = s;
+        }
+    return IPPLB_OK;
+}
+int ipplb_sample_normal(ipplb_ctx*, const double mu[3], const double sd[3], uint64_t seed, long first_id, long n, double* px,
+                        double* py, double* pz) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        double g[3];
+        philox_normal3(seed, (unsigned long long)(first_id + i), g);
+        px[i] = mu[0] + sd[0] * g[0];
+        py[i] = mu[1] + sd[1] * g[1];
+        pz[i] = mu[2] + sd[2] * g[2];
+    }
+    return IPPLB_OK;
+}
+int ipplb_field_fill_pdf(ipplb_ctx*, const ipplb_mesh*, const ipplb_dist*, double*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+// the bucketed store behind --fused is CUDA only
+int ipplb_bins_create(ipplb_ctx*, const ipplb_mesh*, long, ipplb_bins**) { return fail(IPPLB_ERR_NO_DEVICE, "mock: the fused step needs a GPU"); }
+int ipplb_bins_destroy(ipplb_bins*) { return IPPLB_OK; }
+int ipplb_bins_build(ipplb_ctx*, ipplb_bins*, const ipplb_particles*, ipplb_particles*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
+int ipplb_bins_step(ipplb_ctx*, ipplb_bins*, const ipplb_push*, const ipplb_particles*, ipplb_particles*, const double*, double*, double*,
+                    int, const double*, const double*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
+int ipplb_bins_migrate(ipplb_ctx*, ipplb_bins*, ipplb_particles*, const double*, int, double*, long*, long*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
+int ipplb_bins_compact(ipplb_ctx*, ipplb_bins*, const ipplb_particles*, ipplb_particles*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
+int ipplb_bins_kinetic(ipplb_ctx*, ipplb_bins*, const ipplb_particles*, double*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
 
 // ---- one rank: the communicator entry points ---------------------------------------------------------------------------------
 int ipplb_allreduce_sum_f64(ipplb_ctx*, double*) { return IPPLB_OK; }
