@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <functional>
 #include <iomanip>
@@ -158,6 +159,22 @@ namespace b200 {
         cuda_check(cudaMalloc(&p, sizeof(T) * std::max<std::size_t>(n, 1)), "cudaMalloc");
         return p;
     }
+    // IPPL_B200_FUSE=1 (or fusion_enabled() = true before the particles are created): the leapfrog expression sequence of an
+    // unchanged driver is recognised lazily and executed by the fused single-pass step (detail::FusionEngine below).
+    inline bool& fusion_enabled() {
+        static bool on = [] {
+            const char* e = std::getenv("IPPL_B200_FUSE");
+            return e && std::atoi(e) != 0;
+        }();
+        return on;
+    }
+    struct FusionStats {
+        long fused_steps = 0, materialised = 0;
+    };
+    inline FusionStats& fusion_stats() {
+        static FusionStats st;
+        return st;
+    }
 }  // namespace b200
 
 class Communicator {
@@ -268,6 +285,9 @@ inline void initialize(int& argc, char**& argv) {
     }
 }
 inline void finalize() {
+    if (b200::fusion_enabled() && Inform::rank_ref() == 0)
+        std::cout << "ippl_b200 fusion: " << b200::fusion_stats().fused_steps << " fused steps, " << b200::fusion_stats().materialised
+                  << " materialisations" << std::endl;
     if (b200::ctx_ref()) ipplb_ctx_destroy(b200::ctx_ref());
     b200::ctx_ref() = nullptr;
     if (!b200::id_file().empty()) std::remove(b200::id_file().c_str());
@@ -730,9 +750,167 @@ namespace detail {
         virtual void reserve_storage(std::size_t n)   = 0;
         void set_name(const std::string& n) { name_ = n; }
         const std::string& get_name() const { return name_; }
+        void set_engine(class FusionEngine* e) { engine_ = e; }
+        class FusionEngine* engine() const { return engine_; }
 
     protected:
         std::string name_;
+        class FusionEngine* engine_ = nullptr;   // the container's lazy-fusion engine (set by ParticleBase)
+    };
+
+    // Lazy fusion of the alpine leapfrog sequence onto ipplb_bins_step, for drivers that are NOT changed.  An unchanged
+    // driver spells one step as separate attribute expressions and calls (LandauDampingManager.h:265-320):
+    //     gather(E_p, E, R);  P = P - 0.5 dt E_p;  |  P = P - 0.5 dt E_p;  R = R + dt P;  pc->update();  scatter(q, rho, R);
+    // (the bar is the step boundary).  With fusion on, none of the first five does any work: each is RECORDED.  When the
+    // scatter arrives and the record is exactly [gather, kick (, kick), drift, periodic BC] with matching coefficients and a
+    // uniform charge, ONE fused kernel does all of it on the bucketed particle store (where the particles then stay).  Any
+    // other access to the container's attributes in between -- getView(), a driver lambda, a dump that reads P, create(),
+    // an expression that does not fit -- MATERIALISES first: the particles go back to the contiguous attribute arrays
+    // (ipplb_bins_compact) and the recorded operations run one by one through the ordinary kernels, in order, so the
+    // driver always sees what the unfused sequence would have produced (per particle bit for bit; rho to summation
+    // order).  One thing cannot be reproduced: E_p AFTER a fused step (the gather it belongs to was consumed inside the
+    // kernel); reading it then throws.  One rank only for now: several ranks take the unfused path.
+    class FusionEngine {
+    public:
+        enum Kind { GATHER, KICK, DRIFT, BCS };
+        struct Op {
+            Kind kind;
+            double coef;
+            std::function<void()> eager;
+        };
+        ParticleAttribBase* R = nullptr;   // positions
+        const std::size_t* local_num = nullptr;
+        bool busy = false;                 // inside materialise(): every hook is a plain call
+
+        bool active() const { return b200::fusion_enabled() && !busy && R != nullptr && Comm && Comm->size() == 1; }
+        bool pending() const { return !chain_.empty(); }
+        ~FusionEngine() { release(); }
+
+        // -- recording (each returns false when the operation does not continue the pattern) ---------------------------------
+        void record_gather(ParticleAttribBase* target, const double* field, std::function<void()> fill_halo, std::function<void()> eager) {
+            if (pending()) materialise();   // an older, unconsumed record goes first
+            chain_.push_back(Op{GATHER, 0.0, std::move(eager)});
+            e_attr_ = target;
+            e_field_ = field;
+            e_fill_halo_ = std::move(fill_halo);
+        }
+        bool record_axpy(ParticleAttribBase* y, const ParticleAttribBase* x, double a, std::function<void()> eager) {
+            if (chain_.empty() || chain_.front().kind != GATHER) return false;
+            const Kind last = chain_.back().kind;
+            if (x == e_attr_ && y != R && (last == GATHER || (last == KICK && y == vel_ && kicks() < 2))) {
+                vel_ = y;
+                chain_.push_back(Op{KICK, a, std::move(eager)});
+                return true;
+            }
+            if (y == R && x == vel_ && last == KICK) {
+                chain_.push_back(Op{DRIFT, a, std::move(eager)});
+                return true;
+            }
+            return false;
+        }
+        bool record_bc(std::function<void()> eager) {
+            if (chain_.empty() || chain_.back().kind != DRIFT) return false;
+            chain_.push_back(Op{BCS, 0.0, std::move(eager)});
+            return true;
+        }
+        // -- the fused step: true when the record was the whole pattern and has been executed (rho's halo is NOT accumulated) ------
+        bool fused_scatter(double q, double* rho, const ipplb_mesh& mesh) {
+            if (chain_.size() < 4 || chain_.back().kind != BCS) return false;
+            const int nk = kicks();
+            const double c = chain_[1].coef, dt = chain_[chain_.size() - 2].coef;
+            if (nk < 1 || (nk == 2 && chain_[2].coef != c) || c != -(0.5 * dt)) return false;   // not the leapfrog coefficients
+            ipplb_ctx* ctx = b200::ctx();
+            const long n   = (long)*local_num;
+            if (bins_ && (n + n / 8 > cap_ || std::memcmp(&mesh, &bins_mesh_, sizeof(mesh)) != 0)) {
+                if (in_bins_) return false;   // cannot re-bucket from the store: let the caller materialise
+                release();
+            }
+            if (!bins_) {
+                cap_ = n + n / 4 + 65536;
+                b200::check(ipplb_bins_create(ctx, &mesh, cap_, &bins_), "fusion: bins_create");
+                bins_mesh_ = mesh;
+                for (auto& p : spare_) p = b200::device_alloc<double>((std::size_t)cap_);
+                cur_ = ipplb_particles{spare_[0], spare_[1], spare_[2], spare_[3], spare_[4], spare_[5], nullptr, q, 0, cap_};
+                nxt_ = ipplb_particles{spare_[6], spare_[7], spare_[8], spare_[9], spare_[10], spare_[11], nullptr, q, 0, cap_};
+            }
+            if (!in_bins_) {   // bucket the contiguous attribute arrays once; the particles then live in the store
+                ipplb_particles in{R->component_ptr(0),    R->component_ptr(1),    R->component_ptr(2), vel_->component_ptr(0),
+                                   vel_->component_ptr(1), vel_->component_ptr(2), nullptr,             q,
+                                   n,                      (long)std::min(R->capacity(), vel_->capacity())};
+                b200::check(ipplb_bins_build(ctx, bins_, &in, &cur_), "fusion: bins_build");
+                in_bins_ = true;
+            }
+            cur_.q_scalar = nxt_.q_scalar = q;
+            ipplb_push push{};
+            push.kind     = IPPLB_PUSH_LEAPFROG;
+            push.dt       = dt;
+            push.do_kick2 = nk == 2;
+            push.do_kick1 = push.do_drift = push.do_bc = 1;
+            e_fill_halo_();
+            b200::check(ipplb_bins_step(ctx, bins_, &push, &cur_, &nxt_, e_field_, rho, nullptr, 0, nullptr, nullptr), "fusion: bins_step");
+            std::swap(cur_, nxt_);
+            chain_.clear();
+            e_consumed_ = true;
+            ++b200::fusion_stats().fused_steps;
+            return true;
+        }
+        // -- back to what the unfused sequence would hold: contiguous arrays valid, pending operations executed in order --------
+        void materialise() {
+            if (busy || (chain_.empty() && !in_bins_)) return;
+            busy = true;
+            struct Unbusy {
+                bool& b;
+                ~Unbusy() { b = false; }
+            } guard{busy};
+            if (in_bins_) {
+                ipplb_particles out{R->component_ptr(0),    R->component_ptr(1),    R->component_ptr(2), vel_->component_ptr(0),
+                                    vel_->component_ptr(1), vel_->component_ptr(2), nullptr,             cur_.q_scalar,
+                                    0,                      (long)std::min(R->capacity(), vel_->capacity())};
+                b200::check(ipplb_bins_compact(b200::ctx(), bins_, &cur_, &out), "fusion: bins_compact");
+                in_bins_ = false;
+            }
+            std::vector<Op> ops;
+            ops.swap(chain_);
+            if (!ops.empty() && ops.front().kind == GATHER) e_consumed_ = false;   // the gather is about to be computed for real
+            for (auto& op : ops) op.eager();
+            ++b200::fusion_stats().materialised;
+        }
+        // called by every public accessor of an attribute of the container
+        void sync(const ParticleAttribBase* who) {
+            if (busy) return;
+            materialise();
+            if (who == e_attr_ && e_consumed_)
+                throw IpplException("ippl_b200 fusion",
+                                    "the field at the particles was consumed by the fused step and never stored; run with IPPL_B200_FUSE=0 "
+                                    "if the driver reads it between scatter and the next gather");
+        }
+
+    private:
+        int kicks() const {
+            int k = 0;
+            for (auto& op : chain_) k += op.kind == KICK;
+            return k;
+        }
+        void release() {
+            if (bins_) ipplb_bins_destroy(bins_);
+            bins_ = nullptr;
+            for (auto& p : spare_) {
+                if (p) cudaFree(p);
+                p = nullptr;
+            }
+            in_bins_ = false;
+        }
+        std::vector<Op> chain_;
+        ParticleAttribBase *e_attr_ = nullptr, *vel_ = nullptr;   // gather target, velocity attribute
+        const double* e_field_ = nullptr;
+        std::function<void()> e_fill_halo_;
+        bool e_consumed_ = false;
+        ipplb_bins* bins_ = nullptr;
+        ipplb_mesh bins_mesh_{};
+        ipplb_particles cur_{}, nxt_{};
+        double* spare_[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        long cap_     = 0;
+        bool in_bins_ = false;
     };
     // a * attrib  and  attrib +/- a * attrib : the expressions the alpine pushes are made of
     template <class A>
@@ -780,6 +958,7 @@ public:
     }
     // create(n): grows with the communicator's over-allocation factor truncated to int (ParticleAttrib.hpp:37-49)
     void create(std::size_t n) override {
+        touch();
         const std::size_t need = count_ + n;
         if (need > capacity_) {
             const int over         = std::max(1, (int)Comm->getDefaultOverallocation());
@@ -797,6 +976,7 @@ public:
         count_ = need;
     }
     void setCount(std::size_t n) override {
+        touch();
         reserve(n);
         count_ = n;
     }
@@ -822,6 +1002,9 @@ public:
     // the SoA component arrays, usable inside device lambdas (include/ippl/KokkosShim.cuh)
     using view_type = detail::AttribView<ncomp>;
     IPPL_HD view_type getView() const {
+#ifndef __CUDA_ARCH__
+        touch();   // a view hands out the storage: pending lazy operations run first, the charge is no longer known to be uniform
+#endif
         view_type v;
         for (int c = 0; c < ncomp; ++c) v.c[c] = d_[c];
         v.n = count_;
@@ -830,23 +1013,43 @@ public:
     // attrib(i): element access inside kernels (src/Particle/ParticleAttrib.h)
     IPPL_HD auto operator()(std::size_t i) const -> decltype(std::declval<view_type>()(i)) { return getView()(i); }
     std::size_t getParticleCount() const { return count_; }
-    double* component(int c) const { return d_[c]; }
+    double* component(int c) const {
+        touch();
+        return d_[c];
+    }
     // attrib = scalar (ParticleAttrib.hpp:105-116)
     ParticleAttrib& operator=(const T& v) {
+        sync();
         for (int c = 0; c < ncomp; ++c)
             b200::check(ipplb_field_fill(b200::ctx(), d_[c], (long)count_, comp(v, c)), "ParticleAttrib::operator=");
+        if constexpr (ncomp == 1) {
+            uniform_valid_ = true;
+            uniform_value_ = comp(v, 0);
+        }
         return *this;
+    }
+    // lazy fusion (detail::FusionEngine): make this attribute's storage say what the unfused sequence would have produced
+    void sync() const {
+        if (engine_) engine_->sync(this);
     }
     // attrib = expression (ParticleAttrib.hpp:118-130) for y = y +/- a * x: one axpy per component, same rounding
     // as the reference's per-particle y - (a * x)
     ParticleAttrib& operator=(const detail::Axpy<ParticleAttrib>& e) {
         if (e.y != this) throw IpplException("ParticleAttrib::operator=", "only y = y + a * x is supported by the facade");
+        if (engine_ && engine_->active() && ncomp == 3) {   // a kick or the drift of a recorded leapfrog step?
+            ParticleAttrib* self = this;
+            const detail::Axpy<ParticleAttrib> copy = e;
+            if (engine_->record_axpy(this, e.x, e.a, [self, copy] { *self = copy; })) return *this;
+        }
+        sync();
+        e.x->sync();
         for (int c = 0; c < ncomp; ++c)
             b200::check(ipplb_axpy(b200::ctx(), (long)count_, e.a, e.x->d_[c], d_[c]), "ParticleAttrib::operator=");
         return *this;
     }
     // sum over local particles (then ranks): ParticleAttrib.hpp:511-532
     double sum(int c = 0) const {
+        sync();
         // reuse the interior-sum kernel on a 1-D "mesh" of count_ cells without ghosts
         ipplb_mesh m{};
         m.ng[0] = m.nl[0] = (int)count_;
@@ -862,6 +1065,7 @@ public:
     using HostMirror = std::vector<T>;
     HostMirror getHostMirror() const { return HostMirror(count_); }
     void copyFromHost(const HostMirror& h) {
+        touch();
         std::vector<double> tmp(count_);
         for (int c = 0; c < ncomp; ++c) {
             for (std::size_t i = 0; i < count_; ++i) tmp[i] = comp(h[i], c);
@@ -869,6 +1073,7 @@ public:
         }
     }
     void copyToHost(HostMirror& h) const {
+        sync();
         h.resize(count_);
         std::vector<double> tmp(count_);
         fence();
@@ -883,6 +1088,7 @@ public:
     void scatter(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp, const RangePolicy1D& policy,
                  const hash_type& hash_array = {}) const {
         static_assert(ncomp == 1, "scatter deposits a scalar attribute");
+        sync();
         b200::check(ipplb_scatter_cic(b200::ctx(), &f.b200_mesh(), policy.begin(), policy.end(), pp.component(0),
                                       pp.component(1), pp.component(2), d_[0], 0.0, hash_array.extent(0) ? hash_array.data() : nullptr,
                                       f.data()),
@@ -893,6 +1099,13 @@ public:
     template <typename Field, typename PT>
     void scatter(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp) const {
         static_assert(ncomp == 1, "scatter deposits a scalar attribute");
+        if (engine_ && engine_->active() && engine_->pending() && uniform_valid_
+            && static_cast<const detail::ParticleAttribBase*>(&pp) == engine_->R && Field::ncomp == 1
+            && engine_->fused_scatter(uniform_value_, f.data(), f.b200_mesh())) {
+            f.accumulateHalo();   // [gather, kick(s), drift, BC] + this scatter ran as ONE fused kernel
+            return;
+        }
+        sync();
         b200::check(ipplb_scatter_cic(b200::ctx(), &f.b200_mesh(), 0, (long)pp.getParticleCount(), pp.component(0),
                                       pp.component(1), pp.component(2), d_[0], 0.0, nullptr, f.data()),
                     "ParticleAttrib::scatter");
@@ -900,6 +1113,15 @@ public:
     }
     template <typename Field, typename PT>
     void gather(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp, bool addToAttribute = false) {
+        if (engine_ && engine_->active() && ncomp == 3 && Field::ncomp == 3 && !addToAttribute
+            && static_cast<const detail::ParticleAttribBase*>(&pp) == engine_->R) {
+            ParticleAttrib* self = this;
+            Field* fp            = &f;
+            const auto* ppp      = &pp;
+            engine_->record_gather(this, f.data(), [fp] { fp->fillHalo(); }, [self, fp, ppp] { self->gather(*fp, *ppp, false); });
+            return;
+        }
+        sync();
         f.fillHalo();
         double* out[3] = {d_[0], ncomp > 1 ? d_[1] : nullptr, ncomp > 2 ? d_[2] : nullptr};
         b200::check(ipplb_gather_cic(b200::ctx(), &f.b200_mesh(), (long)pp.getParticleCount(), pp.component(0),
@@ -914,8 +1136,14 @@ private:
     static double comp(const Vector<U, D>& v, int c) { return v[c]; }
     template <typename U, unsigned D>
     static double& comp(Vector<U, D>& v, int c) { return v[c]; }
+    void touch() const {   // storage handed out / rewritten
+        sync();
+        uniform_valid_ = false;
+    }
     std::array<double*, 3> d_{nullptr, nullptr, nullptr};
     std::size_t count_ = 0, capacity_ = 0;
+    mutable bool uniform_valid_ = false;   // every element holds uniform_value_ (set by attrib = scalar): what the fused step needs of q
+    double uniform_value_       = 0.0;
 };
 
 template <typename T>
@@ -980,6 +1208,11 @@ public:
     // (ParticleSpatialLayout.hpp:128), else ownership + exchange + compaction (ipplb_update)
     template <class PC>
     void update(PC& pc) {
+        if (auto* eng = pc.R.engine(); eng && eng->active() && bc_ == PERIODIC) {   // the BC of a recorded leapfrog step?
+            ParticleSpatialLayout* self = this;
+            PC* pcp                     = &pc;
+            if (eng->record_bc([self, pcp] { self->update(*pcp); })) return;
+        }
         auto& R = pc.R;
         long n  = (long)pc.getLocalNum();
         double lo[3], hi[3];
@@ -1007,11 +1240,19 @@ public:
     using particle_position_type = typename PLayout::particle_position_type;
     using vector_type            = typename PLayout::vector_type;
     particle_position_type R;
-    ParticleBase() { attributes_.push_back(&R); }
+    ParticleBase() {
+        attributes_.push_back(&R);
+        engine_.R         = &R;
+        engine_.local_num = &localNum_;
+        R.set_engine(&engine_);
+    }
     explicit ParticleBase(PLayout& l) : ParticleBase() { initialize(l); }
     virtual ~ParticleBase() = default;
     void initialize(PLayout& l) { layout_ = &l; }
-    void addAttribute(detail::ParticleAttribBase& a) { attributes_.push_back(&a); }
+    void addAttribute(detail::ParticleAttribBase& a) {
+        attributes_.push_back(&a);
+        a.set_engine(&engine_);
+    }
     void setParticleBC(BC bc) { layout_->setParticleBC(bc); }
     void create(std::size_t nLocal) {
         for (auto* a : attributes_) a->create(nLocal);
@@ -1070,6 +1311,7 @@ protected:
     PLayout* layout_ = nullptr;
     std::vector<detail::ParticleAttribBase*> attributes_;
     std::size_t localNum_ = 0;
+    detail::FusionEngine engine_;   // lazy fusion of the leapfrog sequence (off unless IPPL_B200_FUSE=1)
 };
 
 // ---- RegionLayout (src/Region/RegionLayout.h): physical region of every rank ---------------------------------------------------------

@@ -48,6 +48,10 @@ struct ipplb_poisson {
     ipplb_mesh m;
     std::vector<double> k[3];
 };
+struct ipplb_bins {
+    ipplb_mesh m;
+    long capacity = 0;
+};
 
 namespace {
 std::string g_err;
@@ -393,15 +397,66 @@ int ipplb_sample_normal(ipplb_ctx*, const double mu[3], const double sd[3], uint
     return IPPLB_OK;
 }
 int ipplb_field_fill_pdf(ipplb_ctx*, const ipplb_mesh*, const ipplb_dist*, double*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
-// the bucketed store behind --fused is CUDA only
-int ipplb_bins_create(ipplb_ctx*, const ipplb_mesh*, long, ipplb_bins**) { return fail(IPPLB_ERR_NO_DEVICE, "mock: the fused step needs a GPU"); }
-int ipplb_bins_destroy(ipplb_bins*) { return IPPLB_OK; }
-int ipplb_bins_build(ipplb_ctx*, ipplb_bins*, const ipplb_particles*, ipplb_particles*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
-int ipplb_bins_step(ipplb_ctx*, ipplb_bins*, const ipplb_push*, const ipplb_particles*, ipplb_particles*, const double*, double*, double*,
-                    int, const double*, const double*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
-int ipplb_bins_migrate(ipplb_ctx*, ipplb_bins*, ipplb_particles*, const double*, int, double*, long*, long*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
-int ipplb_bins_compact(ipplb_ctx*, ipplb_bins*, const ipplb_particles*, ipplb_particles*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
-int ipplb_bins_kinetic(ipplb_ctx*, ipplb_bins*, const ipplb_particles*, double*) { return fail(IPPLB_ERR_NO_DEVICE, "mock: no fused step"); }
+// the bucketed store behind the fused step, emulated: "buckets" are plain contiguous arrays, one step = the reference-order
+// sequence gather, kick(s), drift, periodic BC, scatter on the oracle (leapfrog only) -- enough to exercise the HOST logic that
+// drives ipplb_bins_* (the facade's lazy-fusion engine); the real store and kernel are CUDA only.
+int ipplb_bins_create(ipplb_ctx*, const ipplb_mesh* mesh, long capacity, ipplb_bins** out) {
+    ipplb_bins* b = new ipplb_bins();
+    b->m          = *mesh;
+    b->capacity   = capacity;
+    *out          = b;
+    return IPPLB_OK;
+}
+int ipplb_bins_destroy(ipplb_bins* b) {
+    delete b;
+    return IPPLB_OK;
+}
+static void copy6(const ipplb_particles* in, ipplb_particles* out, long n) {
+    const double* s[6] = {in->x, in->y, in->z, in->px, in->py, in->pz};
+    double* d[6]       = {out->x, out->y, out->z, out->px, out->py, out->pz};
+    for (int a = 0; a < 6; ++a) std::memcpy(d[a], s[a], sizeof(double) * n);
+}
+int ipplb_bins_build(ipplb_ctx*, ipplb_bins* b, const ipplb_particles* in, ipplb_particles* out) {
+    if (in->n > b->capacity || out->capacity < in->n) return fail(IPPLB_ERR_CAPACITY, "mock bins_build: capacity");
+    copy6(in, out, in->n);
+    out->n        = in->n;
+    out->q_scalar = in->q_scalar;
+    return IPPLB_OK;
+}
+int ipplb_bins_step(ipplb_ctx*, ipplb_bins* b, const ipplb_push* push, const ipplb_particles* cur, ipplb_particles* nxt, const double* efield,
+                    double* rho, double* exit_buf, int, const double*, const double*) {
+    if (push->kind != IPPLB_PUSH_LEAPFROG || exit_buf) return fail(IPPLB_ERR_ARG, "mock bins_step: single-rank leapfrog only");
+    const long n = cur->n;
+    const orc_mesh m = to_orc(&b->m);
+    copy6(cur, nxt, n);
+    std::vector<double> e0(n), e1(n), e2(n);
+    double* E[3] = {e0.data(), e1.data(), e2.data()};
+    orc_gather_cic(&m, n, nxt->x, nxt->y, nxt->z, efield, 3, E, 0, 1);
+    double* P[3] = {nxt->px, nxt->py, nxt->pz};
+    double* R[3] = {nxt->x, nxt->y, nxt->z};
+    const double c = 0.5 * push->dt;
+    for (int k = 0; k < (push->do_kick2 ? 1 : 0) + (push->do_kick1 ? 1 : 0); ++k)
+        for (int d = 0; d < 3; ++d)
+            for (long i = 0; i < n; ++i) P[d][i] = P[d][i] - c * E[d][i];
+    for (int d = 0; d < 3; ++d) {
+        if (push->do_drift)
+            for (long i = 0; i < n; ++i) R[d][i] = R[d][i] + push->dt * P[d][i];
+        if (push->do_bc) orc_periodic_bc(n, R[d], 0 * b->m.h[d] + b->m.origin[d], b->m.ng[d] * b->m.h[d] + b->m.origin[d], 1);
+    }
+    orc_scatter_cic(&m, 0, n, nxt->x, nxt->y, nxt->z, nullptr, cur->q_scalar, nullptr, rho, 1);
+    nxt->n = n;
+    return IPPLB_OK;
+}
+int ipplb_bins_compact(ipplb_ctx*, ipplb_bins*, const ipplb_particles* cur, ipplb_particles* out) {
+    if (out->capacity < cur->n) return fail(IPPLB_ERR_CAPACITY, "mock bins_compact: capacity");
+    copy6(cur, out, cur->n);
+    out->n = cur->n;
+    return IPPLB_OK;
+}
+int ipplb_bins_migrate(ipplb_ctx*, ipplb_bins*, ipplb_particles*, const double*, int, double*, long*, long*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+int ipplb_bins_kinetic(ipplb_ctx*, ipplb_bins*, const ipplb_particles* cur, double* out) {
+    return ipplb_particles_kinetic(nullptr, cur->n, cur->px, cur->py, cur->pz, out);
+}
 
 // ---- one rank: the communicator entry points ---------------------------------------------------------------------------------
 int ipplb_allreduce_sum_f64(ipplb_ctx*, double*) { return IPPLB_OK; }

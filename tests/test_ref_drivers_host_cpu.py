@@ -106,3 +106,34 @@ def test_restated_drivers_equal_the_unchanged_reference_drivers(drivers, tmp_pat
 def test_api_check_demo_on_the_mock(drivers):
     out = subprocess.run([os.path.join(drivers, "demo_api_check_host")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "scatter(policy, hash)" in out.stdout and "ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("app,csv,cols,fused_steps", [("LandauDamping", "FieldLandau_1_manager.csv", [0, 1, 2], 8),
+                                                       ("BumponTailInstability", "FieldBumponTail_1_manager.csv", [0, 1, 2], 8),
+                                                       ("PenningTrap", "ParticleField_1_manager.csv", [0, 1, 2, 3, 5, 6, 7], 0)])
+def test_lazy_fusion_runs_the_unchanged_drivers_on_the_fused_step(drivers, tmp_path, app, csv, cols, fused_steps):
+    """IPPL_B200_FUSE=1: the facade records the unchanged driver's gather / kick / kick / drift / update() and executes them
+    together with the scatter as ONE ipplb_bins_step (here: the mock's emulation of it; the host logic is what is under test).
+    LandauDamping and BumponTail fuse every step and never materialise; PenningTrap's kicks are driver lambdas over getView(),
+    so every step materialises and nothing fuses.  Either way the CSV is the one of the plain run."""
+    def go(fuse):
+        d = tmp_path / f"fuse{fuse}"
+        (d / "data").mkdir(parents=True)
+        cmd = [os.path.join(drivers, f"ref_{app}_host"), "16", "16", "16", "300000", "8", "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
+               "--info", "0"]
+        out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600, env=dict(os.environ, IPPL_B200_FUSE=str(fuse)))
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return np.loadtxt(d / "data" / csv, skiprows=1)[:, cols], out.stdout
+    plain, log0 = go(0)
+    fused, log1 = go(1)
+    assert "ippl_b200 fusion" not in log0
+    assert f"ippl_b200 fusion: {fused_steps} fused steps, {0 if fused_steps else 9} materialisations" in log1, log1[-500:]
+    assert np.max(np.abs(plain - fused) / np.maximum(np.abs(plain), 1e-300)) <= 1e-12
+
+
+def test_fusion_engine_materialises_correctly_when_the_driver_peeks(drivers):
+    """demos/fusion_check.cpp on the mock: peeks at the particles after the closing kick, between drift and update and right
+    after a fused scatter; same particles and field-energy history as the plain run, 8 of 12 steps fused, 6 materialisations."""
+    out = subprocess.run([os.path.join(drivers, "demo_fusion_check_host")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fusion_check: ok" in out.stdout, out.stdout + out.stderr
+    assert "8 fused steps, 6 materialisations" in out.stdout

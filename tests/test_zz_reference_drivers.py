@@ -28,13 +28,16 @@ def _exe(name):
     return path
 
 
-def _run(tmp_path, exe, grid, np_, nt, csv):
-    d = tmp_path / exe
+def _run(tmp_path, exe, grid, np_, nt, csv, fuse=None, log=None):
+    d = tmp_path / (exe + ("" if fuse is None else f"_fuse{fuse}"))
     (d / "data").mkdir(parents=True)
     cmd = [_exe(exe), str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
            "--info", "0"]
-    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=150)
+    env = dict(os.environ) if fuse is None else dict(os.environ, IPPL_B200_FUSE=str(fuse))
+    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=150, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    if log is not None:
+        log.append(out.stdout)
     return np.loadtxt(d / "data" / csv, skiprows=1)
 
 
@@ -69,3 +72,21 @@ def test_reference_penningtrap_driver(tmp_path):
     assert abs(got[0, 2] / (1.5 * 2000000) - 1.0) <= 5e-3
     h3 = (20.0 / 32) ** 3
     assert np.allclose(got[:, 1], 0.5 * h3 * (got[:, 5] ** 2 + got[:, 6] ** 2 + got[:, 7] ** 2), rtol=1e-8)
+
+
+def test_reference_landau_driver_on_the_fused_step(tmp_path):
+    """IPPL_B200_FUSE=1: the unchanged LandauDamping.cpp with its expression sequence executed by ipplb_bins_step (the facade's
+    lazy-fusion engine; host logic verified on the CPU in tests/test_ref_drivers_host_cpu.py): every step fused, nothing
+    materialised, the reference's known answer reproduced, and the plain run's history to summation order."""
+    golden = np.loadtxt(os.path.join(ROOT, "tests", "golden", "FieldLandau_valid_result.csv"), skiprows=1)
+    log = []
+    fused = _run(tmp_path, "ref_LandauDamping", 16, 10000000, 25, "FieldLandau_1_manager.csv", fuse=1, log=log)
+    plain = _run(tmp_path, "ref_LandauDamping", 16, 10000000, 25, "FieldLandau_1_manager.csv", fuse=0)
+    assert "ippl_b200 fusion: 25 fused steps, 0 materialisations" in log[0], log[0][-500:]
+    assert np.max(np.abs(fused[:, 1:] - golden[:, 1:])) <= 0.4
+    assert np.max(np.abs(fused[:, 1:] - plain[:, 1:]) / np.abs(plain[:, 1:])) <= 1e-9
+
+
+def test_fusion_engine_with_peeks_on_gpu():
+    out = subprocess.run([_exe("fusion_check")], capture_output=True, text=True, timeout=150)
+    assert out.returncode == 0 and "fusion_check: ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
