@@ -868,6 +868,9 @@ namespace detail {
                                     0,                      (long)std::min(R->capacity(), vel_->capacity())};
                 b200::check(ipplb_bins_compact(b200::ctx(), bins_, &cur_, &out), "fusion: bins_compact");
                 in_bins_ = false;
+                if (out.n != (long)*local_num)
+                    throw IpplException("ippl_b200 fusion", "the bucketed store holds " + std::to_string(out.n) + " particles, the container "
+                                                                + std::to_string(*local_num) + " (ipplb_bins_status flags tell why)");
             }
             std::vector<Op> ops;
             ops.swap(chain_);
