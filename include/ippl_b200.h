@@ -412,6 +412,8 @@ int ipplb_orb_cut(ipplb_orb* orb, const double* reduced_host, int n);
 /* boxes_out[nranks][6] = lo[3], hi[3]; *ok = 0 when a box has an axis of length 1 (the reference then keeps the old
  * layout, :93-99).  Destroys the state. */
 int ipplb_orb_finish(ipplb_orb* orb, int* boxes_out, int* ok);
+/* drops a state machine that will not be driven to ipplb_orb_finish (which frees it) */
+int ipplb_orb_destroy(ipplb_orb* o);
 /* perpendicularReduction + allreduce: out_host[k] = sum over ranks of the sum of `field`'s interior cells in plane
  * dom_lo[axis] + k of the domain (cells outside the rank's box contribute nothing). */
 int ipplb_orb_plane_sums(ipplb_ctx* ctx, const ipplb_mesh* mesh, const double* field, int axis, const int dom_lo[3],

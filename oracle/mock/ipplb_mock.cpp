@@ -17,9 +17,15 @@
 #include <vector>
 
 #include <cuda_runtime_api.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <fstream>
+#include <thread>
 
 #include "../../include/ippl_b200.h"
 #include "../../include/ippl/philox.h"
+#include "../../ippl_b200/csrc/layout.h"
 
 // ---- the oracle's C functions (oracle/ippl_oracle.cpp, compiled into the same library) -------------------------------
 extern "C" {
@@ -39,14 +45,33 @@ void orc_periodic_bc(long n, double* x, double lo, double hi, int parallel);
 void orc_halo_periodic(double* v, const int ext[3], int ncomp, int nghost, const int serial[3], int mode);
 double orc_field_sum(const double* v, const int ext[3], int nghost);
 void orc_density(double* v, const int ext[3], int nghost, double cell_volume, double q_over_size);
+void orc_halo_exchange(const int ng[3], int nranks, const int* boxes, int nghost, int periodic, double** fields, int ncomp, int mode);
+void orc_regions(const int ng[3], int nranks, const int* boxes, const double origin[3], const double h[3], double* regions);
+void orc_locate(int nranks, const double* regions, int my, long n, const double* x, const double* y, const double* z, int* dest);
 }
 
 struct ipplb_ctx {
-    int dummy = 0;
+    int rank = 0, nranks = 1;
+    // several ranks = several processes; the "communicator" is a directory (IPPLB_MOCK_DIR) through which every collective
+    // is an all-gather of byte strings: small test sizes only
+    std::string dir;
+    long seq = 0;
+    ipplb::Layout L;
+    bool have_layout = false;
+    double origin[3] = {0, 0, 0}, h[3] = {1, 1, 1};
+    std::vector<int> boxes;        // [nranks][6]
+    std::vector<double> regions;   // [nranks][6]
+    // ipplb_update_plan -> ipplb_update_commit
+    std::vector<int> dest;
+    std::vector<double> arrivals;  // records of 7 doubles
+    long plan_n = -1;
 };
 struct ipplb_poisson {
-    ipplb_mesh m;
+    ipplb_mesh m;        // the whole domain
     std::vector<double> k[3];
+    ipplb_ctx* ctx = nullptr;
+    bool dist = false;
+    ipplb_mesh mine;     // this rank's box (dist)
 };
 struct ipplb_bins {
     ipplb_mesh m;
@@ -106,6 +131,86 @@ void dft_axis(std::vector<cplx>& a, const int n[3], int axis, int sign) {
             }
             for (int t = 0; t < len; ++t) a[base + t * s[axis]] = out[t];
         }
+}
+}  // namespace
+
+// ---- several ranks: every collective is an all-gather of byte strings through a directory ------------------------------------
+namespace {
+using Bytes = std::vector<char>;
+std::vector<Bytes> allgather(ipplb_ctx* c, const void* mine, size_t bytes) {
+    std::vector<Bytes> all(c->nranks);
+    if (c->nranks == 1) {
+        all[0].assign((const char*)mine, (const char*)mine + bytes);
+        return all;
+    }
+    const long q = c->seq++;
+    auto name = [&](long seq, int r) { return c->dir + "/m" + std::to_string(seq) + "_" + std::to_string(r); };
+    {
+        const std::string tmp = name(q, c->rank) + ".tmp";
+        std::ofstream f(tmp, std::ios::binary);
+        f.write((const char*)mine, (std::streamsize)bytes);
+        f.close();
+        std::rename(tmp.c_str(), name(q, c->rank).c_str());
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < c->nranks; ++r) {
+        for (;;) {
+            std::ifstream f(name(q, r), std::ios::binary | std::ios::ate);
+            if (f) {
+                const std::streamsize n = f.tellg();
+                all[r].resize((size_t)n);
+                f.seekg(0);
+                f.read(all[r].data(), n);
+                break;
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                std::fprintf(stderr, "ipplb mock: rank %d waited 120 s for rank %d in collective %ld\n", c->rank, r, q);
+                std::abort();
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
+    // everybody has read collective q - 2 before anybody could finish q - 1: my file of q - 2 can go
+    if (q >= 2) std::remove(name(q - 2, c->rank).c_str());
+    return all;
+}
+template <class T, class Op>
+void allreduce(ipplb_ctx* c, T* v, Op op) {
+    const auto all = allgather(c, v, sizeof(T));
+    T acc;
+    std::memcpy(&acc, all[0].data(), sizeof(T));
+    for (int r = 1; r < c->nranks; ++r) {
+        T x;
+        std::memcpy(&x, all[r].data(), sizeof(T));
+        acc = op(acc, x);
+    }
+    *v = acc;
+}
+int box_len(const ipplb_ctx* c, int r, int d) { return c->boxes[r * 6 + 3 + d] - c->boxes[r * 6 + d] + 1; }
+
+// FFTPeriodicPoissonSolver::solve, GRAD output, on the whole domain: rho_g [nz][ny][nx] -> E_g[c] [nz][ny][nx]
+void solve_global(const ipplb_poisson* s, const std::vector<double>& rho_g, std::vector<double> E_g[3]) {
+    const ipplb_mesh& m = s->m;
+    const int n[3] = {m.ng[0], m.ng[1], m.ng[2]};
+    const long N = (long)n[0] * n[1] * n[2];
+    std::vector<cplx> rh(N);
+    for (long l = 0; l < N; ++l) rh[l] = rho_g[l];
+    for (int a = 0; a < 3; ++a) dft_axis(rh, n, a, -1);
+    for (int c = 0; c < 3; ++c) {
+        std::vector<cplx> t(N);
+        for (int k = 0; k < n[2]; ++k)
+            for (int j = 0; j < n[1]; ++j)
+                for (int i = 0; i < n[0]; ++i) {
+                    const long l        = i + (long)n[0] * (j + (long)n[1] * k);
+                    const double kk[3]  = {s->k[0][i], s->k[1][j], s->k[2][k]};
+                    const double Dr     = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2];
+                    const double factor = Dr != 0.0 ? 1.0 / Dr : 0.0;
+                    t[l] = (rh[l] / (double)N) * cplx(0.0, -(kk[c] * factor));
+                }
+        for (int a = 0; a < 3; ++a) dft_axis(t, n, a, +1);
+        E_g[c].resize(N);
+        for (long l = 0; l < N; ++l) E_g[c][l] = t[l].real();
+    }
 }
 }  // namespace
 
@@ -222,40 +327,59 @@ int ipplb_poisson_create(ipplb_ctx*, const ipplb_mesh* mesh, ipplb_poisson** out
     return IPPLB_OK;
 }
 int ipplb_poisson_create_dist(ipplb_ctx* ctx, const ipplb_layout* layout, const double origin[3], const double h[3], ipplb_poisson** out) {
-    if (ipplb_layout_nranks(layout) != 1) return fail(IPPLB_ERR_ARG, "mock poisson: single rank only");
-    ipplb_mesh m;
-    ipplb_layout_mesh(layout, 0, origin, h, &m);
-    return ipplb_poisson_create(ctx, &m, out);
+    const int nr = ipplb_layout_nranks(layout);
+    ipplb_mesh whole{};
+    for (int d = 0; d < 3; ++d) {
+        whole.ng[d] = whole.nl[d] = layout->L.ng[d];
+        whole.origin[d] = origin[d];
+        whole.h[d]      = h[d];
+    }
+    whole.nghost = layout->L.nghost;
+    const int rc = ipplb_poisson_create(ctx, &whole, out);
+    if (rc || nr == 1) return rc;
+    if (nr != ctx->nranks) return fail(IPPLB_ERR_ARG, "mock poisson: layout rank count != communicator size");
+    (*out)->ctx  = ctx;
+    (*out)->dist = true;
+    ipplb_layout_mesh(layout, ctx->rank, origin, h, &(*out)->mine);
+    return IPPLB_OK;
 }
 int ipplb_poisson_solve(ipplb_poisson* s, double* rho, double* ef) {
-    const ipplb_mesh& m = s->m;
-    const int n[3] = {m.ng[0], m.ng[1], m.ng[2]}, g = m.nghost;
-    const long ex = n[0] + 2 * g, ey = n[1] + 2 * g, N = (long)n[0] * n[1] * n[2];
-    std::vector<cplx> rh(N);
-    for (int k = 0; k < n[2]; ++k)
-        for (int j = 0; j < n[1]; ++j)
-            for (int i = 0; i < n[0]; ++i) rh[i + (long)n[0] * (j + (long)n[1] * k)] = rho[(i + g) + ex * ((j + g) + ey * (k + g))];
-    for (int a = 0; a < 3; ++a) dft_axis(rh, n, a, -1);
-    for (int c = 0; c < 3; ++c) {
-        std::vector<cplx> t(N);
-        for (int k = 0; k < n[2]; ++k)
-            for (int j = 0; j < n[1]; ++j)
-                for (int i = 0; i < n[0]; ++i) {
-                    const long l    = i + (long)n[0] * (j + (long)n[1] * k);
-                    const double kk[3] = {s->k[0][i], s->k[1][j], s->k[2][k]};
-                    const double Dr = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2];
-                    const double factor = Dr != 0.0 ? 1.0 / Dr : 0.0;
-                    t[l] = (rh[l] / (double)N) * cplx(0.0, -(kk[c] * factor));
-                }
-        for (int a = 0; a < 3; ++a) dft_axis(t, n, a, +1);
-        for (int k = 0; k < n[2]; ++k)
-            for (int j = 0; j < n[1]; ++j)
-                for (int i = 0; i < n[0]; ++i) {
-                    const long cell = (i + g) + ex * ((j + g) + ey * (k + g));
-                    ef[3 * cell + c] = t[i + (long)n[0] * (j + (long)n[1] * k)].real();
-                    if (c == 2) rho[cell] = ef[3 * cell + c];   // the inverse lands in rho's storage (:153)
-                }
+    const ipplb_mesh& w = s->m;
+    const ipplb_mesh& m = s->dist ? s->mine : s->m;
+    const int g = m.nghost;
+    const long ex = m.nl[0] + 2 * g, ey = m.nl[1] + 2 * g, N = (long)w.ng[0] * w.ng[1] * w.ng[2];
+    // my interior, x fastest
+    std::vector<double> mine((size_t)m.nl[0] * m.nl[1] * m.nl[2]);
+    for (int k = 0; k < m.nl[2]; ++k)
+        for (int j = 0; j < m.nl[1]; ++j)
+            for (int i = 0; i < m.nl[0]; ++i) mine[i + (long)m.nl[0] * (j + (long)m.nl[1] * k)] = rho[(i + g) + ex * ((j + g) + ey * (k + g))];
+    std::vector<double> rho_g(N);
+    if (s->dist) {   // replicated solve: every rank assembles the whole rho
+        ipplb_ctx* c = s->ctx;
+        const auto all = allgather(c, mine.data(), sizeof(double) * mine.size());
+        for (int r = 0; r < c->nranks; ++r) {
+            const int* b = &c->boxes[r * 6];
+            const int bx = box_len(c, r, 0), by = box_len(c, r, 1), bz = box_len(c, r, 2);
+            const double* src = (const double*)all[r].data();
+            for (int k = 0; k < bz; ++k)
+                for (int j = 0; j < by; ++j)
+                    for (int i = 0; i < bx; ++i)
+                        rho_g[(i + b[0]) + (long)w.ng[0] * ((j + b[1]) + (long)w.ng[1] * (k + b[2]))] = src[i + (long)bx * (j + (long)by * k)];
+        }
+    } else {
+        rho_g = mine;
     }
+    std::vector<double> E_g[3];
+    solve_global(s, rho_g, E_g);
+    for (int c = 0; c < 3; ++c)
+        for (int k = 0; k < m.nl[2]; ++k)
+            for (int j = 0; j < m.nl[1]; ++j)
+                for (int i = 0; i < m.nl[0]; ++i) {
+                    const long cell = (i + g) + ex * ((j + g) + ey * (k + g));
+                    const long gl   = (i + m.first[0]) + (long)w.ng[0] * ((j + m.first[1]) + (long)w.ng[1] * (k + m.first[2]));
+                    ef[3 * cell + c] = E_g[c][gl];
+                    if (c == 2) rho[cell] = E_g[c][gl];   // the inverse lands in rho's storage (:153)
+                }
     return IPPLB_OK;
 }
 int ipplb_poisson_destroy(ipplb_poisson* s) {
@@ -396,7 +520,19 @@ int ipplb_sample_normal(ipplb_ctx*, const double mu[3], const double sd[3], uint
     }
     return IPPLB_OK;
 }
-int ipplb_field_fill_pdf(ipplb_ctx*, const ipplb_mesh*, const ipplb_dist*, double*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+int ipplb_field_fill_pdf(ipplb_ctx*, const ipplb_mesh* m, const ipplb_dist* D, double* f) {
+    const int g = m->nghost;
+    const long ex = m->nl[0] + 2 * g, ey = m->nl[1] + 2 * g;
+    for (int k = 0; k < m->nl[2]; ++k)
+        for (int j = 0; j < m->nl[1]; ++j)
+            for (int i = 0; i < m->nl[0]; ++i) {
+                const int c[3] = {i, j, k};
+                double total = 1.0;
+                for (int d = 0; d < 3; ++d) total *= m_pdf(D, d, ((double)(c[d] + m->first[d]) + 0.5) * m->h[d] + m->origin[d]);
+                f[(i + g) + ex * ((j + g) + ey * (k + g))] = total;
+            }
+    return IPPLB_OK;
+}
 // the bucketed store behind the fused step, emulated: "buckets" are plain contiguous arrays, one step = the reference-order
 // sequence gather, kick(s), drift, periodic BC, scatter on the oracle (leapfrog only) -- enough to exercise the HOST logic that
 // drives ipplb_bins_* (the facade's lazy-fusion engine); the real store and kernel are CUDA only.
@@ -458,21 +594,170 @@ int ipplb_bins_kinetic(ipplb_ctx*, ipplb_bins*, const ipplb_particles* cur, doub
     return ipplb_particles_kinetic(nullptr, cur->n, cur->px, cur->py, cur->pz, out);
 }
 
-// ---- one rank: the communicator entry points ---------------------------------------------------------------------------------
-int ipplb_allreduce_sum_f64(ipplb_ctx*, double*) { return IPPLB_OK; }
-int ipplb_allreduce_sum_i64(ipplb_ctx*, long*) { return IPPLB_OK; }
-int ipplb_allreduce_max_f64(ipplb_ctx*, double*) { return IPPLB_OK; }
-int ipplb_update_plan(ipplb_ctx*, ipplb_particles* p, long* n_after, long*, long*) {
-    if (n_after) *n_after = p->n;
+// ---- the communicator entry points (one rank: trivial; several ranks: processes exchanging through IPPLB_MOCK_DIR) ----------------
+int ipplb_nccl_unique_id(char* id) {
+    std::memset(id, 0, IPPLB_NCCL_ID_BYTES);
     return IPPLB_OK;
 }
-int ipplb_update_commit(ipplb_ctx*, ipplb_particles*) { return IPPLB_OK; }
-int ipplb_ctx_set_layout(ipplb_ctx*, const ipplb_layout* l, const double*, const double*) {
-    return ipplb_layout_nranks(l) == 1 ? IPPLB_OK : fail(IPPLB_ERR_ARG, "mock: single rank only");
+int ipplb_comm_init(ipplb_ctx* c, int rank, int nranks, const char*) {
+    c->rank   = rank;
+    c->nranks = nranks;
+    if (nranks > 1) {
+        const char* d = std::getenv("IPPLB_MOCK_DIR");
+        if (!d) return fail(IPPLB_ERR_ARG, "mock: several ranks need IPPLB_MOCK_DIR (a directory shared by the rank processes)");
+        c->dir = d;
+    }
+    return IPPLB_OK;
 }
-int ipplb_comm_init(ipplb_ctx*, int, int nranks, const char*) { return nranks == 1 ? IPPLB_OK : fail(IPPLB_ERR_ARG, "mock: single rank only"); }
-int ipplb_nccl_unique_id(char*) { return fail(IPPLB_ERR_NCCL, "mock: single rank only"); }
-int ipplb_halo_exchange(ipplb_ctx*, double*, int, int) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
-int ipplb_orb_repartition(ipplb_ctx*, const ipplb_mesh*, int, const double*, int*, int*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+int ipplb_allreduce_sum_f64(ipplb_ctx* c, double* v) {
+    allreduce(c, v, [](double a, double b) { return a + b; });
+    return IPPLB_OK;
+}
+int ipplb_allreduce_sum_i64(ipplb_ctx* c, long* v) {
+    allreduce(c, v, [](long a, long b) { return a + b; });
+    return IPPLB_OK;
+}
+int ipplb_allreduce_max_f64(ipplb_ctx* c, double* v) {
+    allreduce(c, v, [](double a, double b) { return a > b ? a : b; });
+    return IPPLB_OK;
+}
+int ipplb_ctx_set_layout(ipplb_ctx* c, const ipplb_layout* l, const double origin[3], const double h[3]) {
+    if (ipplb_layout_nranks(l) != c->nranks) return fail(IPPLB_ERR_ARG, "mock set_layout: layout rank count != communicator size");
+    c->L           = l->L;
+    c->have_layout = true;
+    c->boxes.resize(6 * (size_t)c->nranks);
+    ipplb_layout_boxes(l, c->boxes.data());
+    c->regions.resize(6 * (size_t)c->nranks);
+    for (int d = 0; d < 3; ++d) { c->origin[d] = origin[d]; c->h[d] = h[d]; }
+    orc_regions(c->L.ng, c->nranks, c->boxes.data(), origin, h, c->regions.data());
+    return IPPLB_OK;
+}
+// BareField::accumulateHalo / fillHalo over ranks: every rank sees every rank's ghosted field, runs the oracle's all-ranks
+// exchange and keeps its own; then the in-rank periodic wrap of the dimensions it owns entirely (oracle.halo_full)
+int ipplb_halo_exchange(ipplb_ctx* c, double* field, int ncomp, int mode) {
+    if (!c->have_layout) return fail(IPPLB_ERR_ARG, "mock halo_exchange: no layout bound");
+    const int g = c->L.nghost, me = c->rank;
+    size_t cells = 1;
+    for (int d = 0; d < 3; ++d) cells *= (size_t)(box_len(c, me, d) + 2 * g);
+    auto all = allgather(c, field, sizeof(double) * cells * ncomp);
+    std::vector<double*> f(c->nranks);
+    for (int r = 0; r < c->nranks; ++r) f[r] = (double*)all[r].data();
+    if (c->nranks > 1) orc_halo_exchange(c->L.ng, c->nranks, c->boxes.data(), g, c->L.periodic, f.data(), ncomp, mode);
+    if (c->L.periodic) {
+        int ext[3], serial[3];
+        for (int d = 0; d < 3; ++d) {
+            ext[d]    = box_len(c, me, d) + 2 * g;
+            serial[d] = box_len(c, me, d) == c->L.ng[d];
+        }
+        orc_halo_periodic(f[me], ext, ncomp, g, serial, mode);
+    }
+    std::memcpy(field, f[me], sizeof(double) * cells * ncomp);
+    return IPPLB_OK;
+}
+// ParticleSpatialLayout::update behind the facade's two-phase migrate (the BC has been applied by the caller): the plan locates
+// and exchanges the leavers' records, the commit removes the leavers with the reference's hole filling and appends the arrivals
+// in ascending source rank (oracle.update)
+int ipplb_update_plan(ipplb_ctx* c, ipplb_particles* p, long* n_after, long* sent, long* recv) {
+    if (n_after) *n_after = p->n;
+    if (c->nranks < 2) return IPPLB_OK;
+    if (!c->have_layout) return fail(IPPLB_ERR_ARG, "mock update_plan: no layout bound");
+    const long n = p->n;
+    c->dest.assign((size_t)n, c->rank);
+    orc_locate(c->nranks, c->regions.data(), c->rank, n, p->x, p->y, p->z, c->dest.data());
+    std::vector<double> out;   // records: dest, x, y, z, px, py, pz, q
+    for (long i = 0; i < n; ++i)
+        if (c->dest[i] != c->rank) {
+            const double rec[8] = {(double)c->dest[i], p->x[i], p->y[i], p->z[i], p->px ? p->px[i] : 0.0, p->py ? p->py[i] : 0.0,
+                                   p->pz ? p->pz[i] : 0.0, p->q ? p->q[i] : p->q_scalar};
+            out.insert(out.end(), rec, rec + 8);
+        }
+    const auto all = allgather(c, out.data(), sizeof(double) * out.size());
+    c->arrivals.clear();
+    for (int r = 0; r < c->nranks; ++r) {
+        const double* rec = (const double*)all[r].data();
+        const size_t cnt  = all[r].size() / (8 * sizeof(double));
+        long from_r = 0;
+        for (size_t k = 0; k < cnt; ++k)
+            if ((int)rec[8 * k] == c->rank && r != c->rank) {
+                c->arrivals.insert(c->arrivals.end(), rec + 8 * k + 1, rec + 8 * k + 8);
+                ++from_r;
+            }
+        if (recv) recv[r] = from_r;
+    }
+    if (sent)
+        for (int r = 0; r < c->nranks; ++r) {
+            sent[r] = 0;
+            for (long i = 0; i < n; ++i) sent[r] += c->dest[i] == r && r != c->rank;
+        }
+    const long nleave = (long)(out.size() / 8), narrive = (long)(c->arrivals.size() / 7);
+    c->plan_n = n;
+    if (n_after) *n_after = n - nleave + narrive;
+    long too_small = (n - nleave + narrive) > p->capacity ? 1 : 0;   // the outcome is collective, like the product's
+    allreduce(c, &too_small, [](long a, long b) { return a + b; });
+    return too_small ? fail(IPPLB_ERR_CAPACITY, "mock update_plan: %ld rank(s) cannot hold their particles after the migration", too_small) : IPPLB_OK;
+}
+int ipplb_update_commit(ipplb_ctx* c, ipplb_particles* p) {
+    if (c->nranks < 2) return IPPLB_OK;
+    if (c->plan_n != p->n) return fail(IPPLB_ERR_ARG, "mock update_commit: call ipplb_update_plan on the same particles first");
+    const long n = p->n;
+    long nd = 0;
+    for (long i = 0; i < n; ++i) nd += c->dest[i] != c->rank;
+    const long keep = n - nd, narrive = (long)(c->arrivals.size() / 7);
+    long too_small = keep + narrive > p->capacity ? 1 : 0;
+    allreduce(c, &too_small, [](long a, long b) { return a + b; });
+    if (too_small) return fail(IPPLB_ERR_CAPACITY, "mock update_commit: capacity");
+    double* arr[7] = {p->x, p->y, p->z, p->px, p->py, p->pz, p->q};
+    // ParticleBase::internalDestroy: the i-th hole among the first n - nd slots takes the i-th survivor of the tail
+    std::vector<long> holes, fill;
+    for (long i = 0; i < keep; ++i)
+        if (c->dest[i] != c->rank) holes.push_back(i);
+    for (long i = keep; i < n; ++i)
+        if (c->dest[i] == c->rank) fill.push_back(i);
+    for (size_t k = 0; k < holes.size(); ++k)
+        for (double* a : arr)
+            if (a) a[holes[k]] = a[fill[k]];
+    for (long k = 0; k < narrive; ++k)
+        for (int a = 0; a < 7; ++a)
+            if (arr[a]) arr[a][keep + k] = c->arrivals[7 * k + a];
+    p->n      = keep + narrive;
+    c->plan_n = -1;
+    return IPPLB_OK;
+}
+int ipplb_update(ipplb_ctx* c, ipplb_particles* p, long* sent, long* recv) {
+    const int rc = ipplb_update_plan(c, p, nullptr, sent, recv);
+    return rc ? rc : ipplb_update_commit(c, p);
+}
+// OrthogonalRecursiveBisection::binaryRepartition: the product's host state machine (ippl_b200/csrc/orb.cpp) fed with plane sums
+// of every rank's interior, summed over the ranks
+int ipplb_orb_repartition(ipplb_ctx* c, const ipplb_mesh* mesh, int nranks, const double* w, int* boxes_out, int* ok) {
+    ipplb_orb* o = nullptr;
+    int rc = ipplb_orb_begin(&o, mesh->ng, nranks);
+    if (rc) return rc;
+    const int g = mesh->nghost;
+    const long ex = mesh->nl[0] + 2 * g, ey = mesh->nl[1] + 2 * g;
+    for (;;) {
+        int lo[3], hi[3], axis, pending;
+        if ((rc = ipplb_orb_next(o, lo, hi, &axis, &pending)) || !pending) break;
+        std::vector<double> red((size_t)(hi[axis] - lo[axis] + 1), 0.0);
+        for (int k = 0; k < mesh->nl[2]; ++k)
+            for (int j = 0; j < mesh->nl[1]; ++j)
+                for (int i = 0; i < mesh->nl[0]; ++i) {
+                    const int gi[3] = {i + mesh->first[0], j + mesh->first[1], k + mesh->first[2]};
+                    bool in = true;
+                    for (int d = 0; d < 3; ++d) in = in && gi[d] >= lo[d] && gi[d] <= hi[d];
+                    if (in) red[gi[axis] - lo[axis]] += w[(i + g) + ex * ((j + g) + ey * (k + g))];
+                }
+        const auto all = allgather(c, red.data(), sizeof(double) * red.size());
+        std::vector<double> tot(red.size(), 0.0);
+        for (int r = 0; r < c->nranks; ++r)
+            for (size_t t = 0; t < red.size(); ++t) tot[t] += ((const double*)all[r].data())[t];
+        if ((rc = ipplb_orb_cut(o, tot.data(), (int)tot.size()))) break;
+    }
+    if (rc) {
+        ipplb_orb_destroy(o);
+        return rc;
+    }
+    return ipplb_orb_finish(o, boxes_out, ok);
+}
 
 }  // extern "C"

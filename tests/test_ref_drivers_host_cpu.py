@@ -137,3 +137,49 @@ def test_fusion_engine_materialises_correctly_when_the_driver_peeks(drivers):
     out = subprocess.run([os.path.join(drivers, "demo_fusion_check_host")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "fusion_check: ok" in out.stdout, out.stdout + out.stderr
     assert "8 fused steps, 6 materialisations" in out.stdout
+
+
+def _run_ranks(drivers, tmp_path, exe, tag, world, grid, np_, nt, csv, threads=4):
+    """`world` processes of one driver on the mock: ippl::initialize reads RANK / WORLD_SIZE like under torchrun; the mock's
+    communicator is a directory (IPPLB_MOCK_DIR)"""
+    d = tmp_path / tag
+    (d / "data").mkdir(parents=True)
+    (d / "comm").mkdir()
+    cmd = [os.path.join(drivers, exe), str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
+           "--info", "0"]
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), IPPLB_NCCL_ID_FILE=str(d / "comm" / "id"),
+                   IPPLB_MOCK_DIR=str(d / "comm"), OMP_NUM_THREADS=str(threads))
+        procs.append(subprocess.Popen(cmd, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        out, _ = p.communicate(timeout=900)
+        logs.append(out)
+    assert all(p.returncode == 0 for p in procs), "\n".join(l[-1500:] for l in logs)
+    return np.loadtxt(d / "data" / csv, skiprows=1), logs[0]
+
+
+def test_unchanged_landau_driver_on_two_ranks_reproduces_the_known_answer(drivers, tmp_path):
+    """The reference generated its known-answer file with 2 ranks (demos/alpine/validation/CMakeLists.txt): the unchanged driver
+    on 2 ranks of the mock -- its own LoadBalancer doing the first ORB repartition, the facade's two-phase migrate, halo
+    exchanges, the replicated solve, the reductions of the dumps and of IpplTimings -- stays within the reference's tolerance."""
+    golden = np.loadtxt(os.path.join(ROOT, "tests", "golden", "FieldLandau_valid_result.csv"), skiprows=1)
+    got, log = _run_ranks(drivers, tmp_path, "ref_LandauDamping_host", "landau2", 2, 16, 10000000, 25, "FieldLandau_2_manager.csv", threads=8)
+    assert got.shape == golden.shape
+    assert np.max(np.abs(got[:, 1:] - golden[:, 1:])) <= 0.4
+    assert "Timing results for 2 rank(s)" in log and "loadBalance" in log and "Could not repartition" not in log
+
+
+def test_unchanged_penning_driver_on_four_ranks_equals_the_restated_one(drivers, tmp_path):
+    """PenningTrap on 4 ranks: the blob makes the ORB repartition non-trivial (first repartition on the analytic density, one
+    more during the run).  The reference's unchanged driver (its LoadBalancer.hpp, ORB through the compat layer) and the
+    repo's restated driver write the same CSV."""
+    kw = dict(world=4, grid=16, np_=400000, nt=6, csv="ParticleField_4_manager.csv")
+    ref, log = _run_ranks(drivers, tmp_path, "ref_PenningTrap_host", "pt_ref", **kw)
+    own, _ = _run_ranks(drivers, tmp_path, "demo_PenningTrap_host", "pt_own", **kw)
+    cols = [0, 1, 2, 3, 5, 6, 7]
+    assert ref.shape == own.shape == (7, 8)
+    assert np.max(np.abs(ref[:, cols] - own[:, cols]) / np.maximum(np.abs(own[:, cols]), 1e-300)) <= 1e-12
+    assert abs(ref[0, 2] / (1.5 * 400000) - 1.0) <= 1e-2
+    assert "Could not repartition" not in log
