@@ -35,6 +35,7 @@
 #include <functional>
 #include <iomanip>
 #include <iostream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -748,6 +749,9 @@ namespace detail {
         virtual double* component_ptr(int c) const    = 0;
         virtual std::size_t capacity() const          = 0;
         virtual void reserve_storage(std::size_t n)   = 0;
+        // a scalar attribute whose every element holds one known value (attrib = scalar): what the fused step needs of q
+        virtual bool uniform(double* /*value*/) const { return false; }
+        virtual void restore_uniform(double /*value*/) {}
         void set_name(const std::string& n) { name_ = n; }
         const std::string& get_name() const { return name_; }
         void set_engine(class FusionEngine* e) { engine_ = e; }
@@ -769,7 +773,8 @@ namespace detail {
     // (ipplb_bins_compact) and the recorded operations run one by one through the ordinary kernels, in order, so the
     // driver always sees what the unfused sequence would have produced (per particle bit for bit; rho to summation
     // order).  One thing cannot be reproduced: E_p AFTER a fused step (the gather it belongs to was consumed inside the
-    // kernel); reading it then throws.  One rank only for now: several ranks take the unfused path.
+    // kernel); reading it then throws.  Several ranks: the step also writes the leavers out and ipplb_bins_migrate exchanges them
+    // (what the restated drivers' --fused path does, demos/Alpine.h).
     class FusionEngine {
     public:
         enum Kind { GATHER, KICK, DRIFT, BCS };
@@ -780,9 +785,10 @@ namespace detail {
         };
         ParticleAttribBase* R = nullptr;   // positions
         const std::size_t* local_num = nullptr;
+        std::function<void(std::size_t)> set_local_num;   // several ranks: the container's count follows the migration
         bool busy = false;                 // inside materialise(): every hook is a plain call
 
-        bool active() const { return b200::fusion_enabled() && !busy && R != nullptr && Comm && Comm->size() == 1; }
+        bool active() const { return b200::fusion_enabled() && !busy && R != nullptr && Comm; }
         bool pending() const { return !chain_.empty(); }
         ~FusionEngine() { release(); }
 
@@ -814,24 +820,33 @@ namespace detail {
             return true;
         }
         // -- the fused step: true when the record was the whole pattern and has been executed (rho's halo is NOT accumulated) ------
-        bool fused_scatter(double q, double* rho, const ipplb_mesh& mesh) {
+        // `region` (min[3], max[3] of this rank, RegionLayout) is needed on several ranks only.  Collective there: every rank
+        // runs the same driver code, so every rank arrives here with the same record; the one rank-local reason not to fuse
+        // (the store has to be rebuilt for a new mesh / more particles while the particles are inside it) is agreed on first.
+        bool fused_scatter(double q, double* rho, const ipplb_mesh& mesh, const double* region) {
             if (chain_.size() < 4 || chain_.back().kind != BCS) return false;
             const int nk = kicks();
             const double c = chain_[1].coef, dt = chain_[chain_.size() - 2].coef;
             if (nk < 1 || (nk == 2 && chain_[2].coef != c) || c != -(0.5 * dt)) return false;   // not the leapfrog coefficients
-            ipplb_ctx* ctx = b200::ctx();
-            const long n   = (long)*local_num;
-            if (bins_ && (n + n / 8 > cap_ || std::memcmp(&mesh, &bins_mesh_, sizeof(mesh)) != 0)) {
-                if (in_bins_) return false;   // cannot re-bucket from the store: let the caller materialise
-                release();
-            }
+            ipplb_ctx* ctx   = b200::ctx();
+            const long n     = (long)*local_num;
+            const bool multi = Comm->size() > 1;
+            const bool stale = bins_ && (n + n / 8 > cap_ || std::memcmp(&mesh, &bins_mesh_, sizeof(mesh)) != 0);
+            double veto      = stale && in_bins_ ? 1.0 : 0.0;   // cannot re-bucket from the store: the caller materialises
+            Comm->allreduce(veto, 1, std::greater<double>());
+            if (veto != 0.0) return false;
+            if (stale) release();
             if (!bins_) {
-                cap_ = n + n / 4 + 65536;
+                cap_ = (multi ? 2 * n : n + n / 4) + 65536;   // migration head-room on several ranks
                 b200::check(ipplb_bins_create(ctx, &mesh, cap_, &bins_), "fusion: bins_create");
                 bins_mesh_ = mesh;
                 for (auto& p : spare_) p = b200::device_alloc<double>((std::size_t)cap_);
                 cur_ = ipplb_particles{spare_[0], spare_[1], spare_[2], spare_[3], spare_[4], spare_[5], nullptr, q, 0, cap_};
                 nxt_ = ipplb_particles{spare_[6], spare_[7], spare_[8], spare_[9], spare_[10], spare_[11], nullptr, q, 0, cap_};
+                if (multi) {   // leavers of a step, as records for ipplb_bins_migrate
+                    exit_cap_ = (int)std::max<long>(n / 4, 1 << 16);
+                    exit_buf_ = b200::device_alloc<double>(6 * (std::size_t)exit_cap_);
+                }
             }
             if (!in_bins_) {   // bucket the contiguous attribute arrays once; the particles then live in the store
                 ipplb_particles in{R->component_ptr(0),    R->component_ptr(1),    R->component_ptr(2), vel_->component_ptr(0),
@@ -847,8 +862,19 @@ namespace detail {
             push.do_kick2 = nk == 2;
             push.do_kick1 = push.do_drift = push.do_bc = 1;
             e_fill_halo_();
-            b200::check(ipplb_bins_step(ctx, bins_, &push, &cur_, &nxt_, e_field_, rho, nullptr, 0, nullptr, nullptr), "fusion: bins_step");
+            b200::check(ipplb_bins_step(ctx, bins_, &push, &cur_, &nxt_, e_field_, rho, exit_buf_, exit_cap_, multi ? region : nullptr,
+                                        multi ? region + 3 : nullptr),
+                        "fusion: bins_step");
             std::swap(cur_, nxt_);
+            if (multi) {   // ParticleSpatialLayout::update for the bucketed store: exchange, append, deposit the arrivals
+                b200::check(ipplb_bins_migrate(ctx, bins_, &cur_, exit_buf_, exit_cap_, rho, nullptr, nullptr), "fusion: bins_migrate");
+                busy = true;   // the attribute arrays only follow the count (they are stale while the particles are in the store)
+                struct Unbusy {
+                    bool& b;
+                    ~Unbusy() { b = false; }
+                } guard{busy};
+                set_local_num((std::size_t)cur_.n);
+            }
             chain_.clear();
             e_consumed_ = true;
             ++b200::fusion_stats().fused_steps;
@@ -901,7 +927,10 @@ namespace detail {
                 if (p) cudaFree(p);
                 p = nullptr;
             }
-            in_bins_ = false;
+            if (exit_buf_) cudaFree(exit_buf_);
+            exit_buf_ = nullptr;
+            exit_cap_ = 0;
+            in_bins_  = false;
         }
         std::vector<Op> chain_;
         ParticleAttribBase *e_attr_ = nullptr, *vel_ = nullptr;   // gather target, velocity attribute
@@ -914,6 +943,8 @@ namespace detail {
         double* spare_[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         long cap_     = 0;
         bool in_bins_ = false;
+        double* exit_buf_ = nullptr;   // several ranks
+        int exit_cap_     = 0;
     };
     // a * attrib  and  attrib +/- a * attrib : the expressions the alpine pushes are made of
     template <class A>
@@ -979,8 +1010,15 @@ public:
         count_ = need;
     }
     void setCount(std::size_t n) override {
-        touch();
+        // from the fusion engine (the count follows a migration inside the bucketed store): a uniform attribute (q = Q / N)
+        // stays uniform, its new slots are filled.  From anywhere else the storage is being rewritten by the caller.
+        const bool from_engine = engine_ && engine_->busy;
+        if (!from_engine) touch();
         reserve(n);
+        if constexpr (ncomp == 1) {
+            if (from_engine && uniform_valid_ && n > count_)
+                b200::check(ipplb_field_fill(b200::ctx(), d_[0] + count_, (long)(n - count_), uniform_value_), "ParticleAttrib::setCount");
+        }
         count_ = n;
     }
     // capacity for at least n particles, contents kept
@@ -1001,6 +1039,17 @@ public:
     double* component_ptr(int c) const override { return d_[c]; }
     std::size_t capacity() const override { return capacity_; }
     void reserve_storage(std::size_t n) override { reserve(n); }
+    bool uniform(double* value) const override {
+        if (ncomp != 1 || !uniform_valid_) return false;
+        *value = uniform_value_;
+        return true;
+    }
+    void restore_uniform(double value) override {
+        if (ncomp == 1) {
+            uniform_valid_ = true;
+            uniform_value_ = value;
+        }
+    }
     // getView(): the reference returns a Kokkos::View<T*> for driver-side kernels; here a view(i)[d] / view(i) proxy over
     // the SoA component arrays, usable inside device lambdas (include/ippl/KokkosShim.cuh)
     using view_type = detail::AttribView<ncomp>;
@@ -1103,10 +1152,22 @@ public:
     void scatter(Field& f, const ParticleAttrib<Vector<PT, 3>>& pp) const {
         static_assert(ncomp == 1, "scatter deposits a scalar attribute");
         if (engine_ && engine_->active() && engine_->pending() && uniform_valid_
-            && static_cast<const detail::ParticleAttribBase*>(&pp) == engine_->R && Field::ncomp == 1
-            && engine_->fused_scatter(uniform_value_, f.data(), f.b200_mesh())) {
-            f.accumulateHalo();   // [gather, kick(s), drift, BC] + this scatter ran as ONE fused kernel
-            return;
+            && static_cast<const detail::ParticleAttribBase*>(&pp) == engine_->R && Field::ncomp == 1) {
+            double region[6] = {0, 0, 0, 0, 0, 0};
+            if (Comm->size() > 1) {   // this rank's physical region (RegionLayout), for the ownership test inside the kernel
+                double o[3], h[3];
+                for (int d = 0; d < 3; ++d) {
+                    o[d] = f.get_mesh().getOrigin()[d];
+                    h[d] = f.get_mesh().getMeshSpacing()[d];
+                }
+                std::vector<double> all(6 * (std::size_t)Comm->size());
+                b200::check(ipplb_layout_regions(f.getLayout().handle(), o, h, all.data()), "ParticleAttrib::scatter (regions)");
+                std::copy_n(all.begin() + 6 * Comm->rank(), 6, region);
+            }
+            if (engine_->fused_scatter(uniform_value_, f.data(), f.b200_mesh(), region)) {
+                f.accumulateHalo();   // [gather, kick(s), drift, update] + this scatter ran as ONE fused step
+                return;
+            }
         }
         sync();
         b200::check(ipplb_scatter_cic(b200::ctx(), &f.b200_mesh(), 0, (long)pp.getParticleCount(), pp.component(0),
@@ -1245,8 +1306,9 @@ public:
     particle_position_type R;
     ParticleBase() {
         attributes_.push_back(&R);
-        engine_.R         = &R;
-        engine_.local_num = &localNum_;
+        engine_.R             = &R;
+        engine_.local_num     = &localNum_;
+        engine_.set_local_num = [this](std::size_t n) { setLocalNum(n); };
         R.set_engine(&engine_);
     }
     explicit ParticleBase(PLayout& l) : ParticleBase() { initialize(l); }
@@ -1297,6 +1359,17 @@ public:
             if (sca) b.capacity = std::min<long>(b.capacity, (long)sca->capacity());
             return b;
         };
+        // lazy fusion wants to know whether the charge is still ONE value after the exchange: it is when every rank's was
+        // uniform with the same value (two small reductions, only with fusion on)
+        double uq = 0.0;
+        bool uniform_everywhere = false;
+        if (b200::fusion_enabled() && sca) {
+            const bool mine = sca->uniform(&uq);
+            double hi = mine ? uq : std::numeric_limits<double>::max(), neg_lo = mine ? -uq : std::numeric_limits<double>::max();
+            Comm->allreduce(hi, 1, std::greater<double>());
+            Comm->allreduce(neg_lo, 1, std::greater<double>());
+            uniform_everywhere = mine && hi == uq && -neg_lo == uq;
+        }
         ipplb_particles b = bundle();
         long n_after      = b.n;
         const int rc      = ipplb_update_plan(b200::ctx(), &b, &n_after, nullptr, nullptr);
@@ -1308,6 +1381,7 @@ public:
         }
         b200::check(ipplb_update_commit(b200::ctx(), &b), "ParticleBase::update (commit)");
         setLocalNum((std::size_t)b.n);
+        if (uniform_everywhere) sca->restore_uniform(uq);
     }
 
 protected:

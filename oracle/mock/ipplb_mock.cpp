@@ -76,6 +76,7 @@ struct ipplb_poisson {
 struct ipplb_bins {
     ipplb_mesh m;
     long capacity = 0;
+    long nexit    = 0;   // leavers of the last step, as 6-double records at the start of exit_buf
 };
 
 namespace {
@@ -560,27 +561,43 @@ int ipplb_bins_build(ipplb_ctx*, ipplb_bins* b, const ipplb_particles* in, ipplb
     return IPPLB_OK;
 }
 int ipplb_bins_step(ipplb_ctx*, ipplb_bins* b, const ipplb_push* push, const ipplb_particles* cur, ipplb_particles* nxt, const double* efield,
-                    double* rho, double* exit_buf, int, const double*, const double*) {
-    if (push->kind != IPPLB_PUSH_LEAPFROG || exit_buf) return fail(IPPLB_ERR_ARG, "mock bins_step: single-rank leapfrog only");
+                    double* rho, double* exit_buf, int exit_cap, const double* rmin, const double* rmax) {
+    if (push->kind != IPPLB_PUSH_LEAPFROG) return fail(IPPLB_ERR_ARG, "mock bins_step: leapfrog only");
     const long n = cur->n;
     const orc_mesh m = to_orc(&b->m);
-    copy6(cur, nxt, n);
-    std::vector<double> e0(n), e1(n), e2(n);
+    std::vector<double> w[6], e0(n), e1(n), e2(n);
+    const double* src[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
+    for (int a = 0; a < 6; ++a) w[a].assign(src[a], src[a] + n);
     double* E[3] = {e0.data(), e1.data(), e2.data()};
-    orc_gather_cic(&m, n, nxt->x, nxt->y, nxt->z, efield, 3, E, 0, 1);
-    double* P[3] = {nxt->px, nxt->py, nxt->pz};
-    double* R[3] = {nxt->x, nxt->y, nxt->z};
+    orc_gather_cic(&m, n, w[0].data(), w[1].data(), w[2].data(), efield, 3, E, 0, 1);
     const double c = 0.5 * push->dt;
     for (int k = 0; k < (push->do_kick2 ? 1 : 0) + (push->do_kick1 ? 1 : 0); ++k)
         for (int d = 0; d < 3; ++d)
-            for (long i = 0; i < n; ++i) P[d][i] = P[d][i] - c * E[d][i];
+            for (long i = 0; i < n; ++i) w[3 + d][i] = w[3 + d][i] - c * E[d][i];
     for (int d = 0; d < 3; ++d) {
         if (push->do_drift)
-            for (long i = 0; i < n; ++i) R[d][i] = R[d][i] + push->dt * P[d][i];
-        if (push->do_bc) orc_periodic_bc(n, R[d], 0 * b->m.h[d] + b->m.origin[d], b->m.ng[d] * b->m.h[d] + b->m.origin[d], 1);
+            for (long i = 0; i < n; ++i) w[d][i] = w[d][i] + push->dt * w[3 + d][i];
+        if (push->do_bc) orc_periodic_bc(n, w[d].data(), 0 * b->m.h[d] + b->m.origin[d], b->m.ng[d] * b->m.h[d] + b->m.origin[d], 1);
     }
-    orc_scatter_cic(&m, 0, n, nxt->x, nxt->y, nxt->z, nullptr, cur->q_scalar, nullptr, rho, 1);
-    nxt->n = n;
+    // ownership (positionInRegion: min < x <= max): stayers go to nxt and are deposited, leavers become records in exit_buf
+    double* dst[6] = {nxt->x, nxt->y, nxt->z, nxt->px, nxt->py, nxt->pz};
+    long ns = 0;
+    b->nexit = 0;
+    for (long i = 0; i < n; ++i) {
+        bool mine = true;
+        if (rmin && rmax)
+            for (int d = 0; d < 3; ++d) mine = mine && w[d][i] > rmin[d] && w[d][i] <= rmax[d];
+        if (mine) {
+            for (int a = 0; a < 6; ++a) dst[a][ns] = w[a][i];
+            ++ns;
+        } else {
+            if (!exit_buf || b->nexit >= exit_cap) return fail(IPPLB_ERR_CAPACITY, "mock bins_step: exit buffer too small");
+            for (int a = 0; a < 6; ++a) exit_buf[6 * b->nexit + a] = w[a][i];
+            ++b->nexit;
+        }
+    }
+    orc_scatter_cic(&m, 0, ns, nxt->x, nxt->y, nxt->z, nullptr, cur->q_scalar, nullptr, rho, 1);
+    nxt->n = ns;
     return IPPLB_OK;
 }
 int ipplb_bins_compact(ipplb_ctx*, ipplb_bins*, const ipplb_particles* cur, ipplb_particles* out) {
@@ -589,7 +606,7 @@ int ipplb_bins_compact(ipplb_ctx*, ipplb_bins*, const ipplb_particles* cur, ippl
     out->n = cur->n;
     return IPPLB_OK;
 }
-int ipplb_bins_migrate(ipplb_ctx*, ipplb_bins*, ipplb_particles*, const double*, int, double*, long*, long*) { return fail(IPPLB_ERR_ARG, "mock: single rank only"); }
+int ipplb_bins_migrate(ipplb_ctx* c, ipplb_bins* b, ipplb_particles* cur, const double* exit_buf, int, double* rho, long*, long*);   // below (needs the transport)
 int ipplb_bins_kinetic(ipplb_ctx*, ipplb_bins*, const ipplb_particles* cur, double* out) {
     return ipplb_particles_kinetic(nullptr, cur->n, cur->px, cur->py, cur->pz, out);
 }
@@ -726,6 +743,37 @@ int ipplb_update_commit(ipplb_ctx* c, ipplb_particles* p) {
 int ipplb_update(ipplb_ctx* c, ipplb_particles* p, long* sent, long* recv) {
     const int rc = ipplb_update_plan(c, p, nullptr, sent, recv);
     return rc ? rc : ipplb_update_commit(c, p);
+}
+// ParticleSpatialLayout::update for the emulated bucketed store: destination of every leaver, exchange, append, deposit
+int ipplb_bins_migrate(ipplb_ctx* c, ipplb_bins* b, ipplb_particles* cur, const double* exit_buf, int, double* rho, long*, long*) {
+    if (c->nranks < 2) return IPPLB_OK;
+    const long ne = b->nexit;
+    std::vector<double> x(ne), y(ne), z(ne);
+    for (long i = 0; i < ne; ++i) { x[i] = exit_buf[6 * i]; y[i] = exit_buf[6 * i + 1]; z[i] = exit_buf[6 * i + 2]; }
+    std::vector<int> dest((size_t)ne, c->rank);
+    orc_locate(c->nranks, c->regions.data(), c->rank, ne, x.data(), y.data(), z.data(), dest.data());
+    std::vector<double> out;   // dest + 6 doubles
+    for (long i = 0; i < ne; ++i) {
+        out.push_back((double)dest[i]);
+        out.insert(out.end(), exit_buf + 6 * i, exit_buf + 6 * i + 6);
+    }
+    const auto all = allgather(c, out.data(), sizeof(double) * out.size());
+    double* dst[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
+    const long n0 = cur->n;
+    for (int r = 0; r < c->nranks; ++r) {
+        const double* rec = (const double*)all[r].data();
+        const size_t cnt  = all[r].size() / (7 * sizeof(double));
+        for (size_t k = 0; k < cnt; ++k)
+            if ((int)rec[7 * k] == c->rank) {
+                if (cur->n >= cur->capacity) return fail(IPPLB_ERR_CAPACITY, "mock bins_migrate: capacity");
+                for (int a = 0; a < 6; ++a) dst[a][cur->n] = rec[7 * k + 1 + a];
+                ++cur->n;
+            }
+    }
+    const orc_mesh m = to_orc(&b->m);
+    if (rho && cur->n > n0) orc_scatter_cic(&m, n0, cur->n, cur->x, cur->y, cur->z, nullptr, cur->q_scalar, nullptr, rho, 1);
+    b->nexit = 0;
+    return IPPLB_OK;
 }
 // OrthogonalRecursiveBisection::binaryRepartition: the product's host state machine (ippl_b200/csrc/orb.cpp) fed with plane sums
 // of every rank's interior, summed over the ranks

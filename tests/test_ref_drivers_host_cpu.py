@@ -139,7 +139,7 @@ def test_fusion_engine_materialises_correctly_when_the_driver_peeks(drivers):
     assert "8 fused steps, 6 materialisations" in out.stdout
 
 
-def _run_ranks(drivers, tmp_path, exe, tag, world, grid, np_, nt, csv, threads=4):
+def _run_ranks(drivers, tmp_path, exe, tag, world, grid, np_, nt, csv, threads=4, fuse=None):
     """`world` processes of one driver on the mock: ippl::initialize reads RANK / WORLD_SIZE like under torchrun; the mock's
     communicator is a directory (IPPLB_MOCK_DIR)"""
     d = tmp_path / tag
@@ -151,6 +151,8 @@ def _run_ranks(drivers, tmp_path, exe, tag, world, grid, np_, nt, csv, threads=4
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), IPPLB_NCCL_ID_FILE=str(d / "comm" / "id"),
                    IPPLB_MOCK_DIR=str(d / "comm"), OMP_NUM_THREADS=str(threads))
+        if fuse is not None:
+            env["IPPL_B200_FUSE"] = str(fuse)
         procs.append(subprocess.Popen(cmd, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     for p in procs:
@@ -183,3 +185,19 @@ def test_unchanged_penning_driver_on_four_ranks_equals_the_restated_one(drivers,
     assert np.max(np.abs(ref[:, cols] - own[:, cols]) / np.maximum(np.abs(own[:, cols]), 1e-300)) <= 1e-12
     assert abs(ref[0, 2] / (1.5 * 400000) - 1.0) <= 1e-2
     assert "Could not repartition" not in log
+
+
+@pytest.mark.parametrize("app,csv,world,expect", [("LandauDamping", "FieldLandau_2_manager.csv", 2, "8 fused steps, 0 materialisations"),
+                                                   ("BumponTailInstability", "FieldBumponTail_4_manager.csv", 4, "fused steps")])
+def test_lazy_fusion_on_several_ranks(drivers, tmp_path, app, csv, world, expect):
+    """IPPL_B200_FUSE=1 on several ranks: the recorded update() includes the migration, so the fused step is followed by
+    ipplb_bins_migrate and the container's count follows; a mid-run ORB repartition (BumponTail on 4 ranks) materialises once
+    and fusion resumes (the charge is still one value on every rank).  Same CSV as the plain run."""
+    kw = dict(world=world, grid=16, np_=400000, nt=8, csv=csv)
+    plain, _ = _run_ranks(drivers, tmp_path, f"ref_{app}_host", "plain", fuse=0, **kw)
+    fused, log = _run_ranks(drivers, tmp_path, f"ref_{app}_host", "fused", fuse=1, **kw)
+    assert expect in log, log[-600:]
+    import re
+    m = re.search(r"ippl_b200 fusion: (\d+) fused steps, (\d+) materialisations", log)
+    assert m and int(m.group(1)) >= 6 and int(m.group(2)) <= 2, log[-600:]
+    assert np.max(np.abs(plain - fused) / np.maximum(np.abs(plain), 1e-300)) <= 1e-12
