@@ -90,3 +90,26 @@ def test_reference_landau_driver_on_the_fused_step(tmp_path):
 def test_fusion_engine_with_peeks_on_gpu():
     out = subprocess.run([_exe("fusion_check")], capture_output=True, text=True, timeout=150)
     assert out.returncode == 0 and "fusion_check: ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_reference_landau_driver_on_two_gpus_plain_and_fused(tmp_path):
+    """The unchanged driver on 2 GPUs (torchrun --no-python; the reference's own validation runs 2 ranks): its LoadBalancer / ORB,
+    the facade's two-phase migrate, NCCL halo exchanges; then the same with IPPL_B200_FUSE=1 (fused step + ipplb_bins_migrate)."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    golden = np.loadtxt(os.path.join(ROOT, "tests", "golden", "FieldLandau_valid_result.csv"), skiprows=1)
+    out = {}
+    for fuse in (0, 1):
+        d = tmp_path / f"two_{fuse}"
+        (d / "data").mkdir(parents=True)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", str(29560 + fuse), _exe("ref_LandauDamping"), "16", "16", "16", "10000000", "25", "FFT", "0.01", "LeapFrog",
+               "--overallocate", "2.0", "--info", "0"]
+        res = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=300, env=dict(os.environ, IPPL_B200_FUSE=str(fuse)))
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        out[fuse] = (np.loadtxt(d / "data" / "FieldLandau_2_manager.csv", skiprows=1), res.stdout)
+    assert np.max(np.abs(out[0][0][:, 1:] - golden[:, 1:])) <= 0.4
+    assert "25 fused steps" in out[1][1], out[1][1][-600:]
+    assert np.max(np.abs(out[1][0][:, 1:] - out[0][0][:, 1:]) / np.abs(out[0][0][:, 1:])) <= 1e-9
