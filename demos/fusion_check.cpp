@@ -20,7 +20,7 @@ struct Result {
     long fused = 0, materialised = 0;
 };
 
-static Result run(bool fuse, int nsteps, int n, int grid) {
+static Result run(bool fuse, int nsteps, int n, int grid, double kick_factor = 0.5, bool peek = true) {
     ippl::b200::fusion_enabled() = fuse;
     const long fused0 = ippl::b200::fusion_stats().fused_steps, mat0 = ippl::b200::fusion_stats().materialised;
     Result out;
@@ -67,15 +67,15 @@ static Result run(bool fuse, int nsteps, int n, int grid) {
         gather(pc.E, E, pc.R);
         out.energy.push_back(energy());
         for (int it = 0; it < nsteps; ++it) {
-            pc.P = pc.P - 0.5 * dt * pc.E;
+            pc.P = pc.P - kick_factor * dt * pc.E;
             pc.R = pc.R + dt * pc.P;
-            if (it == 3) out.psum.push_back(pc.R.sum(1));   // peek between drift and update
+            if (peek && it == 3) out.psum.push_back(pc.R.sum(1));   // peek between drift and update
             pc.update();
             deposit();
-            if (it == 5) out.psum.push_back(pc.P.sum(2));   // peek right after a (fused) scatter: particles are in the store
+            if (peek && it == 5) out.psum.push_back(pc.P.sum(2));   // peek right after a (fused) scatter: particles are in the store
             gather(pc.E, E, pc.R);
-            pc.P = pc.P - 0.5 * dt * pc.E;
-            if (it % 4 == 1) out.psum.push_back(pc.P.sum(0));   // peek after the closing kick
+            pc.P = pc.P - kick_factor * dt * pc.E;
+            if (peek && it % 4 == 1) out.psum.push_back(pc.P.sum(0));   // peek after the closing kick
             out.energy.push_back(energy());
         }
         std::vector<ippl::Vector<double, 3>> r, p;
@@ -123,6 +123,16 @@ int main(int argc, char* argv[]) {
         // the final copy to the host.
         rc |= plain.fused != 0 || plain.materialised != 0 || fused.fused != 8 || fused.materialised != 6;
         rc |= !(ex <= 1e-9 && ep <= 1e-9 && ee <= 1e-9 && es <= 1e-9);
+        // a sequence that LOOKS like the leapfrog step but is not (kicks of 0.3 dt): recorded, refused at the scatter, replayed
+        // through the ordinary kernels -- nothing fuses, nothing changes
+        const Result odd_plain = run(false, 4, n, grid, 0.3, false), odd_fused = run(true, 4, n, grid, 0.3, false);
+        const double ox = worst(odd_plain.x, odd_fused.x, 1e-3), oe = worst(odd_plain.energy, odd_fused.energy, 1e-300);
+        std::cout << "fusion_check: non-leapfrog coefficients: " << odd_fused.fused << " fused steps, " << odd_fused.materialised
+                  << " materialisations; worst relative difference: x " << ox << ", field energy " << oe << std::endl;
+        rc |= odd_fused.fused != 0 || odd_fused.materialised != 5 || !(ox <= 1e-9 && oe <= 1e-9);
+        // and the clean case: no peeks, every step fused, one materialisation (the final copy to the host)
+        const Result clean = run(true, 6, n, grid, 0.5, false), clean_plain = run(false, 6, n, grid, 0.5, false);
+        rc |= clean.fused != 6 || clean.materialised != 1 || !(worst(clean_plain.x, clean.x, 1e-3) <= 1e-9);
         std::cout << (rc ? "fusion_check: FAILED" : "fusion_check: ok") << std::endl;
     } catch (const IpplException& ex) {
         std::cerr << "fusion_check: IPPL exception: " << ex.what() << std::endl;
