@@ -177,6 +177,105 @@ def run_reference(args):
     }))
 
 
+# ---- secondary measurements (after the headline numbers are final; each in its own process) -------------------------
+def _run_sub(cmd, env, limit_s):
+    """One secondary measurement as its own process group: a fault in it (or a hang: killed at the limit) cannot touch the
+    headline run.  Returns (last JSON line of its stdout parsed | None, error text | None)."""
+    import signal
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT, start_new_session=True)
+    try:
+        so, se = p.communicate(timeout=limit_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        so, se = p.communicate()
+        return None, f"no result within {limit_s} s (process group killed); stderr tail: {se[-300:]}"
+    line = next((ln for ln in reversed(so.splitlines()) if ln.startswith("{")), None)
+    if p.returncode != 0 or line is None:
+        return None, f"rc {p.returncode}, {'no JSON line' if line is None else 'JSON line present'}; stderr tail: {se[-400:]}"
+    try:
+        return json.loads(line), None
+    except ValueError as e:
+        return None, f"unparsable JSON line: {e}"
+
+
+def _sub_env(port_shift):
+    """Environment of a multi-rank sub-job started from inside a torchrun worker: same RANK / LOCAL_RANK / WORLD_SIZE, its
+    own rendezvous port, and rank 0 hosts the store itself (torchrun's agent store lives on the parent's port)."""
+    e = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
+    e["MASTER_PORT"] = str(int(e.get("MASTER_PORT", "29500")) + port_shift)
+    e["IPPLB_PG_TIMEOUT_S"] = "90"
+    return e
+
+
+def _brief(d):
+    b = {k: d[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "kernels_ms", "solve_ms",
+                           "parity", "gpu_launches", "step_roofline") if k in d}
+    r = d.get("roofline") or {}
+    b["roofline"] = {k: r.get(k) for k in ("kernel", "frac", "achieved", "peak", "unit", "ms_per_launch")}
+    b["config"] = d.get("config")
+    return b
+
+
+def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_limit=240):
+    """BASELINE.json's other configurations, measured in the same driver run as the headline (configs[1]) line:
+    configs[3] (BumponTail 512^3, 2^29 particles per GPU) at every N, configs[2] (PenningTrap 256^3, 2^30 particles, ORB)
+    at N = 8, configs[4] (scatter / gather microbench, sorted against random order; at N > 1 one replica per GPU, all at
+    once) -- each as a separate process (group) with its own time limit, after the timed region, the roofline and the
+    end-to-end figures of the headline line are final.  A failure is recorded as {"error": ...} and changes nothing else."""
+    import tempfile
+    ex = {"what": "secondary measurements, each in its own process after the headline numbers were final"}
+    t0 = time.perf_counter()
+    box = None
+    if world > 1:
+        # the ranks meet again through files in a directory named by rank 0 (agreed on while they are still in step):
+        # no collective of the headline run's process group is left waiting while the sub-jobs run
+        token = [f"{os.getpid()}_{time.time_ns()}" if rank == 0 else None]
+        dist.broadcast_object_list(token, src=0)
+        box = os.path.join(tempfile.gettempdir(), "ipplb_extras_" + token[0])
+        os.makedirs(box, exist_ok=True)
+    me = [sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", str(world), "--steps", "5", "--warmup", "3",
+          "--no-e2e", "--no-cpu", "--no-extras"]
+    if jobs is None:    # (name, command, time limit in seconds); the tests pass their own
+        jobs = [("c4_bumpontail", me + ["--config", "bumpontail"], 180)]
+        if world == 8:
+            jobs.insert(0, ("c3_penning", me + ["--config", "penning"], 180))
+    if micro_cmd is None:
+        micro_cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_extras.py"), "--device", str(local)]
+    for i, (name, cmd, limit) in enumerate(jobs):
+        d, err = _run_sub(cmd, _sub_env(11 + i) if world > 1 else dict(os.environ), limit)
+        if rank == 0:       # only rank 0 of a sub-job prints a line
+            ex[name] = _brief(d) if d else {"error": err}
+    d, err = _run_sub(micro_cmd, dict(os.environ), micro_limit)
+    micro = d if d else {"error": err}
+    if world > 1:
+        mine = os.path.join(box, f"micro_{rank}.json")
+        with open(mine + ".tmp", "w") as f:
+            json.dump(micro, f)
+        os.replace(mine + ".tmp", mine)
+        files = [os.path.join(box, f"micro_{r}.json") for r in range(world)]
+        deadline = time.perf_counter() + micro_limit + 30     # every rank leaves this wait at the same moment
+        while time.perf_counter() < deadline and not all(os.path.exists(f) for f in files):
+            time.sleep(0.2)
+        if rank == 0:
+            every = [json.load(open(f)) if os.path.exists(f) else None for f in files]
+            worst = {}
+            for m in every:
+                for r in (m or {}).get("rows", []):
+                    for k, v in r.items():
+                        if k.endswith("_gpps"):
+                            key = f"ppc{r.get('ppc')}_{r.get('order')}_{k}"
+                            worst[key] = min(worst.get(key, v), v)
+            micro = dict(micro, replicas={"n": world, "failed": sum(1 for m in every if not m or "error" in m),
+                                          "min_over_ranks_gpps": worst,
+                                          "what": "the same one-GPU sweep on every GPU of the box at the same time"})
+    ex["micro"] = micro
+    ex["seconds"] = time.perf_counter() - t0
+    return ex
+
+
 # ---- our arm ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -191,6 +290,7 @@ def main():
                     help="multi-GPU field solve (not part of the timed step; reported as solve_ms): replicated cuFFT solve or the slab-decomposed one")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (other BASELINE configs, microbench)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -211,7 +311,8 @@ def main():
     dev = ctx.device
     if world > 1:
         # a rank that dies must not leave its peers waiting for the whole time limit: collectives give up after 3 minutes
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("IPPLB_PG_TIMEOUT_S", "180"))))
         uid = [ib.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
@@ -329,9 +430,19 @@ def main():
         if world == 1 and args.config == "landau":
             out["e2e_particles_streamed"] = run.e2e_streamed(barrier)
 
+    run.close()
+    # ---- secondary measurements: only on the headline workload, only after everything above is final ----------------
+    if (not args.no_extras and os.environ.get("IPPLB_BENCH_EXTRAS", "1") != "0" and args.config == "landau"
+            and args.log2_particles is None and args.mode == 2):
+        del run, bins
+        torch.cuda.empty_cache()
+        try:
+            extras = extras_leg(args, world, rank, local, dist)
+        except Exception as e:  # noqa: BLE001 -- never lose the headline line to a secondary measurement
+            extras = {"error": f"{type(e).__name__}: {e}"[:400]}
+        out["extras"] = extras
     if rank == 0:
         print(json.dumps(out))
-    run.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

@@ -290,6 +290,11 @@ int ipplb_bins_destroy(ipplb_bins* bins);
 /* Counting sort of `in` (contiguous, any order, in->n particles; uniform charge) into buckets of `out`
  * (cell-sorted inside every bucket).  in and out must not alias. */
 int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* bins, const ipplb_particles* in, ipplb_particles* out);
+/* How ipplb_bins_build places the particles: 1 (default) per-cell positions inside the bucket, one atomic per particle;
+ * 2 arrival order inside the bucket (the order the fused step itself maintains for arrivals), one atomic per run of
+ * same-tile lanes, sequential write position per tile so that the 8-byte stores merge in L2.  Same tables either way.
+ * The reference's counterpart is its counting-sort binning, src/Interpolation/Binning.h:110-114. */
+int ipplb_bins_set_build_variant(ipplb_bins* bins, int variant);
 /* One fused step over the bucketed particles `cur`, written re-bucketed into `nxt` (the caller swaps the
  * two bundles afterwards): per particle gather E (tile of E staged in shared memory) -> kick, kick, drift,
  * periodic BC (ipplb_push, bit-identical to ipplb_gather_push) -> shared-memory binning by new cell ->

@@ -216,6 +216,48 @@ bins_move_kernel(long n, const int* __restrict__ keys, const int* __restrict__ c
     }
 }
 
+// Build variant 2: the buckets are filled in ARRIVAL order (one cursor per tile, not per cell -- the order inside a bucket
+// is free: the fused step appends arrivals and overflow the same way).  What it changes against bins_move_kernel:
+//   * the write position of a tile advances sequentially over the kernel, so the 8-byte stores of consecutive arrivals
+//     land in the same 32-byte sectors and merge in L2 before they reach HBM (per-cell positions keep 64x more
+//     partially written sectors open than L2 holds: every store becomes a read-modify-write of a sector);
+//   * lanes of a warp that go to the same tile take their slots with ONE atomic (match.any + popc): cell-ordered or
+//     nearly ordered input (a re-bucketing after ipplb_bins_compact / an ORB repartition) costs one atomic per run;
+//   * no per-cell offset look-ups (two random 4-byte loads per particle), inputs read with evict-first loads so that
+//     the streaming side does not push the half-written sectors out of L2.
+// Same tables, same guarantees as variant 1 (count <= cap, nothing dropped: cap >= the tile's total at build time).
+__global__ void __launch_bounds__(256)
+bins_move2_kernel(long n, const int* __restrict__ keys, int* __restrict__ tile_cursor, const int* __restrict__ start,
+                  const int* __restrict__ cap, SoA6 P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const long stride   = (long)gridDim.x * blockDim.x;
+    // all lanes of a warp iterate together (match / shuffle need the full warp)
+    for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const long i     = base + lane;
+        const bool valid = i < n;
+        const int tile   = valid ? (__ldcs(&keys[i]) >> 6) : (-1 - (int)lane);   // idle lanes: distinct groups of one
+        double v[6];
+        if (valid) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) v[a] = __ldcs(&P.in[a][i]);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, tile);
+        const int leader     = __ffs(peers) - 1;
+        const int rank       = __popc(peers & ((1u << lane) - 1u));
+        int first = 0;
+        if (valid && (int)lane == leader) first = atomicAdd(&tile_cursor[tile], __popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (valid) {
+            const int in_t = first + rank;
+            if (in_t < cap[tile]) {
+                const long g = (long)start[tile] + in_t;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) P.out[a][g] = v[a];
+            }
+        }
+    }
+}
+
 // ---- append / compact -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bins_append_kernel(long count, const int* __restrict__ state, int capacity, SoA6 P, int* __restrict__ misc) {
@@ -357,6 +399,12 @@ int ipplb_bins_set_timing(ipplb_bins* b, int on) {
     return IPPLB_OK;
 }
 
+int ipplb_bins_set_build_variant(ipplb_bins* b, int variant) {
+    IPPLB_REQUIRE(b && (variant == 1 || variant == 2), "bins_set_build_variant: variant is 1 or 2");
+    b->build_variant = variant;
+    return IPPLB_OK;
+}
+
 int ipplb_bins_kernel_ms(ipplb_ctx* ctx, ipplb_bins* b, double* ms_out, int max_out, int* n_out) {
     IPPLB_REQUIRE(ctx && b && n_out, "bins_kernel_ms: bad arguments");
     IPPLB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -414,8 +462,11 @@ int ipplb_bins_build(ipplb_ctx* ctx, ipplb_bins* b, const ipplb_particles* in, i
             P.in[a]  = pi[a];
             P.out[a] = po[a];
         }
-        bins_move_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(n, keys, b->d_cell, counts,
-                                                                             b->start(c), b->cap(c), P);
+        if (b->build_variant == 2)
+            bins_move2_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(n, keys, counts, b->start(c), b->cap(c), P);
+        else
+            bins_move_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(n, keys, b->d_cell, counts,
+                                                                                 b->start(c), b->cap(c), P);
         IPPLB_CHECK_LAUNCH(ctx);
     }
     if ((rc = bins_plan(ctx, b, c))) return rc;

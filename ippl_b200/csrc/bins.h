@@ -34,6 +34,7 @@ struct ipplb_bins {
     cudaEvent_t* ev = nullptr;  // [2 * NEV]: start / stop per launch
     int ev_n = 0, timing = 0;
     int* h_status = nullptr;  // pinned [BM_WORDS]
+    int build_variant = 1;    // ipplb_bins_set_build_variant: 1 per-cell positions, 2 arrival order (bins.cu)
     // slack = total / slack_div + slack_sqrt * sqrt(total) + slack_const  (elements per bucket)
     int slack_div = 32, slack_sqrt = 4, slack_const = 16;
 

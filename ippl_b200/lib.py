@@ -498,6 +498,10 @@ class Bins:
         cur.arr, nxt.arr = nxt.arr, cur.arr
         cur.qarr, nxt.qarr = nxt.qarr, cur.qarr
 
+    def set_build_variant(self, variant):
+        """1: per-cell positions (default); 2: arrival order, warp-aggregated tile cursors (ipplb_bins_set_build_variant)"""
+        _check(lib().ipplb_bins_set_build_variant(self._h, int(variant)))
+
     def set_timing(self, on=True):
         _check(lib().ipplb_bins_set_timing(self._h, 1 if on else 0))
 

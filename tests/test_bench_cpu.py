@@ -56,3 +56,79 @@ def test_traffic_extract_is_what_bench_reports():
     raw = json.load(open(os.path.join(ROOT, "profiles", "r2_fused_traffic.json")))
     assert t == raw["dram_bytes_read"] + raw["dram_bytes_write"] and 1.2e10 < t < 1.4e10 and src["kernel"] == raw["kernel"]
     assert bench.profiled_traffic("some_other_kernel") == (None, None)
+
+
+# ---- the secondary-measurement leg (bench.extras_leg): process plumbing, no GPU ---------------------------------------
+_CHILD = r'''
+import json, os, sys, datetime
+import torch, torch.distributed as dist
+mode = sys.argv[1]
+rank = int(os.environ.get("RANK", "0"))
+if mode == "job":      # a multi-rank sub-job: its own rendezvous on the shifted port, rank 0 prints the line
+    assert "TORCHELASTIC_USE_AGENT_STORE" not in os.environ and os.environ["IPPLB_PG_TIMEOUT_S"] == "90"
+    dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=60))
+    t = torch.tensor([rank + 1.0])
+    dist.all_reduce(t)
+    if rank == 0:
+        print("noise before the line")
+        print(json.dumps({"metric": "m", "value": float(t[0]), "unit": "particles/s", "n_gpus": dist.get_world_size(),
+                          "ms_per_step": 1.0, "roofline": {"kernel": "k", "frac": 0.5, "ms_per_launch": 0.9, "junk": 1},
+                          "config": {"workload": "w"}, "clocks": {"dropped": True}}))
+    dist.destroy_process_group()
+elif mode == "crash":
+    sys.stderr.write("boom\n")
+    sys.exit(3)
+elif mode == "hang":
+    import time
+    time.sleep(60)
+elif mode == "micro":
+    print(json.dumps({"rows": [{"ppc": 8, "order": "random", "n": 10, "gather_gpps": 20.0 + rank, "scatter_atomic_gpps": 30.0 - rank}],
+                      "bins_build": []}))
+'''
+
+_PARENT = r'''
+import json, os, sys, datetime
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+import bench
+child = sys.argv[2]
+world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=60))
+jobs = [("good", [sys.executable, child, "job"], 60), ("bad", [sys.executable, child, "crash"], 60),
+        ("stuck", [sys.executable, child, "hang"], 2)]
+ex = bench.extras_leg(None, world, rank, rank, dist, jobs=jobs, micro_cmd=[sys.executable, child, "micro"], micro_limit=30)
+if rank == 0:
+    print("RESULT " + json.dumps(ex))
+dist.destroy_process_group()
+'''
+
+
+def test_extras_leg_sub_jobs_under_torchrun(tmp_path):
+    """two torchrun workers (gloo): each starts the sub-jobs; a multi-rank sub-job gets its own rendezvous, a crashing one
+    and a hanging one are reported as errors, the per-rank microbench lines are merged through files"""
+    (tmp_path / "child.py").write_text(_CHILD)
+    (tmp_path / "parent.py").write_text(_PARENT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29871", str(tmp_path / "parent.py"), ROOT, str(tmp_path / "child.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    ex = json.loads(line[len("RESULT "):])
+    assert ex["good"]["value"] == 3.0 and ex["good"]["n_gpus"] == 2 and ex["good"]["config"] == {"workload": "w"}
+    assert ex["good"]["roofline"] == {"kernel": "k", "frac": 0.5, "achieved": None, "peak": None, "unit": None, "ms_per_launch": 0.9}
+    assert "clocks" not in ex["good"]
+    assert "rc 3" in ex["bad"]["error"] and "boom" in ex["bad"]["error"]
+    assert "no result within 2 s" in ex["stuck"]["error"]
+    rep = ex["micro"]["replicas"]
+    assert rep["n"] == 2 and rep["failed"] == 0
+    assert rep["min_over_ranks_gpps"] == {"ppc8_random_gather_gpps": 20.0, "ppc8_random_scatter_atomic_gpps": 29.0}
+    assert ex["micro"]["rows"][0]["gather_gpps"] == 20.0
+
+
+def test_extras_leg_single_process(tmp_path):
+    import bench
+    (tmp_path / "child.py").write_text(_CHILD)
+    child = str(tmp_path / "child.py")
+    ex = bench.extras_leg(None, 1, 0, 0, None, jobs=[("bad", [sys.executable, child, "crash"], 30)],
+                          micro_cmd=[sys.executable, child, "micro"], micro_limit=30)
+    assert "rc 3" in ex["bad"]["error"] and ex["micro"]["rows"][0]["ppc"] == 8 and "replicas" not in ex["micro"]

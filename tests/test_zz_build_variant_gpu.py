@@ -1,0 +1,100 @@
+"""ipplb_bins_build, variant 2 (arrival order inside the buckets, warp-aggregated tile cursors; ippl_b200/csrc/bins.cu,
+bins_move2_kernel) against variant 1 and the oracle.  The kernel was written after this round's GPU budget was spent and
+has not run on a GPU yet: xfail(strict=False) until it has passed once (a pass shows as XPASS); the file sorts last so
+that a fault in it cannot hide the verified tests.  Variant 1 stays the default.
+
+The reference's counterpart is its counting-sort binning (src/Interpolation/Binning.h:110-114); what is checked is what
+the fused step needs from the store: every bucket holds exactly the particles of its tile (any order), nothing lost,
+and the first fused steps on a variant-2 store give the same particles bit for bit and the oracle's rho."""
+import numpy as np
+import pytest
+
+import oracle
+from test_gpu_parity import TOL_SUM, _canon, _check_buckets, _dev, _rho_err_periodic
+from util import normal_velocities
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="bins_move2_kernel not yet executed on a GPU (written without GPU access)")]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import ippl_b200 as ib
+    c = ib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("order", ["random", "sorted", "one_tile"])
+@pytest.mark.parametrize("ppc", [1, 40])
+def test_build_variant2_buckets_and_first_steps(ctx, ppc, order):
+    import ippl_b200 as ib
+    nr = (20, 16, 12)
+    n = nr[0] * nr[1] * nr[2] * ppc + 7          # not a multiple of the warp size: the last warp has idle lanes
+    h = [4 * np.pi / 16] * 3
+    L = [nr[d] * h[d] for d in range(3)]
+    mo = oracle.Mesh.make(nr, (0, 0, 0), h)
+    mg = ib.Mesh.make(nr, (0, 0, 0), h)
+    rng = np.random.default_rng(300 + ppc)
+    R = [rng.uniform(0, L[d], n) for d in range(3)]
+    if order == "one_tile":                       # every lane of every warp wants the same cursor
+        R = [rng.uniform(4.2 * h[d], 7.4 * h[d], n) for d in range(3)]
+    P = normal_velocities(n, seed=11)
+    if order == "sorted":                         # cell-ordered input: runs of same-tile lanes (one atomic per run)
+        key = (np.floor(R[0] / h[0] + 0.5).astype(np.int64)
+               + 64 * (np.floor(R[1] / h[1] + 0.5).astype(np.int64) + 64 * np.floor(R[2] / h[2] + 0.5).astype(np.int64)))
+        perm = np.argsort(key, kind="stable")
+        R, P = [r[perm] for r in R], [p[perm] for p in P]
+    q = -0.37
+    cap = int(1.6 * n) + 4096
+    src = ib.Particles.from_host(R, P, ctx.device, q=q)
+    got = {}
+    for variant in (1, 2):
+        pb = ib.Particles(cap, ctx.device, q=q)
+        bins = ib.Bins(ctx, mg, cap)
+        bins.set_build_variant(variant)
+        bins.build(src, pb)
+        assert _check_buckets(bins, pb, mg, h, n) == 0     # tiles right, counts right, no overlap, nothing in the tail
+        out = ib.Particles(n, ctx.device)
+        assert bins.compact(pb, out) == n
+        got[variant] = (bins, pb, bins.tables(), _canon(out.host()))
+    # same multiset of particles as the input, same tables as variant 1
+    assert np.array_equal(got[2][3], _canon([*R, *P]))
+    assert np.array_equal(got[2][3], got[1][3])
+    for a, b in zip(got[1][2], got[2][2]):
+        assert np.array_equal(a, b)
+    got[1][0].close()
+    # three fused steps on the variant-2 store against the unfused kernels and the oracle
+    bins, pb = got[2][0], got[2][1]
+    sc = ib.Particles(cap, ctx.device, q=q)
+    dt = 0.5 * h[0]
+    ef = 0.2 * rng.normal(size=mg.cells * 3)
+    oracle.halo_periodic(ef, mo.ext, 3, 1, (1, 1, 1), "fill")
+    efd = _dev(ctx, ef)
+    push = ib.leapfrog_push(dt)
+    pa = ib.Particles.from_host(R, P, ctx.device, q=q)
+    rho = ctx.field(mg)
+    for it in range(3):
+        ctx.gather_push(mg, push, pa, efd)
+        Ro = pa.host()
+        want = oracle.field_zeros(mo)
+        oracle.scatter_cic(mo, Ro[0], Ro[1], Ro[2], q, want)
+        rho.zero_()
+        bins.step(push, pb, sc, efd, rho)
+        _check_buckets(bins, pb, mg, h, n)
+        out = ib.Particles(n, ctx.device)
+        assert bins.compact(pb, out) == n
+        assert np.array_equal(_canon(out.host()), _canon(Ro))
+        assert _rho_err_periodic(rho, want, mo) <= TOL_SUM
+    bins.close()
+
+
+def test_build_variant_argument_check(ctx):
+    import ippl_b200 as ib
+    mg = ib.Mesh.make((8, 8, 8), (0, 0, 0), (1.0, 1.0, 1.0))
+    bins = ib.Bins(ctx, mg, 4096)
+    with pytest.raises(ib.IpplbError):
+        bins.set_build_variant(3)
+    bins.set_build_variant(2)
+    bins.set_build_variant(1)
+    bins.close()
