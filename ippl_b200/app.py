@@ -146,15 +146,33 @@ class MiniApp:
             ctx.halo_accumulate_periodic(mesh, self.rho)
             sol = ib.Poisson(ctx, mesh)
         ctx.field_density(mesh, self.rho, h[0] * h[1] * h[2], self.q * self.n_total / (Lg[0] * Lg[1] * Lg[2]))
-        sol.solve(self.rho, self.ef)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sol.solve(self.rho, self.ef)
-        e1.record()
-        torch.cuda.synchronize()
-        self.solve_ms = e0.elapsed_time(e1)
+        rho0 = self.rho.clone()     # the solve leaves the last gradient component in rho (like the reference's in-place transform)
+
+        def timed_solve(solver, ef):
+            solver.solve(self.rho, ef)          # first call: plans, work space
+            torch.cuda.synchronize()
+            self.rho.copy_(rho0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            solver.solve(self.rho, ef)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+        self.solve_ms = timed_solve(sol, self.ef)
         sol.close()
+        if self.world > 1 and self.fft == "slab":
+            # the slab-decomposed solve next to the replicated one on the same rho: agreement and time of both
+            ref = ib.Poisson(ctx, None, layout=self.layout, origin=self.origin, h=h, slab=False)
+            ef_ref = torch.zeros_like(self.ef)
+            self.rho.copy_(rho0)
+            ms_ref = timed_solve(ref, ef_ref)
+            ref.close()
+            num = torch.stack([(self.ef - ef_ref).square().sum(), ef_ref.square().sum()])
+            if self.dist is not None:
+                self.dist.all_reduce(num)
+            self.solve_check = {"rel_l2_slab_vs_replicated": float((num[0] / num[1]).sqrt()), "slab_ms": self.solve_ms,
+                                "replicated_ms": ms_ref, "finite": bool(torch.isfinite(self.ef).all())}
+            del ef_ref
 
     # ---- one step of the hot path -----------------------------------------------------------------------------------
     def fill_e_halo(self):
@@ -236,6 +254,8 @@ class MiniApp:
         c = {}
         if self.world > 1:
             c["field_solve"] = self.fft
+            if getattr(self, "solve_check", None):
+                c["field_solve_check"] = self.solve_check
         if self.orb is not None:
             c["orb"] = {k: self.orb[k] for k in ("applied", "imbalance_before", "imbalance_after")}
         if self.world > 1 and self.bins is not None:
