@@ -219,12 +219,13 @@ def _brief(d):
     return b
 
 
-def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_limit=240):
+def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_limit=240, variant_cmds=None):
     """BASELINE.json's other configurations, measured in the same driver run as the headline (configs[1]) line:
     configs[3] (BumponTail 512^3, 2^29 particles per GPU) at every N, configs[2] (PenningTrap 256^3, 2^30 particles, ORB)
     at N = 8, configs[4] (scatter / gather microbench, sorted against random order; at N > 1 one replica per GPU, all at
-    once) -- each as a separate process (group) with its own time limit, after the timed region, the roofline and the
-    end-to-end figures of the headline line are final.  A failure is recorded as {"error": ...} and changes nothing else."""
+    once), and on rank 0 the A/B runs of the two kernel variants that were written without GPU access -- each as a separate
+    process (group) with its own time limit, after the timed region, the roofline and the end-to-end figures of the
+    headline line are final.  A failure is recorded as {"error": ...} and changes nothing else."""
     import tempfile
     ex = {"what": "secondary measurements, each in its own process after the headline numbers were final"}
     t0 = time.perf_counter()
@@ -244,8 +245,12 @@ def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_
             jobs.insert(0, ("c3_penning", me + ["--config", "penning"], 180))
         if world > 1:   # the slab-decomposed FFT solve on the 512^3 mesh, checked against and timed next to the replicated one
             jobs.append(("fft_slab_512", me + ["--config", "bumpontail", "--fft", "slab", "--log2-particles", "26"], 150))
+    micro = [sys.executable, os.path.join(ROOT, "scripts", "bench_extras.py"), "--device", str(local), "--part"]
     if micro_cmd is None:
-        micro_cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_extras.py"), "--device", str(local)]
+        micro_cmd = micro + ["verified"]
+    if variant_cmds is None:    # kernel variants that have never run: one process each, in the one-GPU run only
+        variant_cmds = [] if world > 1 else [("micro_gather_variants", micro + ["gather_variants"], 150),
+                                             ("micro_build_variants", micro + ["build_variants"], 150)]
     for i, (name, cmd, limit) in enumerate(jobs):
         d, err = _run_sub(cmd, _sub_env(11 + i) if world > 1 else dict(os.environ), limit)
         if rank == 0:       # only rank 0 of a sub-job prints a line
@@ -257,11 +262,20 @@ def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_
         with open(mine + ".tmp", "w") as f:
             json.dump(micro, f)
         os.replace(mine + ".tmp", mine)
-        files = [os.path.join(box, f"micro_{r}.json") for r in range(world)]
-        deadline = time.perf_counter() + micro_limit + 30     # every rank leaves this wait at the same moment
+    if rank == 0:
+        for name, cmd, limit in variant_cmds:
+            d, err = _run_sub(cmd, dict(os.environ), limit)
+            ex[name] = d if d else {"error": err}
+    if world > 1:
+        # every rank leaves this wait at the same moment: rank 0's marker appears when its variant runs are over
+        with open(os.path.join(box, f"done_{rank}"), "w") as f:
+            f.write("1")
+        files = [os.path.join(box, f"done_{r}") for r in range(world)]
+        deadline = time.perf_counter() + micro_limit + sum(v[2] for v in variant_cmds) + 30
         while time.perf_counter() < deadline and not all(os.path.exists(f) for f in files):
             time.sleep(0.2)
         if rank == 0:
+            files = [os.path.join(box, f"micro_{r}.json") for r in range(world)]
             every = [json.load(open(f)) if os.path.exists(f) else None for f in files]
             worst = {}
             for m in every:

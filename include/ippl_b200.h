@@ -116,6 +116,11 @@ int ipplb_gather_cic(ipplb_ctx* ctx, const ipplb_mesh* mesh, long n, const doubl
  * valid halo.  Reads and rewrites x,y,z,px,py,pz in place. */
 int ipplb_gather_push(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* push,
                       ipplb_particles* p, const double* efield);
+/* How ipplb_gather_cic (3 components) and ipplb_gather_push read the field: 1 (default) one 8-byte load per node and
+ * component (24 per particle); 2 the two x-neighbours of a stencil row with 16-byte loads (14 per particle) -- fewer load
+ * wavefronts on unordered particles, where every lane touches its own sectors.  Bit-identical results.  Falls back to 1
+ * when the field pointer is not 16-byte aligned. */
+int ipplb_ctx_set_gather_variant(ipplb_ctx* ctx, int variant);
 
 /* ---- unfused particle ops (arbitrary driver expressions) ---------------------------------- */
 /* y[i] = y[i] + a * x[i]  (ParticleAttrib::operator=(Expression), ParticleAttrib.hpp:118-130, for

@@ -82,6 +82,7 @@ struct ipplb_ctx {
     bool own_stream     = false;
     long launches       = 0;
     int num_sms         = 148;
+    int gather_variant  = 1;  // ipplb_ctx_set_gather_variant: 1 eight-byte loads per node component, 2 sixteen-byte loads per x-pair
     // scratch pools (grown on demand, never shrunk -- same policy as the reference's
     // BufferHandler, src/Communicate/BufferHandler.hpp:14-34)
     ipplb::Scratch keys, counts, cub_tmp, reduce, send, recv, misc;

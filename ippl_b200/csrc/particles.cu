@@ -4,6 +4,8 @@
 // All kernels are HBM-bound streaming kernels; no tensor cores (nothing here is a contraction).
 #include <cub/device/device_scan.cuh>
 
+#include <cstdint>
+
 #include "keys.cuh"
 #include "push.cuh"
 
@@ -173,6 +175,45 @@ gather_push_kernel(MeshDev m, PushDev P, long n, double* __restrict__ x, double*
     }
 }
 
+// variant 2 of the two kernels above (ipplb_ctx_set_gather_variant): gather_point3_vec, otherwise the same
+__global__ void __launch_bounds__(256)
+gather3v_kernel(MeshDev m, long n, const double* __restrict__ x, const double* __restrict__ y,
+                const double* __restrict__ z, const double* __restrict__ f, double* __restrict__ o0,
+                double* __restrict__ o1, double* __restrict__ o2, int add) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Cic c;
+        cic_setup(m, x[i], y[i], z[i], c);
+        double g[3];
+        gather_point3_vec(m, c, f, g);
+        double* o[3] = {o0, o1, o2};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) o[d][i] = add ? dadd(o[d][i], g[d]) : g[d];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_push_v_kernel(MeshDev m, PushDev P, long n, double* __restrict__ x, double* __restrict__ y,
+                     double* __restrict__ z, double* __restrict__ px, double* __restrict__ py,
+                     double* __restrict__ pz, const double* __restrict__ ef) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double r[3] = {x[i], y[i], z[i]};
+        double p[3] = {px[i], py[i], pz[i]};
+        Cic c;
+        cic_setup(m, r[0], r[1], r[2], c);
+        double E[3];
+        gather_point3_vec(m, c, ef, E);
+        push_particle(P, r, p, E);
+        x[i]  = r[0];
+        y[i]  = r[1];
+        z[i]  = r[2];
+        px[i] = p[0];
+        py[i] = p[1];
+        pz[i] = p[2];
+    }
+}
+
 // unfused pieces --------------------------------------------------------------------------------
 __global__ void axpy_kernel(long n, double a, const double* __restrict__ x, double* __restrict__ y) {
     const long stride = (long)gridDim.x * blockDim.x;
@@ -285,7 +326,9 @@ int ipplb_gather_cic(ipplb_ctx* ctx, const ipplb_mesh* mesh, long n, const doubl
     if (n == 0) return IPPLB_OK;
     MeshDev m = make_mesh_dev(mesh);
     int grid  = grid_for(ctx, n, 256, 16);
-    if (ncomp == 3)
+    if (ncomp == 3 && ctx->gather_variant == 2 && ((uintptr_t)field & 15) == 0)
+        gather3v_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, x, y, z, field, out[0], out[1], out[2], add_to_attribute);
+    else if (ncomp == 3)
         gather_kernel<3><<<grid, 256, 0, ctx->stream>>>(m, n, x, y, z, field, out[0], out[1], out[2],
                                                         add_to_attribute);
     else
@@ -301,9 +344,19 @@ int ipplb_gather_push(ipplb_ctx* ctx, const ipplb_mesh* mesh, const ipplb_push* 
     if (p->n == 0) return IPPLB_OK;
     MeshDev m = make_mesh_dev(mesh);
     PushDev P = make_push_dev(mesh, push);
-    gather_push_kernel<<<grid_for(ctx, p->n, 256, 16), 256, 0, ctx->stream>>>(
-        m, P, p->n, p->x, p->y, p->z, p->px, p->py, p->pz, efield);
+    if (ctx->gather_variant == 2 && ((uintptr_t)efield & 15) == 0)
+        gather_push_v_kernel<<<grid_for(ctx, p->n, 256, 16), 256, 0, ctx->stream>>>(
+            m, P, p->n, p->x, p->y, p->z, p->px, p->py, p->pz, efield);
+    else
+        gather_push_kernel<<<grid_for(ctx, p->n, 256, 16), 256, 0, ctx->stream>>>(
+            m, P, p->n, p->x, p->y, p->z, p->px, p->py, p->pz, efield);
     IPPLB_CHECK_LAUNCH(ctx);
+    return IPPLB_OK;
+}
+
+int ipplb_ctx_set_gather_variant(ipplb_ctx* ctx, int variant) {
+    IPPLB_REQUIRE(ctx && (variant == 1 || variant == 2), "ctx_set_gather_variant: variant is 1 or 2");
+    ctx->gather_variant = variant;
     return IPPLB_OK;
 }
 

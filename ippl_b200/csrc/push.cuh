@@ -34,6 +34,38 @@ __device__ __forceinline__ void gather_point(const MeshDev& m, const Cic& c,
     gather_point_at<NCOMP>(c.whi, [&](int p) { return cic_node(m, c.a, p); }, f, out);
 }
 
+// Gather, variant 2 (three components, AoS-3 field): the two x-neighbours of a stencil row are 6 contiguous doubles that
+// start on a 16-byte boundary or 8 bytes behind one, so a row is three 16-byte loads (+ one 8-byte load in the odd
+// case) instead of six 8-byte loads: 14 load instructions per particle instead of 24.  On unordered particles every lane
+// of a load touches its own sector, and the number of such load wavefronts is what the kernel pays for.  Same weights,
+// same fold order (CIC.hpp:63-65): bit-identical to gather_point<3>.  `f` must be 16-byte aligned.
+__device__ __forceinline__ void load_pair3(const double* __restrict__ f, long node_lo, double v[6]) {
+    const long e  = node_lo * 3;   // first element of the pair
+    const long e0 = e & ~1L;       // the 16-byte aligned element at or one before it
+    const double2* q = reinterpret_cast<const double2*>(f + e0);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    if (e & 1) {
+        v[0] = a.y; v[1] = b.x; v[2] = b.y; v[3] = c.x; v[4] = c.y;
+        v[5] = __ldg(f + e + 5);   // (not a fourth 16-byte load: its upper half may lie behind the end of the field)
+    } else {
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+    }
+}
+__device__ __forceinline__ void gather_point3_vec(const MeshDev& m, const Cic& c, const double* __restrict__ f, double out[3]) {
+    double w[8], v[4][6];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) w[p] = cic_weight(c.whi, p);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) load_pair3(f, cic_node(m, c.a, 2 * r + 1), v[r]);   // stencil point 2r+1 = (a0-1, ., .), 2r = its +x neighbour
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double acc = dmul(w[7], v[3][d]);
+#pragma unroll
+        for (int p = 6; p >= 0; --p) acc = dadd(dmul(w[p], (p & 1) ? v[p >> 1][d] : v[p >> 1][3 + d]), acc);
+        out[d] = acc;
+    }
+}
+
 struct PushDev {
     int kind, do_kick2, do_kick1, do_drift, do_bc;
     double dt, c;          // c = 0.5*dt

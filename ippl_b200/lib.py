@@ -262,6 +262,10 @@ class Context:
     def sync(self):
         _check(lib().ipplb_sync(self._h))
 
+    def set_gather_variant(self, variant):
+        """1: 8-byte field loads (default); 2: 16-byte loads per x-pair of stencil nodes (ipplb_ctx_set_gather_variant)"""
+        _check(lib().ipplb_ctx_set_gather_variant(self._h, int(variant)))
+
     @property
     def launches(self):
         return lib().ipplb_launch_count(self._h)

@@ -81,6 +81,8 @@ elif mode == "crash":
 elif mode == "hang":
     import time
     time.sleep(60)
+elif mode == "variant":
+    print(json.dumps({"part": sys.argv[2], "rows": [{"v2_same_bits": True}]}))
 elif mode == "micro":
     print(json.dumps({"rows": [{"ppc": 8, "order": "random", "n": 10, "gather_gpps": 20.0 + rank, "scatter_atomic_gpps": 30.0 - rank}],
                       "bins_build": []}))
@@ -96,7 +98,8 @@ world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
 dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=60))
 jobs = [("good", [sys.executable, child, "job"], 60), ("bad", [sys.executable, child, "crash"], 60),
         ("stuck", [sys.executable, child, "hang"], 2)]
-ex = bench.extras_leg(None, world, rank, rank, dist, jobs=jobs, micro_cmd=[sys.executable, child, "micro"], micro_limit=30)
+ex = bench.extras_leg(None, world, rank, rank, dist, jobs=jobs, micro_cmd=[sys.executable, child, "micro"], micro_limit=30,
+                      variant_cmds=[("va", [sys.executable, child, "variant", "a"], 30), ("vb", [sys.executable, child, "crash"], 30)])
 if rank == 0:
     print("RESULT " + json.dumps(ex))
 dist.destroy_process_group()
@@ -123,6 +126,7 @@ def test_extras_leg_sub_jobs_under_torchrun(tmp_path):
     assert rep["n"] == 2 and rep["failed"] == 0
     assert rep["min_over_ranks_gpps"] == {"ppc8_random_gather_gpps": 20.0, "ppc8_random_scatter_atomic_gpps": 29.0}
     assert ex["micro"]["rows"][0]["gather_gpps"] == 20.0
+    assert ex["va"] == {"part": "a", "rows": [{"v2_same_bits": True}]} and "rc 3" in ex["vb"]["error"]
 
 
 def test_extras_leg_single_process(tmp_path):
@@ -130,5 +134,7 @@ def test_extras_leg_single_process(tmp_path):
     (tmp_path / "child.py").write_text(_CHILD)
     child = str(tmp_path / "child.py")
     ex = bench.extras_leg(None, 1, 0, 0, None, jobs=[("bad", [sys.executable, child, "crash"], 30)],
-                          micro_cmd=[sys.executable, child, "micro"], micro_limit=30)
+                          micro_cmd=[sys.executable, child, "micro"], micro_limit=30,
+                          variant_cmds=[("va", [sys.executable, child, "variant", "a"], 30)])
     assert "rc 3" in ex["bad"]["error"] and ex["micro"]["rows"][0]["ppc"] == 8 and "replicas" not in ex["micro"]
+    assert ex["va"]["part"] == "a"

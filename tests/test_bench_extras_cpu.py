@@ -50,6 +50,14 @@ def _fake_bindings(torch, calls):
         def close(self):
             calls.append("close")
 
+        def set_gather_variant(self, v):
+            calls.append(f"gather_variant{v}")
+
+        def gather(self, mesh, x, y, z, ef, out, add=False):
+            for o in out:
+                o.zero_()
+            calls.append("gather")
+
         def __getattr__(self, name):   # halo_fill_periodic, scatter, gather, gather_push, scatter_sorted
             def op(*a, **k):
                 calls.append(name)
@@ -93,7 +101,7 @@ def _fake_bindings(torch, calls):
     return ib
 
 
-def test_bench_extras_script_logic(monkeypatch, capsys):
+def _run_part(monkeypatch, capsys, part):
     import torch
     calls = []
     monkeypatch.setitem(sys.modules, "ippl_b200", _fake_bindings(torch, calls))
@@ -114,15 +122,38 @@ def test_bench_extras_script_logic(monkeypatch, capsys):
     spec = importlib.util.spec_from_file_location("bench_extras", os.path.join(ROOT, "scripts", "bench_extras.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    monkeypatch.setattr(sys, "argv", ["bench_extras.py", "--device", "0", "--grid", "6", "--ppc", "1", "3", "--reps", "3"])
+    monkeypatch.setattr(sys, "argv", ["bench_extras.py", "--part", part, "--device", "0", "--grid", "6", "--ppc", "1", "3", "--reps", "3"])
     mod.main()
     d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    assert [b["ppc"] for b in d["bins_build"]] == [1, 3] and all("error" not in b for b in d["bins_build"]), d["bins_build"]
-    b = d["bins_build"][1]
-    assert b["n"] == 3 * 216 and b["v1_ms"] == b["v2_ms"] == 2.0 and b["speedup"] == 1.0
-    assert b["v2_same_tables"] and b["v2_same_particles"] and b["v2_step_rho_rel_l2"] == 0.0
+    assert d["part"] == part
+    return d, calls
+
+
+def test_bench_extras_verified_part(monkeypatch, capsys):
+    d, calls = _run_part(monkeypatch, capsys, "verified")
     rows = d["rows"]
-    assert all("error" not in r for r in rows), rows
     assert [(r["ppc"], r["order"]) for r in rows] == [(1, "sorted"), (1, "random"), (1, "bucketed"), (3, "sorted"), (3, "random"), (3, "bucketed")]
-    assert rows[0]["scatter_sorted_gpps"] == 216 / 2.0 / 1e6 and "scatter_sorted_gpps" not in rows[1] and rows[2]["fused_step_gpps"] > 0
-    assert {"variant1", "variant2", "gather", "gather_push", "scatter", "scatter_sorted", "close"} <= set(calls)
+    assert rows[0]["scatter_sorted_gpps"] == 216 / 2.0 / 1e6 and "scatter_sorted_gpps" not in rows[1]
+    assert rows[2]["fused_step_gpps"] > 0 and rows[5]["bins_build_ms"] == 2.0 and rows[5]["n"] == 3 * 216
+    assert {"gather", "gather_push", "scatter", "scatter_sorted", "close"} <= set(calls)
+    assert not any(c.startswith(("variant", "gather_variant")) for c in calls)     # no variant is touched by this part
+
+
+def test_bench_extras_gather_variants_part(monkeypatch, capsys):
+    d, calls = _run_part(monkeypatch, capsys, "gather_variants")
+    rows = d["rows"]
+    assert [(r["ppc"], r["order"]) for r in rows] == [(1, "sorted"), (1, "random"), (3, "sorted"), (3, "random")]
+    for r in rows:
+        assert r["v2_same_bits"] is True and r["gather_speedup"] == 1.0 and r["gather_push_v2_gpps"] == r["gather_push_v1_gpps"] > 0
+    seq = [c for c in calls if c.startswith("gather_variant")]
+    assert seq[:3] == ["gather_variant1", "gather_variant2", "gather_variant1"] and seq[-1] == "gather_variant1"
+
+
+def test_bench_extras_build_variants_part(monkeypatch, capsys):
+    d, calls = _run_part(monkeypatch, capsys, "build_variants")
+    rows = d["rows"]
+    assert [r["ppc"] for r in rows] == [1, 3]
+    b = rows[1]
+    assert b["n"] == 3 * 216 and b["build_v1_ms"] == b["build_v2_ms"] == 2.0 and b["build_speedup"] == 1.0
+    assert b["v2_same_tables"] and b["v2_same_particles"] and b["v2_step_rho_rel_l2"] == 0.0
+    assert [c for c in calls if c.startswith("variant")] == ["variant1", "variant2"] * 2
