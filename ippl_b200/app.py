@@ -170,8 +170,12 @@ class MiniApp:
             num = torch.stack([(self.ef - ef_ref).square().sum(), ef_ref.square().sum()])
             if self.dist is not None:
                 self.dist.all_reduce(num)
-            self.solve_check = {"rel_l2_slab_vs_replicated": float((num[0] / num[1]).sqrt()), "slab_ms": self.solve_ms,
-                                "replicated_ms": ms_ref, "finite": bool(torch.isfinite(self.ef).all())}
+            rel, finite = float((num[0] / num[1]).sqrt()), bool(torch.isfinite(self.ef).all())
+            good = finite and rel <= 1e-9
+            if not good:      # the steps that follow must not run on a wrong field: the mismatch is reported, not hidden
+                self.ef.copy_(ef_ref)
+            self.solve_check = {"rel_l2_slab_vs_replicated": rel, "slab_ms": self.solve_ms, "replicated_ms": ms_ref, "finite": finite,
+                                "field_used_by_the_steps": "slab solve" if good else "replicated solve (slab result rejected)"}
             del ef_ref
 
     # ---- one step of the hot path -----------------------------------------------------------------------------------
