@@ -212,7 +212,7 @@ def _sub_env(port_shift):
 
 def _brief(d):
     b = {k: d[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "kernels_ms", "solve_ms",
-                           "parity", "gpu_launches", "step_roofline") if k in d}
+                           "parity", "gpu_launches", "step_roofline", "run") if k in d}
     r = d.get("roofline") or {}
     b["roofline"] = {k: r.get(k) for k in ("kernel", "frac", "achieved", "peak", "unit", "ms_per_launch")}
     b["config"] = d.get("config")
@@ -407,9 +407,9 @@ def main():
     achieved = alg / (ms_launch * 1e-3) / 1e9
     step_bytes = BYTES_PER_PARTICLE_STEP * n_local + BYTES_PER_CELL_STEP * ncell_int
     step_achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
-    cfg = config_dict(w, world, bins is not None)
-    cfg["tail_fraction"] = st["n_tail"] / max(st["n_local"], 1)
-    cfg.update(run.extra_config())
+    cfg = config_dict(w, world, bins is not None)     # the workload: the same object in both arms' lines
+    run_info = {"tail_fraction": st["n_tail"] / max(st["n_local"], 1)}   # what this run found: kept out of `config`
+    run_info.update(run.extra_config())
 
     out = {
         "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -421,7 +421,7 @@ def main():
                      "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch, "ms_per_launch_how": how},
         "step_roofline": {"bytes_per_particle": BYTES_PER_PARTICLE_STEP, "achieved": step_achieved, "peak": peak,
                           "unit": "GB/s", "frac": step_achieved / peak},
-        "kernels_ms": kern, "solve_ms": run.solve_ms,
+        "kernels_ms": kern, "solve_ms": run.solve_ms, "run": run_info,
     }
     if parity is not None:
         out["parity"] = parity

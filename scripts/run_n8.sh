@@ -17,7 +17,7 @@ for f in ("n8", "n4", "penning_n8", "bumpontail_n8"):
     try:
         d = json.load(open(f"gpurun_out/bench_r2_{f}.json"))
         print(f, "value %.4g" % d["value"], "ms/step %.4f" % d["ms_per_step"], "kernel %.4f" % d["roofline"]["ms_per_launch"], "frac %.3f" % d["roofline"]["frac"],
-              "e2e %.4g" % d["e2e"]["value"], d["kernels_ms"], d["config"].get("tail_fraction"), d["config"].get("orb"), d["config"].get("migrated_fraction_last_step"), d.get("parity", {}).get("rho_rel_l2"))
+              "e2e %.4g" % d["e2e"]["value"], d["kernels_ms"], d.get("run", d["config"]).get("tail_fraction"), d.get("run", d["config"]).get("orb"), d.get("run", d["config"]).get("migrated_fraction_last_step"), d.get("parity", {}).get("rho_rel_l2"))
     except Exception as e:
         print(f, "failed", e)
 P
