@@ -12,7 +12,7 @@ run() {   # run <seconds> <log name> <command...>
     echo "$name: rc=$? ($(tail -1 gpurun_out/first_$name.log | cut -c1-160))"
 }
 # 1. the validated suite first (kernel parity, loop ranks, facade drivers): must stay green
-run 900 suite python -m pytest tests -q -m gpu -x --deselect tests/test_zz_reference_drivers.py --deselect tests/test_zz_slab_fft_gpu.py
+run 900 suite python -m pytest tests -q -m gpu -x --deselect tests/test_zz_reference_drivers.py --deselect tests/test_zz_slab_fft_gpu.py --deselect tests/test_zz_variants_gpu.py
 # 2. the reference's lambdas / unchanged drivers / lazy fusion, one by one
 run 120 ref_lambdas demos/ref_lambdas
 run 300 ref_drivers python -m pytest tests/test_zz_reference_drivers.py -q -rA

@@ -1,0 +1,22 @@
+"""The two kernel variants written after this round's GPU budget was spent -- ipplb_bins_build variant 2
+(tests/variant_build_check.py) and the gather kernels' variant 2 (tests/variant_gather_check.py) -- each checked in its OWN
+pytest process: a CUDA fault in a kernel that has never run poisons the CUDA context of the process it happens in, and must
+not reach the rest of the suite or the other variant.  xfail(strict=False) until each has passed once on a GPU (a pass shows
+as XPASS); both variants are opt-in, the defaults are the verified kernels."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="kernel variant not yet executed on a GPU (written without GPU access)")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("check", ["variant_build_check.py", "variant_gather_check.py"])
+def test_kernel_variant_in_its_own_process(check):
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", check), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1500:]
+    assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1500:]
