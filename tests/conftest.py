@@ -1,7 +1,10 @@
 import os
 import sys
+import time
 
 import pytest
+
+os.environ.setdefault("IPPLB_TEST_SESSION_T0", repr(time.time()))   # tests/util.py: first_run_timeout
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -16,6 +16,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from util import first_run_timeout
+
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="reference drivers built unchanged for sm_100a but not yet executed on a GPU")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,7 +36,7 @@ def _run(tmp_path, exe, grid, np_, nt, csv, fuse=None, log=None):
     cmd = [_exe(exe), str(grid), str(grid), str(grid), str(np_), str(nt), "FFT", "0.01", "LeapFrog", "--overallocate", "2.0",
            "--info", "0"]
     env = dict(os.environ) if fuse is None else dict(os.environ, IPPL_B200_FUSE=str(fuse))
-    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=150, env=env)
+    out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=first_run_timeout(90), env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     if log is not None:
         log.append(out.stdout)
@@ -42,7 +44,7 @@ def _run(tmp_path, exe, grid, np_, nt, csv, fuse=None, log=None):
 
 
 def test_reference_lambdas_against_cabi_kernels():
-    out = subprocess.run([_exe("ref_lambdas")], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([_exe("ref_lambdas")], capture_output=True, text=True, timeout=first_run_timeout(60))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 
@@ -88,7 +90,7 @@ def test_reference_landau_driver_on_the_fused_step(tmp_path):
 
 
 def test_fusion_engine_with_peeks_on_gpu():
-    out = subprocess.run([_exe("fusion_check")], capture_output=True, text=True, timeout=150)
+    out = subprocess.run([_exe("fusion_check")], capture_output=True, text=True, timeout=first_run_timeout(60))
     assert out.returncode == 0 and "fusion_check: ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
@@ -107,7 +109,7 @@ def test_reference_landau_driver_on_two_gpus_plain_and_fused(tmp_path):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                "--master-port", str(29560 + fuse), _exe("ref_LandauDamping"), "16", "16", "16", "10000000", "25", "FFT", "0.01", "LeapFrog",
                "--overallocate", "2.0", "--info", "0"]
-        res = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=300, env=dict(os.environ, IPPL_B200_FUSE=str(fuse)))
+        res = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=first_run_timeout(150), env=dict(os.environ, IPPL_B200_FUSE=str(fuse)))
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
         out[fuse] = (np.loadtxt(d / "data" / "FieldLandau_2_manager.csv", skiprows=1), res.stdout)
     assert np.max(np.abs(out[0][0][:, 1:] - golden[:, 1:])) <= 0.4

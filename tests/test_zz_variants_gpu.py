@@ -9,6 +9,8 @@ import sys
 
 import pytest
 
+from util import first_run_timeout
+
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="kernel variant not yet executed on a GPU (written without GPU access)")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,6 +19,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("check", ["variant_build_check.py", "variant_gather_check.py"])
 def test_kernel_variant_in_its_own_process(check):
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", check), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"],
-                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+                         cwd=ROOT, capture_output=True, text=True, timeout=first_run_timeout(150))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1500:]
     assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1500:]
