@@ -191,7 +191,7 @@ def _run_sub(cmd, env, limit_s):
         except ProcessLookupError:
             pass
         so, se = p.communicate()
-        return None, f"no result within {limit_s} s (process group killed); stderr tail: {se[-300:]}"
+        return None, f"no result within {limit_s:.0f} s (process group killed); stderr tail: {se[-300:]}"
     line = next((ln for ln in reversed(so.splitlines()) if ln.startswith("{")), None)
     if p.returncode != 0 or line is None:
         return None, f"rc {p.returncode}, {'no JSON line' if line is None else 'JSON line present'}; stderr tail: {se[-400:]}"
@@ -219,7 +219,7 @@ def _brief(d):
     return b
 
 
-def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_limit=240, variant_cmds=None):
+def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_limit=240, variant_cmds=None, budget_s=600.0, min_left_s=15.0):
     """BASELINE.json's other configurations, measured in the same driver run as the headline (configs[1]) line:
     configs[3] (BumponTail 512^3, 2^29 particles per GPU) at every N, configs[2] (PenningTrap 256^3, 2^30 particles, ORB)
     at N = 8, configs[4] (scatter / gather microbench, sorted against random order; at N > 1 one replica per GPU, all at
@@ -229,6 +229,13 @@ def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_
     import tempfile
     ex = {"what": "secondary measurements, each in its own process after the headline numbers were final"}
     t0 = time.perf_counter()
+
+    def run_sub(cmd, env, limit):
+        # every sub-run has its own limit, and all of them together `budget_s` (the driver's limit for one bench run is fixed)
+        left = budget_s - (time.perf_counter() - t0)
+        if left < min_left_s:
+            return None, f"not started: the {budget_s:.0f} s budget of the secondary measurements was spent"
+        return _run_sub(cmd, env, min(float(limit), left))
     box = None
     if world > 1:
         # the ranks meet again through files in a directory named by rank 0 (agreed on while they are still in step):
@@ -252,10 +259,10 @@ def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_
         variant_cmds = [] if world > 1 else [("micro_gather_variants", micro + ["gather_variants"], 150),
                                              ("micro_build_variants", micro + ["build_variants"], 150)]
     for i, (name, cmd, limit) in enumerate(jobs):
-        d, err = _run_sub(cmd, _sub_env(11 + i) if world > 1 else dict(os.environ), limit)
+        d, err = run_sub(cmd, _sub_env(11 + i) if world > 1 else dict(os.environ), limit)
         if rank == 0:       # only rank 0 of a sub-job prints a line
             ex[name] = _brief(d) if d else {"error": err}
-    d, err = _run_sub(micro_cmd, dict(os.environ), micro_limit)
+    d, err = run_sub(micro_cmd, dict(os.environ), micro_limit)
     micro = d if d else {"error": err}
     if world > 1:
         mine = os.path.join(box, f"micro_{rank}.json")
@@ -264,14 +271,14 @@ def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_
         os.replace(mine + ".tmp", mine)
     if rank == 0:
         for name, cmd, limit in variant_cmds:
-            d, err = _run_sub(cmd, dict(os.environ), limit)
+            d, err = run_sub(cmd, dict(os.environ), limit)
             ex[name] = d if d else {"error": err}
     if world > 1:
         # every rank leaves this wait at the same moment: rank 0's marker appears when its variant runs are over
         with open(os.path.join(box, f"done_{rank}"), "w") as f:
             f.write("1")
         files = [os.path.join(box, f"done_{r}") for r in range(world)]
-        deadline = time.perf_counter() + micro_limit + sum(v[2] for v in variant_cmds) + 30
+        deadline = min(time.perf_counter() + micro_limit + sum(v[2] for v in variant_cmds), t0 + budget_s) + 30
         while time.perf_counter() < deadline and not all(os.path.exists(f) for f in files):
             time.sleep(0.2)
         if rank == 0:

@@ -121,7 +121,7 @@ def test_extras_leg_sub_jobs_under_torchrun(tmp_path):
     assert ex["good"]["roofline"] == {"kernel": "k", "frac": 0.5, "achieved": None, "peak": None, "unit": None, "ms_per_launch": 0.9}
     assert "clocks" not in ex["good"]
     assert "rc 3" in ex["bad"]["error"] and "boom" in ex["bad"]["error"]
-    assert "no result within 2 s" in ex["stuck"]["error"]
+    assert "no result within 2" in ex["stuck"]["error"] and "killed" in ex["stuck"]["error"]
     rep = ex["micro"]["replicas"]
     assert rep["n"] == 2 and rep["failed"] == 0
     assert rep["min_over_ranks_gpps"] == {"ppc8_random_gather_gpps": 20.0, "ppc8_random_scatter_atomic_gpps": 29.0}
@@ -138,3 +138,13 @@ def test_extras_leg_single_process(tmp_path):
                           variant_cmds=[("va", [sys.executable, child, "variant", "a"], 30)])
     assert "rc 3" in ex["bad"]["error"] and ex["micro"]["rows"][0]["ppc"] == 8 and "replicas" not in ex["micro"]
     assert ex["va"]["part"] == "a"
+
+
+def test_extras_leg_budget(tmp_path):
+    """all sub-runs together stay inside one budget: what does not fit is not started"""
+    import bench
+    (tmp_path / "child.py").write_text(_CHILD)
+    child = str(tmp_path / "child.py")
+    ex = bench.extras_leg(None, 1, 0, 0, None, jobs=[("stuck", [sys.executable, child, "hang"], 60)],
+                          micro_cmd=[sys.executable, child, "micro"], micro_limit=30, variant_cmds=[], budget_s=3.0, min_left_s=1.0)
+    assert "no result within" in ex["stuck"]["error"] and "not started" in ex["micro"]["error"] and ex["seconds"] < 10
