@@ -61,10 +61,10 @@ def test_traffic_extract_is_what_bench_reports():
 # ---- the secondary-measurement leg (bench.extras_leg): process plumbing, no GPU ---------------------------------------
 _CHILD = r'''
 import json, os, sys, datetime
-import torch, torch.distributed as dist
 mode = sys.argv[1]
 rank = int(os.environ.get("RANK", "0"))
 if mode == "job":      # a multi-rank sub-job: its own rendezvous on the shifted port, rank 0 prints the line
+    import torch, torch.distributed as dist
     assert "TORCHELASTIC_USE_AGENT_STORE" not in os.environ and os.environ["IPPLB_PG_TIMEOUT_S"] == "90"
     dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=60))
     t = torch.tensor([rank + 1.0])
