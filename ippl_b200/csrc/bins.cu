@@ -226,6 +226,8 @@ bins_move_kernel(long n, const int* __restrict__ keys, const int* __restrict__ c
 //   * no per-cell offset look-ups (two random 4-byte loads per particle), inputs read with evict-first loads so that
 //     the streaming side does not push the half-written sectors out of L2.
 // Same tables, same guarantees as variant 1 (count <= cap, nothing dropped: cap >= the tile's total at build time).
+// [host-emulation begin: bins_move2_kernel]  (tests/test_kernel_text_cpu.py compiles the text between the markers for the
+// host with a lock-step warp emulator, tests/emu/emu_bins_move2.cpp, and runs it)
 __global__ void __launch_bounds__(256)
 bins_move2_kernel(long n, const int* __restrict__ keys, int* __restrict__ tile_cursor, const int* __restrict__ start,
                   const int* __restrict__ cap, SoA6 P) {
@@ -257,6 +259,7 @@ bins_move2_kernel(long n, const int* __restrict__ keys, int* __restrict__ tile_c
         }
     }
 }
+// [host-emulation end: bins_move2_kernel]
 
 // ---- append / compact -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
