@@ -15,6 +15,7 @@
 
 namespace ipplb {
 
+// [host-emulation begin: slab structs]  (tests/test_kernel_text_cpu.py compiles the marked text for the host, tests/emu/emu_slab.cpp)
 struct CopyDev {
     long src_off, dst_off;
     long ss[3], ds[3];
@@ -25,6 +26,7 @@ struct CopyDev {
 struct BufTable {
     double* p[SB_COUNT];
 };
+// [host-emulation end: slab structs]
 
 struct SlabState {
     SlabPlan plan;
@@ -36,6 +38,7 @@ struct SlabState {
     bool have2d = false, have1d = false;
 };
 
+// [host-emulation begin: slab kernels]
 // a list of strided 3-D sub-box copies: blockIdx.y picks the copy, the x dimension strides over its elements
 __global__ void __launch_bounds__(256) slab_copy_kernel(const CopyDev* __restrict__ list, const BufTable B) {
     const CopyDev c = list[blockIdx.y];
@@ -81,6 +84,7 @@ __global__ void kspace_slab_kernel(int nxh, int nyl, int nz, int ys, double inv_
         g2[t]    = make_cuDoubleComplex(b * c, -(a * c));
     }
 }
+// [host-emulation end: slab kernels]
 
 void slab_free(SlabState* st) {
     if (!st) return;

@@ -56,3 +56,131 @@ def test_gather_variant2_device_functions_on_the_host(tmp_path):
     log = _build_and_run(tmp_path, "emu_gather_v2.cpp",
                          ["-std=c++17", "-ffp-contract=off", "-w", "-I/usr/local/cuda/include", f"-I{ROOT}"], "EMU_GATHER_V2_OK")
     assert log.count(": ok") == 5 and "FAILED" not in log
+
+
+# ---- the slab-decomposed FFT solve: its two kernels' text inside the numpy executor of the plan --------------------------------
+def _slab_emulation_library(tmp_path):
+    import ctypes as C
+    src = open(os.path.join(ROOT, "ippl_b200", "csrc", "fftdist.cu")).read()
+    structs = re.search(r"// \[host-emulation begin: slab structs\].*?\n(.*?)// \[host-emulation end: slab structs\]", src, re.S)
+    kernels = re.search(r"// \[host-emulation begin: slab kernels\]\n(.*?)// \[host-emulation end: slab kernels\]", src, re.S)
+    assert structs and kernels, "markers not found in fftdist.cu"
+    (tmp_path / "structs.inc").write_text(structs.group(1))
+    (tmp_path / "kernels.inc").write_text(kernels.group(1))
+    lib = str(tmp_path / "libemu_slab.so")
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", f'-DSTRUCT_TEXT="{tmp_path / "structs.inc"}"',
+                         f'-DKERNEL_TEXT="{tmp_path / "kernels.inc"}"', os.path.join(EMU, "emu_slab.cpp"), "-o", lib],
+                        capture_output=True, text=True, timeout=300)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    return C.CDLL(lib)
+
+
+def test_slab_kernels_text_in_the_numpy_executor_of_the_plan(tmp_path):
+    """tests/test_slabplan_cpu.py's execution of the plan for all ranks, with the device executor's own kernels (source text
+    of slab_copy_kernel and kspace_slab_kernel, launch geometry of run_copies / transforms) doing the copies and the k-space
+    step; numpy only transforms (cuFFT conventions: unnormalised, half spectrum in x).  <= 1e-12 of the whole-domain solve."""
+    import ctypes as C
+
+    import numpy as np
+
+    import ippl_b200 as ib
+    import oracle
+    import test_slabplan_cpu as T
+    emu = _slab_emulation_library(tmp_path)
+
+    class CopyDev(C.Structure):
+        _fields_ = [("src_off", C.c_long), ("dst_off", C.c_long), ("ss", C.c_long * 3), ("ds", C.c_long * 3), ("n", C.c_int * 3),
+                    ("src_buf", C.c_int), ("dst_buf", C.c_int), ("elem", C.c_int)]
+    assert emu.emu_sizeof_copydev() == C.sizeof(CopyDev)
+    BUFS = ib.SlabPlan.BUFS
+
+    def k_tables(ng, origin, h):   # poisson_k_tables (poisson.cu), FFTPeriodicPoissonSolver.hpp:66-70, 127-137
+        out = []
+        for d in range(3):
+            N = ng[d]
+            i = np.arange(N // 2 + 1 if d == 0 else N)
+            Len = (origin[d] + N * h[d]) - origin[d]
+            out.append(np.ascontiguousarray((i != N // 2) * 2 * np.pi / Len * (i - (i > N // 2) * N)))
+        return out
+
+    class Rank(T.Rank):
+        cap = 4096
+
+        def copies(self, phase, which):
+            rows = self.plan.rows(phase, which)
+            if not rows:
+                return
+            arr = (CopyDev * len(rows))()
+            for a, c in zip(arr, rows):
+                a.src_off, a.dst_off, a.elem = c["src_off"], c["dst_off"], c["elem"]
+                a.src_buf, a.dst_buf = BUFS.index(c["src"]), BUFS.index(c["dst"])
+                for k in range(3):
+                    a.ss[k], a.ds[k], a.n[k] = c["ss"][k], c["ds"][k], c["n"][k]
+            ptrs = (C.c_void_p * len(BUFS))(*[self.buf[b].ctypes.data for b in BUFS])
+            biggest = max(c["n"][0] * c["n"][1] * c["n"][2] for c in rows)
+            emu.emu_slab_copies(arr, len(rows), ptrs, C.c_long(biggest), C.c_long(self.cap))
+
+    def step1(rk, origin, h):
+        p = rk.plan
+        nx, ny, nz = p.ng
+        nxh, nyl = p.nxh, p.ye - p.ys
+        if not nyl:
+            return
+        SZ = nz * nyl * nxh
+        sz = rk.buf["specz"]
+        sz[:SZ] = np.fft.fft(sz[:SZ].reshape(nz, nyl, nxh), axis=0).ravel()               # cufftExecZ2Z forward, in place
+        kx, ky, kz = k_tables(p.ng, origin, h)
+        at = lambda k: C.c_void_p(sz.ctypes.data + 16 * SZ * k)                              # noqa: E731
+        emu.emu_kspace(nxh, nyl, nz, p.ys, C.c_double(1.0 / (nx * ny * nz)), kx.ctypes.data_as(C.c_void_p),
+                       ky.ctypes.data_as(C.c_void_p), kz.ctypes.data_as(C.c_void_p), at(0), at(1), at(2), at(3), C.c_long(rk.cap))
+        for c in range(3):                                                                 # cufftExecZ2Z inverse: unnormalised
+            sz[(1 + c) * SZ:(2 + c) * SZ] = (np.fft.ifft(sz[(1 + c) * SZ:(2 + c) * SZ].reshape(nz, nyl, nxh), axis=0) * nz).ravel()
+
+    for ng, world, kind, cap in (((16, 12, 10), 2, "default", 4096), ((24, 16, 16), 8, "orb", 3), ((9, 7, 11), 5, "default", 1),
+                                 ((10, 6, 5), 8, "default", 4096)):
+        origin, h = (0.0, 0.5, -1.0), (0.3, 0.25, 0.4)
+        layout = ib.Layout(ng, world)
+        if kind == "orb":
+            layout.set_boxes(T.orb_like(ng, world))
+        rng = np.random.default_rng(7)
+        rho_g = rng.normal(size=(ng[2], ng[1], ng[0]))
+        rho_g -= rho_g.mean()
+        N, nxh = ng[0] * ng[1] * ng[2], ng[0] // 2 + 1
+        rhat = np.fft.rfftn(rho_g) / N
+        want = np.stack([np.fft.irfftn(rhat * np.broadcast_to(M, rho_g.shape)[:, :, :nxh], s=rho_g.shape, axes=(0, 1, 2)) * N
+                         for M in oracle.poisson_kspace_multipliers(ng, origin, h)], axis=-1)
+        Rank.cap = cap          # small caps force the kernels' grid-stride loops
+        ranks = [Rank(layout, r, origin, h) for r in range(world)]
+        g = ranks[0].plan.nghost
+        for rk in ranks:
+            f = rk.first
+            rk.buf["rho"].reshape(rk.ext[2], rk.ext[1], rk.ext[0])[g:-g, g:-g, g:-g] = \
+                rho_g[f[2]:f[2] + rk.nl[2], f[1]:f[1] + rk.nl[1], f[0]:f[0] + rk.nl[0]]
+        for phase in range(4):
+            for rk in ranks:
+                rk.copies(phase, 0)
+            T.exchange(ranks, phase)
+            for rk in ranks:
+                rk.copies(phase, 2)
+            if phase < 3:
+                for rk in ranks:
+                    if phase == 1:
+                        step1(rk, origin, h)
+                    else:
+                        T.transforms(rk, phase, origin, h)
+        scale = np.abs(want).max()
+        for r, rk in enumerate(ranks):
+            f = rk.first
+            ef = rk.buf["ef"].reshape(rk.ext[2], rk.ext[1], rk.ext[0], 3)
+            got = ef[g:-g, g:-g, g:-g]
+            ref = want[f[2]:f[2] + rk.nl[2], f[1]:f[1] + rk.nl[1], f[0]:f[0] + rk.nl[0]]
+            assert np.isfinite(got).all(), f"{ng} x{world} rank {r}: E interior not fully written"
+            assert np.max(np.abs(got - ref)) <= 1e-12 * scale, (ng, world, r, np.max(np.abs(got - ref)) / scale)
+            halo = ef.copy()
+            halo[g:-g, g:-g, g:-g] = np.nan
+            assert np.isnan(halo).all(), f"rank {r}: the solve wrote into E's ghost layers"
+            rho = rk.buf["rho"].reshape(rk.ext[2], rk.ext[1], rk.ext[0])
+            assert np.array_equal(rho[g:-g, g:-g, g:-g], got[..., 2])
+        for rk in ranks:
+            rk.plan.close()
+        layout.close()
