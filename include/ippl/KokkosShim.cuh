@@ -79,6 +79,8 @@ KOKKOS_INLINE_FUNCTION double abs(double a) { return ::fabs(a); }
 inline void fence() { ippl::b200::check(ipplb_sync(ippl::b200::ctx()), "Kokkos::fence"); }
 inline void fence(const std::string&) { fence(); }
 
+// [host-emulation begin: shim reducers]  (tests/test_kernel_text_cpu.py compiles the marked text of this header for the
+// host and runs the reduction kernels under a lock-step block emulator, tests/emu/emu_shim_reduce.cpp)
 // reducers: the result lands in the referenced host scalar when parallel_reduce returns (blocking, like Kokkos with a
 // scalar result)
 template <class T>
@@ -105,6 +107,7 @@ struct Min {
     static __host__ __device__ T identity() { return DBL_MAX; }
     static __host__ __device__ void join(T& a, const T& b) { a = b < a ? b : a; }
 };
+// [host-emulation end: shim reducers]
 
 namespace shim {
     inline cudaStream_t stream() { return (cudaStream_t)ipplb_ctx_stream(ippl::b200::ctx()); }
@@ -114,6 +117,7 @@ namespace shim {
     }
 
 #ifndef IPPL_SHIM_HOST_EMULATION
+    // [host-emulation begin: shim kernels]
     template <class F>
     __global__ void __launch_bounds__(256) for_kernel(long b, long e, F f) {
         for (long i = b + (long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long)gridDim.x * blockDim.x) f((std::size_t)i);
@@ -168,6 +172,7 @@ namespace shim {
         block_join<R0>(a0, out);
         block_join<R1>(a1, out + 1);
     }
+    // [host-emulation end: shim kernels]
 
     // result slots in device memory, initialised with the reducers' identities; read back when the launch is done
     struct Slots {

@@ -184,3 +184,17 @@ def test_slab_kernels_text_in_the_numpy_executor_of_the_plan(tmp_path):
         for rk in ranks:
             rk.plan.close()
         layout.close()
+
+
+def test_kokkos_shim_reduction_kernels_under_a_lockstep_block_emulator(tmp_path):
+    """for_kernel / reduce1_kernel / reduce2_kernel / block_join / atomic_join of include/ippl/KokkosShim.cuh -- the device
+    code behind the unchanged reference drivers' Kokkos::parallel_for / parallel_reduce, which the shim's own host-emulation
+    mode replaces by host loops -- cut out of the header and run as 256 host threads per block (tests/emu/emu_shim_reduce.cpp)"""
+    src = open(os.path.join(ROOT, "include", "ippl", "KokkosShim.cuh")).read()
+    red = re.search(r"// \[host-emulation begin: shim reducers\].*?\n(.*?)// \[host-emulation end: shim reducers\]", src, re.S)
+    ker = re.search(r"// \[host-emulation begin: shim kernels\]\n(.*?)// \[host-emulation end: shim kernels\]", src, re.S)
+    assert red and ker, "markers not found in KokkosShim.cuh"
+    (tmp_path / "reducers.inc").write_text(red.group(1))
+    (tmp_path / "kernels.inc").write_text(ker.group(1))
+    _build_and_run(tmp_path, "emu_shim_reduce.cpp", ["-std=c++20", "-pthread", f'-DREDUCER_TEXT="{tmp_path / "reducers.inc"}"',
+                                                     f'-DKERNEL_TEXT="{tmp_path / "kernels.inc"}"'], "EMU_SHIM_REDUCE_OK")
