@@ -148,3 +148,172 @@ def test_extras_leg_budget(tmp_path):
     ex = bench.extras_leg(None, 1, 0, 0, None, jobs=[("stuck", [sys.executable, child, "hang"], 60)],
                           micro_cmd=[sys.executable, child, "micro"], micro_limit=30, variant_cmds=[], budget_s=3.0, min_left_s=1.0)
     assert "no result within" in ex["stuck"]["error"] and "not started" in ex["micro"]["error"] and ex["seconds"] < 10
+
+
+def test_main_line_on_stand_ins(monkeypatch, capsys):
+    """bench.main() from argument parsing to the printed line, with the GPU side (context, mini-app, CUDA events) replaced by
+    stand-ins: the line carries what the contract asks for, `config` is the workload object, the findings sit under `run`,
+    the secondary measurements are attached after everything else and a failure in them cannot lose the line"""
+    import types
+
+    import torch
+
+    import bench
+    import ippl_b200 as ib
+    from ippl_b200 import app
+
+    class Ev:
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 40.0     # ms for the whole timed region
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    for name in ("synchronize", "set_device", "empty_cache"):
+        monkeypatch.setattr(torch.cuda, name, lambda *a, **k: None)
+
+    class Ctx:
+        device = "cpu"
+        launches = 0
+
+        def __init__(self, local):
+            pass
+
+        def close(self):
+            pass
+
+    class Bins:
+        def set_timing(self, on):
+            pass
+
+        def kernel_ms(self):
+            return [3.9, 4.1]
+
+    class Mini:
+        def __init__(self, ctx, w, rank, world, mode=2, fft="replicated", dist=None):
+            self.w, self.bins, self.solve_ms, self.n_mine = w, Bins(), 0.2, w["n_local"]
+            self.mesh = types.SimpleNamespace(nl=w["ng"], cells=(w["ng"][0] + 2) ** 3)
+            self.steps = 0
+
+        def initialise(self):
+            pass
+
+        def step(self, first=False):
+            self.steps += 1
+
+        def status(self):
+            return {"n_local": self.n_mine, "n_tail": 5, "n_exit": 0, "flags": 0}
+
+        def phase_ms(self):
+            return {"rho_zero": 0.01}
+
+        def extra_config(self):
+            return {"found": 1}
+
+        def e2e(self, steps, barrier):
+            return {"ms_per_step": 5.0, "steps": steps, "h2d_bytes_per_step": 1, "d2h_bytes_per_step": 2, "what": "w"}
+
+        def e2e_streamed(self, barrier):
+            return {"value": 1.0}
+
+        def close(self):
+            self.closed = True
+
+    monkeypatch.setattr(ib, "Context", Ctx)
+    monkeypatch.setattr(app, "MiniApp", Mini)
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": 1.0, "sm_max_mhz": 1.0, "reasons": []})
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+
+    def line(extras):
+        monkeypatch.setattr(bench, "extras_leg", extras)
+        monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "10", "--warmup", "3", "--no-cpu"])
+        bench.main()
+        return json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+    d = line(lambda *a, **k: {"stub": True})
+    w = app.workload("landau", 1)
+    assert d["config"] == bench.config_dict(w, 1, True) and d["run"] == {"tail_fraction": 5 / w["n_local"], "found": 1}
+    assert d["ms_per_step"] == 4.0 and d["value"] == w["n_local"] / 4.0e-3 and d["n_gpus"] == 1 and d["steps"] == 10 and d["warmup"] == 3
+    assert d["roofline"]["ms_per_launch"] == 4.0 and d["roofline"]["ms_per_launch"] <= d["ms_per_step"] and 0 < d["roofline"]["frac"] < 1
+    assert d["roofline"]["traffic"] and d["e2e"]["value"] == w["n_local"] / 5.0e-3 and d["e2e"]["unit"] == "particles/s"
+    assert d["extras"] == {"stub": True} and d["dtype"] == "f64" and d["higher_is_better"] is True and d["vs_baseline"] is None
+
+    def broken(*a, **k):
+        raise RuntimeError("secondary measurement fell over")
+    d = line(broken)
+    assert "fell over" in d["extras"]["error"] and d["ms_per_step"] == 4.0
+    monkeypatch.setenv("IPPLB_BENCH_EXTRAS", "0")
+    assert "extras" not in line(broken)
+
+
+def test_first_solve_restores_rho_and_checks_the_slab_solve(monkeypatch):
+    """MiniApp._first_solve on stand-ins: a solve leaves the last gradient component in rho, so the timed solve must start
+    from the restored rho; with --fft slab the slab result is compared with the replicated one on the same rho and a
+    disagreeing slab field is reported and not used for the steps"""
+    import types
+
+    import torch
+
+    import ippl_b200 as ib
+    from ippl_b200 import app
+
+    class Ev:
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.5
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    seen = []
+
+    class Solver:
+        def __init__(self, ctx, mesh, layout=None, origin=None, h=None, slab=False):
+            self.slab = slab
+
+        def solve(self, rho, ef):
+            seen.append(("slab" if self.slab else "replicated", float(rho.sum())))
+            ef.copy_(torch.cat([rho, 2 * rho, 3 * rho]) * (Solver.slab_factor if self.slab else 1.0))
+            rho.copy_(ef[-len(rho):])          # the solve clobbers rho with the last component
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(ib, "Poisson", Solver)
+    ctx = types.SimpleNamespace(device="cpu", scatter=lambda *a, **k: None, halo_exchange=lambda *a, **k: None,
+                                halo_accumulate_periodic=lambda *a, **k: None, field_density=lambda *a, **k: None)
+    w = app.workload("landau", 2, 10)
+
+    def make(fft, world):
+        m = app.MiniApp(ctx, w, 0, world, fft=fft)
+        m.parts = types.SimpleNamespace(arr={k: torch.zeros(4) for k in "xyz"})
+        m.n_mine, m.n_total, m.q, m.mesh, m.layout = 4, 8, -1.0, None, None
+        m.rho, m.ef = torch.arange(1.0, 6.0, dtype=torch.float64), torch.zeros(15, dtype=torch.float64)
+        return m
+
+    Solver.slab_factor = 1.0
+    m = make("replicated", 1)
+    m._first_solve()
+    assert [s[1] for s in seen] == [15.0, 15.0] and m.solve_ms == 1.5          # both solves saw the same rho
+    assert torch.equal(m.ef[:5], torch.arange(1.0, 6.0, dtype=torch.float64)) and not hasattr(m, "solve_check")
+    seen.clear()
+    m = make("slab", 2)
+    m._first_solve()
+    assert [s for s in seen] == [("slab", 15.0), ("slab", 15.0), ("replicated", 15.0), ("replicated", 15.0)]
+    assert m.solve_check["rel_l2_slab_vs_replicated"] == 0.0 and m.solve_check["field_used_by_the_steps"] == "slab solve"
+    assert m.extra_config()["field_solve_check"] == m.solve_check
+    Solver.slab_factor = 1.001                                                  # a slab solve that is off by 0.1 %
+    m = make("slab", 2)
+    m._first_solve()
+    assert abs(m.solve_check["rel_l2_slab_vs_replicated"] - 1e-3) < 1e-9 and "rejected" in m.solve_check["field_used_by_the_steps"]
+    assert torch.equal(m.ef[:5], torch.arange(1.0, 6.0, dtype=torch.float64))  # the steps get the replicated field
