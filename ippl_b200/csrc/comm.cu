@@ -898,7 +898,8 @@ static int arrivals_p2p(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, dou
     double* out[6] = {cur->x, cur->y, cur->z, cur->px, cur->py, cur->pz};
     for (int k = 0; k < 6; ++k) a.out[k] = out[k];
     a.q = cur->q_scalar; a.rho = rho;
-    arrivals_p2p_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(a);
+    // latency bound (record load -> cursor atomic -> dependent stores): as many resident warps as the 40-register kernel allows
+    arrivals_p2p_kernel<<<ctx->num_sms * 6, 256, 0, ctx->stream>>>(a);
     IPPLB_CHECK_LAUNCH(ctx);
     M->parity ^= 1;
     return IPPLB_OK;
