@@ -250,6 +250,8 @@ def extras_leg(args, world, rank, local, dist, jobs=None, micro_cmd=None, micro_
         jobs = [("c4_bumpontail", me + ["--config", "bumpontail"], 180)]
         if world == 8:
             jobs.insert(0, ("c3_penning", me + ["--config", "penning"], 180))
+        if world == 1:  # the same workload on the unfused kernels (gather+push, counting sort by cell, sorted scatter): what the fused step replaces
+            jobs.append(("c2_unfused_mode1", me + ["--mode", "1"], 120))
         if world > 1:   # the slab-decomposed FFT solve on the 512^3 mesh, checked against and timed next to the replicated one
             jobs.append(("fft_slab_512", me + ["--config", "bumpontail", "--fft", "slab", "--log2-particles", "26"], 150))
     micro = [sys.executable, os.path.join(ROOT, "scripts", "bench_extras.py"), "--device", str(local), "--part"]
