@@ -811,6 +811,8 @@ arrivals_kernel(MeshDev m, const double* __restrict__ recs, int na, long tail_po
     }
 }
 
+// [host-emulation begin: arrivals_p2p_kernel]  (tests/test_kernel_text_cpu.py compiles the marked text for the host and runs
+// it under a lock-step block emulator, tests/emu/emu_arrivals.cpp)
 struct ArriveArgs {
     MeshDev m;
     const int* matrix;      // [nranks][nranks] leavers per (source, destination)
@@ -849,7 +851,10 @@ __global__ void __launch_bounds__(256) arrivals_p2p_kernel(const ArriveArgs a) {
         Cic c;
         cic_setup(a.m, r0.x, r0.y, r1.x, c);
         const int cx = c.a[0] - a.m.nghost, cy = c.a[1] - a.m.nghost, cz = c.a[2] - a.m.nghost;
-        if (cx < 0 || cx > a.m.nl[0] || cy < 0 || cy > a.m.nl[1] || cz < 0 || cz > a.m.nl[2]) {
+        // (v - v == 0 fails for NaN and infinities; the conversion to a cell index turns NaN into cell 0, which is inside
+        //  the box of a rank that starts there)
+        const bool finite = (r0.x - r0.x == 0.0) && (r0.y - r0.y == 0.0) && (r1.x - r1.x == 0.0);
+        if (!finite || cx < 0 || cx > a.m.nl[0] || cy < 0 || cy > a.m.nl[1] || cz < 0 || cz > a.m.nl[2]) {
             // not a position of this rank's box (a non-finite position ends up here through the "stay" fallback of
             // the destination search): no bucket can take it -- flag it instead of indexing the tables with it
             atomicOr(&a.misc[BM_ST_FLAGS], IPPLB_FLAG_INTERNAL);
@@ -884,6 +889,7 @@ __global__ void __launch_bounds__(256) arrivals_p2p_kernel(const ArriveArgs a) {
     if (n_bucket) { atomicAdd(&a.misc[BM_ST_BUCKETED], n_bucket); atomicAdd(&a.misc[BM_ST_TOTAL], n_bucket); }
     if (n_tail) { atomicAdd(&a.misc[BM_ST_TAIL], n_tail); atomicAdd(&a.misc[BM_ST_TOTAL], n_tail); }
 }
+// [host-emulation end: arrivals_p2p_kernel]
 
 static int arrivals_p2p(ipplb_ctx* ctx, ipplb_bins* b, ipplb_particles* cur, double* rho) {
     CommPlan* P = (CommPlan*)ctx->plan;

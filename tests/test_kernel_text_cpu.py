@@ -198,3 +198,19 @@ def test_kokkos_shim_reduction_kernels_under_a_lockstep_block_emulator(tmp_path)
     (tmp_path / "kernels.inc").write_text(ker.group(1))
     _build_and_run(tmp_path, "emu_shim_reduce.cpp", ["-std=c++20", "-pthread", f'-DREDUCER_TEXT="{tmp_path / "reducers.inc"}"',
                                                      f'-DKERNEL_TEXT="{tmp_path / "kernels.inc"}"'], "EMU_SHIM_REDUCE_OK")
+
+
+def test_arrivals_kernel_text_under_a_lockstep_block_emulator(tmp_path):
+    """arrivals_p2p_kernel (ippl_b200/csrc/comm.cu), the multi-GPU step's kernel that drops the inbox records into their
+    buckets: GPU-verified in round 2, then given a check that refuses records outside the rank's box without GPU access.
+    Its text, with the product's own cic.cuh / bins.h, as 256 host threads per block (tests/emu/emu_arrivals.cpp): valid
+    records land once (bucket or tail), records on the box's upper faces are accepted, zeroed / non-finite / foreign
+    records are refused and flagged, a full tail is flagged, status words and deposited charge add up.  (This run found
+    that a NaN coordinate converts to cell 0 and passed the first version of the check on ranks whose box starts there.)"""
+    src = open(os.path.join(ROOT, "ippl_b200", "csrc", "comm.cu")).read()
+    m = re.search(r"// \[host-emulation begin: arrivals_p2p_kernel\].*?\n(struct ArriveArgs.*?)// \[host-emulation end: arrivals_p2p_kernel\]", src, re.S)
+    assert m, "markers not found in comm.cu"
+    (tmp_path / "arrivals.inc").write_text(m.group(1))
+    log = _build_and_run(tmp_path, "emu_arrivals.cpp", ["-std=c++20", "-w", "-pthread", "-ffp-contract=off", "-I/usr/local/cuda/include",
+                                                         f"-I{ROOT}", f'-DKERNEL_TEXT="{tmp_path / "arrivals.inc"}"'], "EMU_ARRIVALS_OK")
+    assert log.count(": ok") == 3 and "FAILED" not in log
