@@ -115,6 +115,7 @@ def main():
                      "gather_gpps": gpps(n, timed(lambda: ctx.gather(mesh, x, y, z, ef, eout))),
                      "gather_push_gpps": gpps(n, timed(lambda: ctx.gather_push(mesh, push, work, ef), reset=reset))}
                 if order == "sorted":
+                    reset()     # back to the cell-sorted positions the offsets describe
                     r["scatter_sorted_gpps"] = gpps(n, timed(lambda: ctx.scatter_sorted(mesh, n, x, y, z, q, off, rho), reset=zero_rho))
                 out["rows"].append(r)
             del srt, eout
