@@ -17,6 +17,8 @@ run 900 suite python -m pytest tests -q -m gpu -x --deselect tests/test_zz_refer
 run 120 ref_lambdas demos/ref_lambdas
 run 300 ref_drivers python -m pytest tests/test_zz_reference_drivers.py -q -rA
 run 120 fusion_check demos/fusion_check
+# 2b. the two opt-in kernel variants (bucket build v2, gather v2), each in its own pytest process
+run 400 variants python -m pytest tests/test_zz_variants_gpu.py -q -rA
 # 3. slab-decomposed FFT on in-process ranks
 run 300 slab_fft python tests/slab_fft_check.py
 # 4. the headline bench (unchanged kernel; checks nothing regressed)
