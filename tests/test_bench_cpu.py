@@ -317,3 +317,25 @@ def test_first_solve_restores_rho_and_checks_the_slab_solve(monkeypatch):
     m._first_solve()
     assert abs(m.solve_check["rel_l2_slab_vs_replicated"] - 1e-3) < 1e-9 and "rejected" in m.solve_check["field_used_by_the_steps"]
     assert torch.equal(m.ef[:5], torch.arange(1.0, 6.0, dtype=torch.float64))  # the steps get the replicated field
+
+
+def test_main_line_on_two_ranks_with_stand_ins(tmp_path):
+    """bench.main() under torchrun with 2 workers (tests/bench_main_stand_in.py: gloo for NCCL, stand-ins for the GPU side):
+    one line from rank 0, whole-job value from the slowest rank's time, the parity object, the end-to-end maximum, the
+    secondary measurements merged over the ranks"""
+    from ippl_b200 import app
+    (tmp_path / "child.py").write_text(_CHILD)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29921", os.path.join(ROOT, "tests", "bench_main_stand_in.py"), str(tmp_path / "child.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    w = app.workload("landau", 2)
+    assert d["n_gpus"] == 2 and d["ms_per_step"] == 25.0 / 6 and d["value"] == 2 * w["n_local"] / (25.0 / 6 * 1e-3)
+    assert d["parity"] == {"counts_exact": True, "ranks": 2} and d["config"]["workload"].startswith("alpine LandauDamping 256x128x128")
+    assert d["run"]["field_solve"] == "replicated" and d["roofline"]["traffic"] is None
+    assert d["e2e"]["ms_per_step"] == 6.0 and d["e2e"]["value"] == 2 * w["n_local"] / 6.0e-3 and "e2e_particles_streamed" not in d
+    ex = d["extras"]
+    assert ex["job"]["value"] == 3.0 and ex["job"]["n_gpus"] == 2 and ex["micro"]["replicas"]["n"] == 2 and ex["micro"]["replicas"]["failed"] == 0
