@@ -23,11 +23,11 @@ def canon(cols):
     return a[np.lexsort(a.T[::-1])]
 
 
-def orb_like_boxes(ng, world):
+def orb_like_boxes(ng, world, shifts=((0, 2), (1, -1))):
     """unequal boxes that tile the domain (what an ORB repartition produces): cuts moved off the middle"""
     boxes = oracle.partition(ng, world).copy()
     # move every interior cut along x by +2 cells and along y by -1 cell where the layout has such cuts
-    for d, shift in ((0, 2), (1, -1)):
+    for d, shift in shifts:
         cuts = sorted(set(int(b[d]) for b in boxes) - {0})
         for c in cuts:
             for b in boxes:
@@ -72,6 +72,8 @@ LAYOUTS = [(2, "default"), (4, "default"), (8, "default"), (4, "orb"), (8, "orb"
 
 
 def make_job(world, kind, ng=(24, 16, 16)):
+    if kind == "orb_z":   # also the z cut off the middle (tests/loop_orb_z_check.py: the 127 / 129 split of the PenningTrap blob)
+        return Job(world, ng, orb_like_boxes(ng, world, shifts=((0, 2), (1, -1), (2, -1))))
     return Job(world, ng, orb_like_boxes(ng, world) if kind == "orb" else None)
 
 

@@ -1,7 +1,9 @@
-"""The two kernel variants written after this round's GPU budget was spent -- ipplb_bins_build variant 2
-(tests/variant_build_check.py) and the gather kernels' variant 2 (tests/variant_gather_check.py) -- each checked in its OWN
-pytest process: a CUDA fault in a kernel that has never run poisons the CUDA context of the process it happens in, and must
-not reach the rest of the suite or the other variant.  xfail(strict=False) until each has passed once on a GPU (a pass shows
+"""First executions, each in its OWN pytest process: the two kernel variants written after this round's GPU budget was spent
+-- ipplb_bins_build variant 2 (tests/variant_build_check.py) and the gather kernels' variant 2
+(tests/variant_gather_check.py) -- and the multi-rank parity tests on a layout whose z cut is off the middle
+(tests/loop_orb_z_check.py: the geometry of the PenningTrap run).  Why separate processes: a CUDA
+fault in code that has never run poisons the CUDA context of the process it happens in, and must not reach the rest of
+the suite or the other checks.  xfail(strict=False) until each has passed once on a GPU (a pass shows
 as XPASS); both variants are opt-in, the defaults are the verified kernels."""
 import os
 import subprocess
@@ -16,7 +18,7 @@ pytestmark = [pytest.mark.gpu,
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("check", ["variant_build_check.py", "variant_gather_check.py"])
+@pytest.mark.parametrize("check", ["variant_build_check.py", "variant_gather_check.py", "loop_orb_z_check.py"])
 def test_kernel_variant_in_its_own_process(check):
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", check), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"],
                          cwd=ROOT, capture_output=True, text=True, timeout=first_run_timeout(150))
