@@ -23,3 +23,9 @@ def test_update_z_cut_off_the_middle():
 
 def test_fused_step_and_peer_migration_z_cut_off_the_middle():
     T.test_loop_fused_step_and_peer_migration_vs_oracle(8, "orb_z")
+
+
+def test_fused_step_with_the_penning_push_z_cut_off_the_middle():
+    """the PenningTrap kicks in the multi-rank fused step (the generic kernel variant with the ownership test): the one
+    combination of push and decomposition that only the faulted 8-GPU run of this round had executed"""
+    T.test_loop_fused_step_and_peer_migration_vs_oracle(8, "orb_z", push_kind="penning")

@@ -158,9 +158,10 @@ def test_loop_update_vs_oracle(world, kind):
 
 
 @pytest.mark.parametrize("world,kind", LAYOUTS)
-def test_loop_fused_step_and_peer_migration_vs_oracle(world, kind):
+def test_loop_fused_step_and_peer_migration_vs_oracle(world, kind, push_kind="leapfrog"):
     """The multi-GPU step of bench.py / the facade (fillHalo(E), fused step with ownership test, peer-memory migration,
-    accumulateHalo(rho)) on in-process ranks against the oracle's all-ranks step, four steps"""
+    accumulateHalo(rho)) on in-process ranks against the oracle's all-ranks step, four steps.  (push_kind "penning": the
+    PenningTrap kicks instead of the leapfrog ones, tests/loop_orb_z_check.py.)"""
     import torch
     job = make_job(world, kind)
     ib = job.ib
@@ -186,7 +187,8 @@ def test_loop_fused_step_and_peer_migration_vs_oracle(world, kind):
             ef.append(torch.from_numpy(ef_o[r].copy()).to(dev))
             rho.append(job.ctxs[r].field(job.meshes[r]))
         job.loop.migrate_connect(max(n // 2, 1024))
-        push = ib.leapfrog_push(dt)
+        push = ib.leapfrog_push(dt) if push_kind == "leapfrog" else ib.penning_push(dt, origin, tuple(job.Lg))
+        pp = oracle.penning_params(origin, tuple(job.Lg), dt) if push_kind == "penning" else None
         for it in range(4):
             # ---- oracle, all ranks: fillHalo(E); gather; kick, kick, drift; update (BC + migrate); scatter; accumulateHalo
             oracle.halo_full(ng, boxes, ef_o, 3, "fill")
@@ -195,7 +197,13 @@ def test_loop_fused_step_and_peer_migration_vs_oracle(world, kind):
                 nn = len(p["x"])
                 E = [np.zeros(nn) for _ in range(3)]
                 oracle.gather_cic(job.meshes_o[r], p["x"], p["y"], p["z"], ef_o[r], E)
+                if pp is not None:      # PenningTrapManager.h:313-333 (closing kick of the last step), :256-272
+                    Rl, Pl = [p[k] for k in "xyz"], [p[k] for k in ("px", "py", "pz")]
+                    oracle.penning_kick(2, pp, Rl, Pl, E)
+                    oracle.penning_kick(1, pp, Rl, Pl, E)
                 for d, k in enumerate(("px", "py", "pz")):
+                    if pp is not None:
+                        break
                     oracle.kick(p[k], E[d], 0.5 * dt)
                     oracle.kick(p[k], E[d], 0.5 * dt)
                 for kx, kp in zip("xyz", ("px", "py", "pz")):
