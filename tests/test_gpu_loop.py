@@ -201,11 +201,10 @@ def test_loop_fused_step_and_peer_migration_vs_oracle(world, kind, push_kind="le
                     Rl, Pl = [p[k] for k in "xyz"], [p[k] for k in ("px", "py", "pz")]
                     oracle.penning_kick(2, pp, Rl, Pl, E)
                     oracle.penning_kick(1, pp, Rl, Pl, E)
-                for d, k in enumerate(("px", "py", "pz")):
-                    if pp is not None:
-                        break
-                    oracle.kick(p[k], E[d], 0.5 * dt)
-                    oracle.kick(p[k], E[d], 0.5 * dt)
+                else:
+                    for d, k in enumerate(("px", "py", "pz")):
+                        oracle.kick(p[k], E[d], 0.5 * dt)
+                        oracle.kick(p[k], E[d], 0.5 * dt)
                 for kx, kp in zip("xyz", ("px", "py", "pz")):
                     oracle.drift(p[kx], p[kp], dt)
             lo = [0 * h[d] + origin[d] for d in range(3)]
