@@ -467,7 +467,7 @@ def main():
             extras = {"error": f"{type(e).__name__}: {e}"[:400]}
         out["extras"] = extras
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)      # on its way before any tear-down: a stuck destroy must not cost the line
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
