@@ -189,7 +189,7 @@ def main():
         del base, work
         torch.cuda.empty_cache()
     out["seconds"] = time.perf_counter() - t_start
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     ctx.close()
 
 
