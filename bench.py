@@ -193,12 +193,16 @@ def _run_sub(cmd, env, limit_s):
         so, se = p.communicate()
         return None, f"no result within {limit_s:.0f} s (process group killed); stderr tail: {se[-300:]}"
     line = next((ln for ln in reversed(so.splitlines()) if ln.startswith("{")), None)
-    if p.returncode != 0 or line is None:
-        return None, f"rc {p.returncode}, {'no JSON line' if line is None else 'JSON line present'}; stderr tail: {se[-400:]}"
+    if line is None:
+        return None, f"rc {p.returncode}, no JSON line; stderr tail: {se[-400:]}"
     try:
-        return json.loads(line), None
+        d = json.loads(line)
     except ValueError as e:
-        return None, f"unparsable JSON line: {e}"
+        return None, f"rc {p.returncode}, unparsable JSON line: {e}"
+    if p.returncode != 0:   # the line is printed when the measurement is complete: a non-zero exit after it is the tear-down's
+        d["exit_code_after_the_line"] = p.returncode
+        d["stderr_tail"] = se[-300:]
+    return d, None
 
 
 def _sub_env(port_shift):
@@ -212,7 +216,7 @@ def _sub_env(port_shift):
 
 def _brief(d):
     b = {k: d[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "kernels_ms", "solve_ms",
-                           "parity", "gpu_launches", "step_roofline", "run") if k in d}
+                           "parity", "gpu_launches", "step_roofline", "run", "exit_code_after_the_line", "stderr_tail") if k in d}
     r = d.get("roofline") or {}
     b["roofline"] = {k: r.get(k) for k in ("kernel", "frac", "achieved", "peak", "unit", "ms_per_launch")}
     b["config"] = d.get("config")

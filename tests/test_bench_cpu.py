@@ -75,6 +75,9 @@ if mode == "job":      # a multi-rank sub-job: its own rendezvous on the shifted
                           "ms_per_step": 1.0, "roofline": {"kernel": "k", "frac": 0.5, "ms_per_launch": 0.9, "junk": 1},
                           "config": {"workload": "w"}, "clocks": {"dropped": True}}))
     dist.destroy_process_group()
+elif mode == "late_crash":      # the measurement is complete and printed, then the tear-down fails
+    print(json.dumps({"metric": "m", "value": 7.0}), flush=True)
+    sys.exit(5)
 elif mode == "crash":
     sys.stderr.write("boom\n")
     sys.exit(3)
@@ -133,10 +136,11 @@ def test_extras_leg_single_process(tmp_path):
     import bench
     (tmp_path / "child.py").write_text(_CHILD)
     child = str(tmp_path / "child.py")
-    ex = bench.extras_leg(None, 1, 0, 0, None, jobs=[("bad", [sys.executable, child, "crash"], 30)],
+    ex = bench.extras_leg(None, 1, 0, 0, None, jobs=[("bad", [sys.executable, child, "crash"], 30), ("late", [sys.executable, child, "late_crash"], 30)],
                           micro_cmd=[sys.executable, child, "micro"], micro_limit=30,
                           variant_cmds=[("va", [sys.executable, child, "variant", "a"], 30)])
     assert "rc 3" in ex["bad"]["error"] and ex["micro"]["rows"][0]["ppc"] == 8 and "replicas" not in ex["micro"]
+    assert ex["late"]["value"] == 7.0 and ex["late"]["exit_code_after_the_line"] == 5      # a complete measurement is kept
     assert ex["va"]["part"] == "a"
 
 
